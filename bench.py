@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the polynomial-ring hot path on B200 (contract in the task statement, §④).
+
+Default workload (BASELINE.json metric "FHEW/TFHE bootstraps/sec ...; NTT GB/s vs HBM roofline"):
+  step  = one batch of FHEW NAND gate bootstraps (Fhew::op, scheme/fhew/src/fhew.rs:31-39) at the reference's own
+          test parameter set FHEW-T (scheme/fhew/src/fhew/boolean.rs:225-239), `--batch` gates per GPU (default 16384),
+          keys resident on the device, synthetic uniformly random key material / ciphertexts (timing does not depend
+          on the values; parity is covered by tests/ and by the bit-exact sample check in the cpu_baseline leg).
+  value = gates/s over all ranks, inputs resident in HBM (device pointers, fhe_fhew_bootstrap_batch).
+  e2e   = the same through the host-slice C-ABI call fhe_fhew_bootstrap_batch_host (pinned host buffers, H2D + D2H
+          inside the timed region).
+  ntt   = BASELINE configs[1]: batched negacyclic NTT/iNTT sweep N = 2^10..2^16, 4096 polynomials, GB/s against the
+          measured HBM copy peak (MEASURED_PEAKS.json) — extra keys on the same JSON line.
+  --impl reference : the CPU restatement of the reference (oracle/liborc.so; the Rust reference cannot be built in
+          this image) on all host cores, same metric/config, bounded sample per step.
+Multi-GPU: one process per GPU (torchrun), batch sharded by ciphertext (weak scaling), no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fhew_nand_bootstraps_per_sec"
+UNIT = "bootstraps/s"
+FHEW_T_Q = 268409857  # first of two_adic_primes(28, 10) (boolean.rs:225-239)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_fhew_key(param, seed):
+    """Synthetic key material in the reference layout (uniform residues; bootstrapping.rs:92-99 shapes)."""
+    n, q = param.n, param.big_q
+    rng = np.random.default_rng(seed)
+    ksk_a = rng.integers(0, param.q_ks, size=(n * param.ks_d, param.n_s), dtype=np.uint64)
+    ksk_b = rng.integers(0, param.q_ks, size=(n * param.ks_d,), dtype=np.uint64)
+    brk = rng.integers(0, q, size=(param.n_s, 2 * param.rgsw_d, 2, n), dtype=np.uint64)
+    ak = rng.integers(0, q, size=(param.w + 1, param.rlwe_d, 2, n), dtype=np.uint64)
+    g, m = 5, 2 * n
+    ak_t = np.array([m - g] + [pow(g, v, m) for v in range(1, param.w + 1)], dtype=np.int64)
+    return ksk_a, ksk_b, brk, ak, ak_t
+
+
+def synth_cts(param, count, seed):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, param.big_q, size=(count, param.n + 1), dtype=np.uint64)
+
+
+def fhew_algorithmic_counts(param, steps_ext, steps_auto):
+    """Closed-form integer work of one bootstrap in the fused dataflow: butterflies and MACs."""
+    n, lg = param.n, param.log_n
+    bf = (n // 2) * lg
+    ext = steps_ext * ((2 * param.rgsw_d + 2) * bf)
+    aut = steps_auto * ((param.rlwe_d + 2) * bf)
+    mac = steps_ext * (2 * param.rgsw_d * 2 * n) + steps_auto * (param.rlwe_d * 2 * n)
+    return ext + aut, mac
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (port of the reference's algorithm and dataflow: u128 % modmul, 3 transforms per product,
+    coefficient-form keys) on all host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import orc
+    orc.build()
+    orc.lib()
+    cores = os.cpu_count() or 1
+    P = orc.fhew_testing_param()
+    K = orc.FhewKey(P, 0x5EED0001)
+    sample = max(cores, 2 * cores if args.ref_sample is None else args.ref_sample)
+    bits = np.random.default_rng(3).integers(0, 2, size=2 * sample).astype(np.int32)
+    cts = K.encrypt(bits, 3)
+    lin = (cts[:sample] + cts[sample:]) % np.uint64(P.big_q)
+    for _ in range(args.warmup_ref):
+        K.op([1, 1, 1, 0], lin[:cores], threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = K.op([1, 1, 1, 0], lin, threads=cores)
+    dt = time.perf_counter() - t0
+    assert (K.decrypt(out) == 1 - (bits[:sample] & bits[sample:])).all()
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 (u128 % modmul)", "data": "synthetic",
+            "config": {"workload": "FHEW NAND gate bootstrap, FHEW-T (boolean.rs:225-239): N=512 Q=268409857 d=4 n_s=100 w=10",
+                       "batch_per_step": sample, "note": "CPU restatement of the reference (Rust toolchain absent); bounded sample"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d gates/step x %d steps" % (sample, args.steps)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def ntt_sweep(pkg, ctx, torch, hbm_peak, reps, log_ns, batch):
+    """BASELINE configs[1]: forward + inverse, in place, device resident; buffers rotate through a pool larger than L2."""
+    from learn_fhe_b200 import util
+    out = []
+    pool_bytes = 1 << 30
+    pool = torch.empty(pool_bytes // 8, dtype=torch.int64, device="cuda:%d" % ctx.device)
+    stream = torch.cuda.current_stream(ctx.device)
+    for log_n in log_ns:
+        for bits, w in ((64, 8), (32, 4)):
+            q = pkg.first_two_adic_prime(55 if bits == 64 else 28, log_n + 1)
+            n = 1 << log_n
+            words = batch * n
+            view_words = words if bits == 64 else words // 2  # int64 words backing the u32 view
+            nbuf = max(1, min(8, (pool_bytes // 8) // view_words))
+            bufs = [pool[i * view_words:(i + 1) * view_words] for i in range(nbuf)]
+            for b in bufs:  # valid residues: zero is fine for timing (data independent), but use a pattern
+                b.random_(0, 1 << 27)
+                if bits == 32:
+                    b.bitwise_and_((((1 << 27) - 1) << 32) | ((1 << 27) - 1))
+            name_f = "fhe_ntt_fwd_u64" if bits == 64 else "fhe_ntt_fwd_u32"
+            name_i = "fhe_ntt_inv_u64" if bits == 64 else "fhe_ntt_inv_u32"
+            res = {}
+            for name, key in ((name_f, "fwd"), (name_i, "inv")):
+                for i in range(3):
+                    ctx.call(name, q, log_n, batch, pkg.dptr(bufs[i % nbuf]))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                stream.synchronize()
+                e0.record(stream)
+                for i in range(reps):
+                    ctx.call(name, q, log_n, batch, pkg.dptr(bufs[i % nbuf]))
+                e1.record(stream)
+                e1.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                gbs = 2.0 * words * w / (ms * 1e-3) / 1e9
+                res[key] = {"ms": ms, "gbs": gbs, "frac": gbs / hbm_peak}
+            out.append({"log_n": log_n, "word_bits": bits, "batch": batch, "q": q, "buffers_rotated": nbuf,
+                        "fwd_gbs": round(res["fwd"]["gbs"], 1), "inv_gbs": round(res["inv"]["gbs"], 1),
+                        "fwd_frac_hbm": round(res["fwd"]["frac"], 4), "inv_frac_hbm": round(res["inv"]["frac"], 4),
+                        "fwd_ms": round(res["fwd"]["ms"], 4), "inv_ms": round(res["inv"]["ms"], 4)})
+    del pool
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="gate bootstraps per GPU per step")
+    ap.add_argument("--ref-sample", type=int, default=None, help="gates per step of the reference arm (default 2 x cores)")
+    ap.add_argument("--no-ntt", action="store_true", help="skip the NTT sweep leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ntt-reps", type=int, default=20)
+    args = ap.parse_args()
+    args.warmup_ref = max(1, min(args.warmup, 1))
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import _pkg
+    pkg = _pkg.load_package()
+    from learn_fhe_b200 import fhew
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    hbm_peak, peak_src, peak_json = peaks()
+    ctx = pkg.Context(local)
+    ctx.use_torch_stream()
+    stream = torch.cuda.current_stream(local)
+
+    param = fhew.single_key_testing_param(FHEW_T_Q)
+    # keys: generated on rank 0, uploaded + transformed there, then broadcast once over NCCL
+    key_np = synth_fhew_key(param, 0x5EED0000)
+    if rank == 0:
+        bk = fhew.BootstrappingKey(ctx, param, *key_np)
+    else:  # placeholder of the right shape; contents arrive by broadcast
+        bk = fhew.BootstrappingKey(ctx, param, *[np.zeros_like(x) if i < 4 else x for i, x in enumerate(key_np)])
+    if world > 1:
+        bk.broadcast(dist, root=0)
+    table = [1, 1, 1, 0]
+    f_np = fhew.gate_poly(param, table)
+    post = fhew.big_q_by_8(param)
+    f_dev = pkg.to_dev(f_np, local)
+    B = args.batch
+    ct_words = B * (param.n + 1)
+    # rotate over enough distinct input/output sets to exceed L2 (126 MB)
+    nset = max(2, int(np.ceil(160e6 / (2 * ct_words * 8))))
+    ins = [pkg.to_dev(synth_cts(param, B, 1000 * rank + i), local) for i in range(nset)]
+    outs = [torch.empty_like(ins[0]) for _ in range(nset)]
+
+    def step(i):
+        fhew.Bootstrapping.bootstrap_dev(bk, f_dev, ins[i % nset], outs[i % nset], post_add=post)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ker_evs = []
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    launches = ctx.launches - l0
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # dominant kernel timed alone on its stream (blind rotation): live CUDA events around the kernel launch only
+    kt = bk.time_kernels(f_dev, ins[0], outs[0], post, reps=max(2, args.steps))
+
+    # e2e: host-slice C ABI with pinned host buffers
+    h_in = torch.empty((B, param.n + 1), dtype=torch.int64).pin_memory()
+    h_out = torch.empty((B, param.n + 1), dtype=torch.int64).pin_memory()
+    h_in.numpy().view(np.uint64)[:] = synth_cts(param, B, 77 + rank)
+    h_f = torch.from_numpy(f_np.view(np.int64)).pin_memory()
+
+    def step_host():
+        ctx.call("fhe_fhew_bootstrap_batch_host", bk.h, pkg.hptr(h_f.numpy()), post, B, pkg.hptr(h_in.numpy()), pkg.hptr(h_out.numpy()))
+
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / float(t.item())
+    # device-path outputs must equal host-path outputs on the same inputs (consistency, cheap)
+    chk_in = pkg.to_dev(h_in.numpy().view(np.uint64)[:64].copy(), local)
+    chk_out = torch.empty_like(chk_in)
+    fhew.Bootstrapping.bootstrap_dev(bk, f_dev, chk_in, chk_out, post_add=post)
+    torch.cuda.synchronize()
+    assert np.array_equal(pkg.to_host(chk_out), h_out.numpy().view(np.uint64)[:64]), "device and host paths disagree"
+    if world > 1:  # every rank must hold rank 0's key: same probe input -> same output everywhere
+        probe = pkg.to_dev(synth_cts(param, 8, 4242), local)
+        pout = torch.empty_like(probe)
+        fhew.Bootstrapping.bootstrap_dev(bk, f_dev, probe, pout, post_add=post)
+        torch.cuda.synchronize()
+        gathered = [torch.empty_like(pout) for _ in range(world)]
+        dist.all_gather(gathered, pout)
+        assert all(torch.equal(g, gathered[0]) for g in gathered), "ranks disagree after key broadcast"
+
+    ntt = None
+    if rank == 0 and not args.no_ntt:
+        ntt = ntt_sweep(pkg, ctx, torch, hbm_peak, args.ntt_reps, list(range(10, 17)), 4096)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import orc  # cpu_baseline leg: the oracle as the timed CPU port + bit-exact checker of a GPU sample
+        orc.build()
+        cores = os.cpu_count() or 1
+        P = orc.fhew_testing_param()
+        K = orc.FhewKey.from_arrays(P, *key_np) if hasattr(orc.FhewKey, "from_arrays") else None
+        sample = 2 * cores
+        if K is not None:
+            lin = h_in.numpy().view(np.uint64)[:sample].copy()
+            t0 = time.perf_counter()
+            ref = K.op(table, lin, threads=cores)
+            dt = time.perf_counter() - t0
+            assert np.array_equal(ref, h_out.numpy().view(np.uint64)[:sample]), "GPU output differs from the oracle"
+            checked = True
+        else:
+            K = orc.FhewKey(P, 0x5EED0001)
+            bits = np.random.default_rng(3).integers(0, 2, size=2 * sample).astype(np.int32)
+            cts = K.encrypt(bits, 3)
+            lin = (cts[:sample] + cts[sample:]) % np.uint64(P.big_q)
+            t0 = time.perf_counter()
+            K.op(table, lin, threads=cores)
+            dt = time.perf_counter() - t0
+            checked = False
+        cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d gates of the same workload on %d threads (%.1f s)%s" % (sample, cores, dt, ", GPU outputs bit-identical" if checked else "")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 (Q < 2^30 residues, u64 MAC accumulators)", "data": "synthetic",
+                "config": {"workload": "FHEW NAND gate bootstrap (Fhew::op), FHEW-T (boolean.rs:225-239): N=512 Q=268409857 "
+                                       "RGSW/RLWE B=2^7 d=4, n_s=100 q_ks=2^16, w=10",
+                           "batch_per_gpu": B, "global_batch": B * world, "sharding": "by ciphertext, keys replicated (NCCL broadcast once)",
+                           "l2": "inputs rotate over %d distinct in/out sets (%.0f MB) > L2" % (nset, nset * 2 * ct_words * 8 / 1e6)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ct_words * 8 + param.n * 8),
+                        "d2h_bytes_per_step": int(ct_words * 8)},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": kt["roofline"], "kernels": kt["kernels"], "cpu_baseline": cpu, "peak_source": peak_src}
+        if ntt is not None:
+            line["ntt"] = ntt
+            best = max(ntt, key=lambda r: (r["log_n"], r["word_bits"]))
+            line["roofline_ntt"] = {"bound": "hbm", "achieved": best["fwd_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": best["fwd_frac_hbm"], "traffic": None,
+                                    "kernel": "ntt fwd u64 N=2^%d batch 4096" % best["log_n"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

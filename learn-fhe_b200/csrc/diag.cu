@@ -1,0 +1,82 @@
+// Pipe-peak microbenchmarks: measured INT32 multiply throughput of the device the context
+// runs on.  The modular-NTT kernels are bound by the fma pipe's integer multiply rate (IMAD / IMAD.HI / IMAD.WIDE),
+// for which MEASURED_PEAKS.json carries no figure; bench.py divides the blind-rotation kernel's algorithmic
+// multiply count by these numbers.
+#include "ctx.cuh"
+
+namespace fhe {
+
+// mode 0: 32-bit IMAD (x = x * a + b); mode 1: IMAD.HI (__umulhi); mode 2: IMAD.WIDE (u32 x u32 + u64)
+template <int MODE>
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t a, uint32_t b, int iters, uint32_t* __restrict__ sink) {
+    constexpr int ILP = 8;
+    uint32_t x[ILP];
+    uint64_t w[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+        x[j] = threadIdx.x * 2654435761u + j * 40503u + blockIdx.x;
+        w[j] = x[j];
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int j = 0; j < ILP; ++j) {
+                if (MODE == 0)
+                    x[j] = x[j] * a + b;
+                else if (MODE == 1)
+                    x[j] = __umulhi(x[j], a) + b;
+                else
+                    w[j] = (uint64_t)(uint32_t)w[j] * a + w[j];
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc ^= x[j] ^ (uint32_t)w[j] ^ (uint32_t)(w[j] >> 32);
+    if (acc == 0x12345u) sink[0] = acc;  // keeps the chains alive without a store in the common case
+}
+
+template <int MODE>
+static fhe_status run_peak(fhe_ctx* ctx, double* tops) {
+    const int iters = 4096;
+    const unsigned grid = (unsigned)ctx->sm_count * 8;
+    void* sink;
+    FHE_CHECK(ensure_scratch(ctx, 256, &sink));
+    cudaEvent_t e0, e1;
+    FHE_CUDA(ctx, cudaEventCreate(&e0));
+    FHE_CUDA(ctx, cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        FHE_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        imad_peak_kernel<MODE><<<grid, 256, 0, ctx->stream>>>(0x9E3779B1u, 12345u, iters, (uint32_t*)sink);
+        FHE_CHECK(after_launch(ctx, "imad_peak_kernel"));
+        FHE_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        FHE_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        FHE_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        double ops = (double)grid * 256 * (double)iters * 8 * 8;
+        double t = ops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t > best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tops = best;
+    return FHE_OK;
+}
+
+}  // namespace fhe
+
+using namespace fhe;
+
+extern "C" fhe_status fhe_diag_int32_peak(fhe_ctx* ctx, double* imad_tops, double* imad_hi_tops, double* imad_wide_tops) {
+    if (!ctx) return FHE_EINVAL;
+    double a = 0, b = 0, c = 0;
+    FHE_CHECK(run_peak<0>(ctx, &a));
+    FHE_CHECK(run_peak<1>(ctx, &b));
+    FHE_CHECK(run_peak<2>(ctx, &c));
+    if (imad_tops) *imad_tops = a;
+    if (imad_hi_tops) *imad_hi_tops = b;
+    if (imad_wide_tops) *imad_wide_tops = c;
+    return FHE_OK;
+}

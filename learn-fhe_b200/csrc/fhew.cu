@@ -1,0 +1,420 @@
+// FHEW / LMKCDEY gate bootstrapping on sm_100a (K8-K12 of SURVEY.md §2).
+//
+//   fhew_prologue_kernel      mod_switch -> Lwe::key_switch -> mod_switch_odd   (lwe.rs:90-99,151-160)
+//   fhew_blind_rotate_kernel  persistent CTA per ciphertext: LMKCDEY schedule built in shared memory, accumulator
+//                             (2N words) and digit polynomials resident in shared memory across all ~208 steps; per
+//                             step: decompose -> 2d (or d) forward NTT -> MAC against pre-transformed key rows
+//                             streamed from L2 -> 2 inverse NTT -> (+ b(X^t)); epilogue sample_extract (+ Q/8)
+//                             (bootstrapping.rs:149-231, rgsw.rs:116-128, rlwe.rs:177-202, fhew.rs:31-39)
+//   fhew_step_kernel          one external product / automorphism per accumulator (parity tests, util-level callers)
+// All per-thread logic lives in fhew_core.cuh (shared with tests/hostsim).
+#include <algorithm>
+#include <vector>
+
+#include "ctx.cuh"
+#include "fhew_core.cuh"
+
+struct fhe_fhew_key {
+    fhe_fhew_param param;
+    fhe::FhewDev P;
+    fhe::LweKsDev K;
+    uint32_t kmax = 0;
+    void* d_brk = nullptr;
+    void* d_ak = nullptr;
+    void* d_ksk = nullptr;
+    void* d_dlog = nullptr;
+    int* d_err = nullptr;
+    size_t brk_bytes = 0, ak_bytes = 0, ksk_bytes = 0;
+};
+
+namespace fhe {
+
+static constexpr int BR_THREADS = 128;
+static constexpr int PRO_G = 4;
+static constexpr int PRO_THREADS = 128;
+
+__global__ void fhew_pack_rows_kernel(const uint32_t* __restrict__ ab /* [rows][2][N] eval form */, uint2* __restrict__ out, uint32_t n,
+                                      unsigned long long rows) {
+    unsigned long long total = rows * n;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long r = i / n;
+        uint32_t c = (uint32_t)(i - r * n);
+        out[i] = make_uint2(ab[(r * 2) * n + c], ab[(r * 2 + 1) * n + c]);
+    }
+}
+
+template <typename CT, typename OT>
+__global__ void __launch_bounds__(PRO_THREADS) fhew_prologue_kernel(LweKsDev K, const CT* __restrict__ ct_in, OT* __restrict__ out,
+                                                                      unsigned long long count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* digs = reinterpret_cast<uint32_t*>(smem_raw);
+    const uint32_t len = K.n * K.ks_dec.d;
+    uint32_t* b_in = digs + (size_t)PRO_G * len;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    const unsigned long long groups = (count + PRO_G - 1) / PRO_G;
+    for (unsigned long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+        const unsigned long long base = grp * PRO_G;
+        for (int g = 0; g < PRO_G; ++g) {
+            unsigned long long c = base + g < count ? base + g : count - 1;  // clamp (duplicates are not stored)
+            lwe_phase_digits(K, ct_in + c * (K.n + 1), digs + (size_t)g * len, b_in + g, tid, nthr);
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j <= K.n_s; j += nthr) {
+            uint32_t acc[PRO_G];
+            lwe_phase_gemv<PRO_G>(K, digs, j, acc);
+            for (int g = 0; g < PRO_G; ++g)
+                if (base + g < count) out[(base + g) * (K.n_s + 1) + j] = (OT)lwe_phase_out(K, acc[g], j, b_in[g]);
+        }
+        __syncthreads();
+    }
+}
+
+// mode 0: out = LWE ciphertext [N+1] (sample_extract + post_add); mode 1: out = accumulator [2][N]
+template <typename FT, typename OT>
+__global__ void __launch_bounds__(BR_THREADS) fhew_blind_rotate_kernel(FhewDev P, uint32_t kmax, const FT* __restrict__ f,
+                                                                          const uint32_t* __restrict__ ct2n, uint32_t post_add,
+                                                                          unsigned long long count, OT* __restrict__ out, int mode,
+                                                                          int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
+    const uint32_t n = 1u << P.log_n;
+    uint16_t* steps = reinterpret_cast<uint16_t*>(smem + (size_t)(2 + kmax) * n);
+    const uint32_t max_steps = P.n_s + n + 2;
+    uint32_t* a2n = reinterpret_cast<uint32_t*>(steps + ((max_steps + 1) & ~1u));
+    __shared__ uint32_t ns_sh;
+    // schedule scratch aliases the (not yet used) digit region
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(fhew_dig(smem, n, 0));
+    uint16_t* sorted = cnt + n;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    auto run = [&](auto phase) {
+        phase(tid, nthr);
+        __syncthreads();
+    };
+    for (unsigned long long ct = blockIdx.x; ct < count; ct += gridDim.x) {
+        const uint32_t* src = ct2n + ct * (P.n_s + 1);
+        for (uint32_t j = tid; j <= P.n_s; j += nthr) a2n[j] = src[j];
+        __syncthreads();
+        if (tid == 0) ns_sh = build_schedule(n, P.n_s, P.w, a2n, P.dlog, cnt, sorted, steps);
+        fhew_phase_init(P, smem, f, a2n[P.n_s], tid, nthr);
+        __syncthreads();
+        uint32_t ns = ns_sh;
+        if (ns == 0xFFFFFFFFu) {  // reference: unreachable!() (bootstrapping.rs:221)
+            if (tid == 0) atomicExch(err, 1);
+            ns = 0;
+        }
+        for (uint32_t s = 0; s < ns; ++s) fhew_step(P, smem, steps[s], run);
+        if (mode == 0) {
+            fhew_phase_extract(P, smem, post_add, out + ct * (n + 1), tid, nthr);
+        } else {
+            OT* o = out + ct * 2ull * n;
+            for (uint32_t i = tid; i < n; i += nthr) {
+                o[i] = (OT)smem[swz<uint32_t>(i)];
+                o[n + i] = (OT)smem[n + swz<uint32_t>(i)];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename IT, typename OT>
+__global__ void __launch_bounds__(BR_THREADS) fhew_step_kernel(FhewDev P, uint32_t kmax, uint32_t kind_flag, const uint32_t* __restrict__ idx,
+                                                                 const IT* __restrict__ acc_in, OT* __restrict__ acc_out, unsigned long long count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
+    const uint32_t n = 1u << P.log_n;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    auto run = [&](auto phase) {
+        phase(tid, nthr);
+        __syncthreads();
+    };
+    for (unsigned long long c = blockIdx.x; c < count; c += gridDim.x) {
+        const IT* in = acc_in + c * 2ull * n;
+        for (uint32_t i = tid; i < n; i += nthr) {
+            smem[swz<uint32_t>(i)] = (uint32_t)in[i];
+            smem[n + swz<uint32_t>(i)] = (uint32_t)in[n + i];
+        }
+        __syncthreads();
+        fhew_step(P, smem, kind_flag | idx[c], run);
+        OT* o = acc_out + c * 2ull * n;
+        for (uint32_t i = tid; i < n; i += nthr) {
+            o[i] = (OT)smem[swz<uint32_t>(i)];
+            o[n + i] = (OT)smem[n + swz<uint32_t>(i)];
+        }
+        __syncthreads();
+    }
+}
+
+static size_t br_smem_bytes(const fhe_fhew_key* key) {
+    const uint32_t n = 1u << key->P.log_n;
+    const uint32_t max_steps = key->P.n_s + n + 2;
+    return (size_t)(2 + key->kmax) * n * 4 + (size_t)((max_steps + 1) & ~1u) * 2 + (size_t)(key->P.n_s + 1) * 4 + 16;
+}
+
+template <typename K>
+static fhe_status persistent_grid(fhe_ctx* ctx, K kern, int threads, size_t smem, unsigned long long items, unsigned* grid) {
+    FHE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    int occ = 0;
+    FHE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) return fail(ctx, FHE_EUNSUPPORTED, "kernel does not fit on an SM (smem %zu bytes)", smem);
+    *grid = (unsigned)std::min<unsigned long long>(items, (unsigned long long)ctx->sm_count * occ);
+    return FHE_OK;
+}
+
+static fhe_status upload_rows_eval(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* rows_ab, size_t rows, void** d_out, size_t* bytes) {
+    const uint32_t n = 1u << key->P.log_n;
+    const size_t words = rows * 2 * n;
+    std::vector<uint32_t> h(words);
+    const uint64_t q = key->param.big_q;
+    for (size_t i = 0; i < words; ++i) {
+        FHE_REQUIRE(ctx, rows_ab[i] < q, "key coefficient out of range");
+        h[i] = (uint32_t)rows_ab[i];
+    }
+    uint32_t* d_tmp = nullptr;
+    FHE_CUDA(ctx, cudaMalloc(&d_tmp, words * 4));
+    cudaError_t e = cudaMemcpyAsync(d_tmp, h.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    fhe_status st = e == cudaSuccess ? FHE_OK : fail(ctx, FHE_ECUDA, "key upload: %s", cudaGetErrorString(e));
+    if (st == FHE_OK) st = launch_ntt_u32(ctx, (uint32_t)q, (unsigned)key->P.log_n, rows * 2, d_tmp, true);
+    if (st == FHE_OK) {
+        *bytes = rows * n * sizeof(uint2);
+        if (cudaMalloc(d_out, *bytes) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "key alloc");
+    }
+    if (st == FHE_OK) {
+        unsigned long long total = (unsigned long long)rows * n;
+        unsigned grid = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)ctx->sm_count * 8);
+        fhew_pack_rows_kernel<<<grid, 256, 0, ctx->stream>>>(d_tmp, (uint2*)*d_out, n, rows);
+        st = after_launch(ctx, "fhew_pack_rows_kernel");
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_tmp);
+    return st;
+}
+
+static fhe_status run_prologue(fhe_ctx* ctx, const fhe_fhew_key* key, size_t count, const uint64_t* d_ct_in, bool sw_in, bool sw_out,
+                               uint32_t* d_out32, uint64_t* d_out64) {
+    LweKsDev K = key->K;
+    K.switch_in = sw_in;
+    K.switch_out = sw_out;
+    const size_t smem = ((size_t)PRO_G * K.n * K.ks_dec.d + PRO_G) * 4;
+    unsigned grid;
+    unsigned long long groups = (count + PRO_G - 1) / PRO_G;
+    if (d_out32) {
+        auto kern = fhew_prologue_kernel<uint64_t, uint32_t>;
+        FHE_CHECK(persistent_grid(ctx, kern, PRO_THREADS, smem, groups, &grid));
+        kern<<<grid, PRO_THREADS, smem, ctx->stream>>>(K, d_ct_in, d_out32, count);
+    } else {
+        auto kern = fhew_prologue_kernel<uint64_t, uint64_t>;
+        FHE_CHECK(persistent_grid(ctx, kern, PRO_THREADS, smem, groups, &grid));
+        kern<<<grid, PRO_THREADS, smem, ctx->stream>>>(K, d_ct_in, d_out64, count);
+    }
+    return after_launch(ctx, "fhew_prologue_kernel");
+}
+
+template <typename OT>
+static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n, uint32_t post_add,
+                                   size_t count, OT* d_out, int mode) {
+    const size_t smem = br_smem_bytes(key);
+    auto kern = fhew_blind_rotate_kernel<uint64_t, OT>;
+    unsigned grid;
+    FHE_CHECK(persistent_grid(ctx, kern, BR_THREADS, smem, count, &grid));
+    FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
+    kern<<<grid, BR_THREADS, smem, ctx->stream>>>(key->P, key->kmax, d_f, d_ct2n, post_add, count, d_out, mode, key->d_err);
+    return after_launch(ctx, "fhew_blind_rotate_kernel");
+}
+
+static fhe_status check_err_flag(fhe_ctx* ctx, const fhe_fhew_key* key) {
+    int h = 0;
+    FHE_CUDA(ctx, cudaMemcpyAsync(&h, key->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h) return fail(ctx, FHE_EINVAL, "blind rotation met an even non-zero exponent (reference: unreachable!, bootstrapping.rs:221)");
+    return FHE_OK;
+}
+
+}  // namespace fhe
+
+using namespace fhe;
+
+extern "C" {
+
+fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uint64_t* ksk_a, const uint64_t* ksk_b, const uint64_t* brk,
+                               const uint64_t* ak, const int64_t* ak_t, fhe_fhew_key** out) {
+    if (!ctx || !pp || !out) return FHE_EINVAL;
+    *out = nullptr;
+    FHE_REQUIRE(ctx, ksk_a && ksk_b && brk && ak && ak_t, "null key pointer");
+    FHE_REQUIRE(ctx, pp->log_n >= 2 && pp->log_n <= 11, "FHEW u32 path supports 4 <= N <= 2048 (got log_n = %u)", pp->log_n);
+    FHE_REQUIRE(ctx, pp->big_q < (1ull << 30), "FHEW u32 path needs Q < 2^30 (54/55-bit multi-key parameters are a later row)");
+    FHE_REQUIRE(ctx, pp->q_ks >= 2 && pp->q_ks <= (1ull << 32) && (pp->q_ks & (pp->q_ks - 1)) == 0, "q_ks must be a power of two <= 2^32");
+    FHE_REQUIRE(ctx, pp->w >= 1 && pp->w < 40, "window w must be in [1, 39]");
+    FHE_REQUIRE(ctx, pp->rgsw_d >= 1 && pp->rlwe_d >= 1 && pp->ks_d >= 1 && pp->rgsw_log_b >= 1 && pp->rlwe_log_b >= 1 && pp->ks_log_b >= 1,
+                "decomposor parameters must be positive");
+    FHE_REQUIRE(ctx, pp->rgsw_log_b * pp->rgsw_d <= 64 && pp->rlwe_log_b * pp->rlwe_d <= 64 && pp->ks_log_b * pp->ks_d <= 32,
+                "decomposor log_b * d too large");
+    FHE_REQUIRE(ctx, 2 * pp->rgsw_d <= 16, "2 * rgsw_d must be <= 16 (64-bit MAC accumulator bound)");
+    FHE_REQUIRE(ctx, pp->n_s >= 1 && pp->n_s < 32768, "n_s out of range");
+    const uint32_t n = 1u << pp->log_n;
+    const NttTable* t;
+    FHE_CHECK(get_ntt_table(ctx, pp->big_q, 32, n, &t));
+    fhe_fhew_key* key = new fhe_fhew_key();
+    key->param = *pp;
+    const uint64_t q = pp->big_q;
+    FhewDev& P = key->P;
+    P.m = make_mod<Mod32>(q);
+    P.log_n = (int)pp->log_n;
+    P.n_s = pp->n_s;
+    P.w = pp->w;
+    P.g_dec = make_decomp(q, pp->rgsw_log_b, pp->rgsw_d);
+    P.r_dec = make_decomp(q, pp->rlwe_log_b, pp->rlwe_d);
+    P.small_digits = (pp->rgsw_log_b * pp->rgsw_d <= 32 && pp->rlwe_log_b * pp->rlwe_d <= 32) ? 1 : 0;
+    P.tw = (const TwPair<uint32_t>*)t->d_fwd;
+    P.itw = (const TwPair<uint32_t>*)t->d_inv;
+    const uint64_t ninv = host_invmod(n % q, q);
+    P.ninv = make_twpair<uint32_t>(ninv, q);
+    P.wninv = make_twpair<uint32_t>(host_mulmod(t->h_inv[1], ninv, q), q);
+    for (unsigned v = 0; v <= pp->w; ++v) P.ak_t[v] = (uint32_t)(((ak_t[v] % (int64_t)(2 * n)) + 2 * n) % (2 * n));
+    key->kmax = std::max(2 * pp->rgsw_d, pp->rlwe_d);
+    fhe_status st = upload_rows_eval(ctx, key, brk, (size_t)pp->n_s * 2 * pp->rgsw_d, &key->d_brk, &key->brk_bytes);
+    if (st == FHE_OK) st = upload_rows_eval(ctx, key, ak, (size_t)(pp->w + 1) * pp->rlwe_d, &key->d_ak, &key->ak_bytes);
+    if (st == FHE_OK) {
+        std::vector<uint16_t> dlog(2 * n);
+        build_dlog_table(n, dlog.data());
+        if (cudaMalloc(&key->d_dlog, dlog.size() * 2) != cudaSuccess || cudaMalloc((void**)&key->d_err, sizeof(int)) != cudaSuccess ||
+            cudaMemcpy(key->d_dlog, dlog.data(), dlog.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess)
+            st = fail(ctx, FHE_ECUDA, "dlog upload failed");
+    }
+    if (st == FHE_OK) {
+        LweKsDev& K = key->K;
+        K.big_q = q;
+        K.n = n;
+        K.n_s = pp->n_s;
+        K.q_ks = pp->q_ks;
+        K.q_out = 2 * n;
+        K.ks_dec = make_decomp(pp->q_ks, pp->ks_log_b, pp->ks_d);
+        K.switch_in = K.switch_out = 1;
+        const size_t len = (size_t)n * pp->ks_d, ld = pp->n_s + 1;
+        std::vector<uint32_t> h(len * ld);
+        for (size_t idx = 0; idx < len && st == FHE_OK; ++idx) {
+            for (size_t j = 0; j < pp->n_s; ++j) h[idx * ld + j] = (uint32_t)ksk_a[idx * pp->n_s + j];
+            h[idx * ld + pp->n_s] = (uint32_t)ksk_b[idx];
+        }
+        key->ksk_bytes = h.size() * 4;
+        if (cudaMalloc(&key->d_ksk, key->ksk_bytes) != cudaSuccess ||
+            cudaMemcpy(key->d_ksk, h.data(), key->ksk_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            st = fail(ctx, FHE_ECUDA, "ksk upload failed");
+        K.ksk = (const uint32_t*)key->d_ksk;
+    }
+    if (st != FHE_OK) {
+        fhe_fhew_key_free(ctx, key);
+        return st;
+    }
+    P.brk = (const uint2*)key->d_brk;
+    P.ak = (const uint2*)key->d_ak;
+    P.dlog = (const uint16_t*)key->d_dlog;
+    *out = key;
+    return FHE_OK;
+}
+
+void fhe_fhew_key_free(fhe_ctx* ctx, fhe_fhew_key* key) {
+    if (!key) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (key->d_brk) cudaFree(key->d_brk);
+    if (key->d_ak) cudaFree(key->d_ak);
+    if (key->d_ksk) cudaFree(key->d_ksk);
+    if (key->d_dlog) cudaFree(key->d_dlog);
+    if (key->d_err) cudaFree(key->d_err);
+    delete key;
+}
+
+fhe_status fhe_fhew_prologue_batch(fhe_ctx* ctx, const fhe_fhew_key* key, size_t count, const uint64_t* d_ct_in, uint64_t* d_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    return run_prologue(ctx, key, count, d_ct_in, true, true, nullptr, d_out);
+}
+fhe_status fhe_lwe_key_switch_batch(fhe_ctx* ctx, const fhe_fhew_key* key, size_t count, const uint64_t* d_ct_in, uint64_t* d_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    return run_prologue(ctx, key, count, d_ct_in, false, false, nullptr, d_out);
+}
+
+static fhe_status fhew_step_api(fhe_ctx* ctx, const fhe_fhew_key* key, uint32_t flag, size_t count, const uint32_t* d_idx,
+                                const uint64_t* d_acc_in, uint64_t* d_acc_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    const uint32_t n = 1u << key->P.log_n;
+    const size_t smem = (size_t)(2 + key->kmax) * n * 4;
+    auto kern = fhew_step_kernel<uint64_t, uint64_t>;
+    unsigned grid;
+    FHE_CHECK(persistent_grid(ctx, kern, BR_THREADS, smem, count, &grid));
+    kern<<<grid, BR_THREADS, smem, ctx->stream>>>(key->P, key->kmax, flag, d_idx, d_acc_in, d_acc_out, count);
+    return after_launch(ctx, "fhew_step_kernel");
+}
+fhe_status fhe_fhew_external_product(fhe_ctx* ctx, const fhe_fhew_key* key, size_t count, const uint32_t* d_idx, const uint64_t* d_acc_in,
+                                     uint64_t* d_acc_out) {
+    return fhew_step_api(ctx, key, 0u, count, d_idx, d_acc_in, d_acc_out);
+}
+fhe_status fhe_fhew_automorphism(fhe_ctx* ctx, const fhe_fhew_key* key, size_t count, const uint32_t* d_idx, const uint64_t* d_acc_in,
+                                 uint64_t* d_acc_out) {
+    return fhew_step_api(ctx, key, FHEW_STEP_AUTO, count, d_idx, d_acc_in, d_acc_out);
+}
+
+fhe_status fhe_fhew_blind_rotate_batch(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, size_t count, const uint64_t* d_ct2n,
+                                       uint64_t* d_acc_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    // narrow the [count][n_s+1] u64 input to u32 through the prologue-free path: reuse scratch
+    void* scratch;
+    const size_t words = count * (key->P.n_s + 1);
+    FHE_CHECK(ensure_scratch(ctx, words * 4, &scratch));
+    std::vector<uint64_t> h(words);
+    FHE_CUDA(ctx, cudaMemcpyAsync(h.data(), d_ct2n, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> h32(words);
+    for (size_t i = 0; i < words; ++i) h32[i] = (uint32_t)h[i];
+    FHE_CUDA(ctx, cudaMemcpyAsync(scratch, h32.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FHE_CHECK(run_blind_rotate<uint64_t>(ctx, key, d_f, (const uint32_t*)scratch, 0, count, d_acc_out, 1));
+    return check_err_flag(ctx, key);
+}
+
+fhe_status fhe_fhew_bootstrap_batch(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, uint64_t post_add, size_t count,
+                                    const uint64_t* d_ct_in, uint64_t* d_ct_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_f && d_ct_in && d_ct_out, "null pointer");
+    FHE_REQUIRE(ctx, post_add < key->param.big_q, "post_add out of range");
+    void* scratch;
+    FHE_CHECK(ensure_scratch(ctx, count * (key->P.n_s + 1) * 4, &scratch));
+    FHE_CHECK(run_prologue(ctx, key, count, d_ct_in, true, true, (uint32_t*)scratch, nullptr));
+    return run_blind_rotate<uint64_t>(ctx, key, d_f, (const uint32_t*)scratch, (uint32_t)post_add, count, d_ct_out, 0);
+}
+
+fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* f, uint64_t post_add, size_t count,
+                                         const uint64_t* ct_in, uint64_t* ct_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, f && ct_in && ct_out, "null pointer");
+    const uint32_t n = 1u << key->P.log_n;
+    const size_t ct_bytes = count * (n + 1) * 8, f_bytes = (size_t)n * 8;
+    void *d_in, *d_out, *d_f;
+    FHE_CHECK(ensure_stage_d(ctx, 0, ct_bytes, &d_in));
+    FHE_CHECK(ensure_stage_d(ctx, 1, ct_bytes, &d_out));
+    FHE_CHECK(ensure_stage_d(ctx, 2, f_bytes, &d_f));
+    FHE_CUDA(ctx, cudaMemcpyAsync(d_in, ct_in, ct_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CUDA(ctx, cudaMemcpyAsync(d_f, f, f_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CHECK(fhe_fhew_bootstrap_batch(ctx, key, (const uint64_t*)d_f, post_add, count, (const uint64_t*)d_in, (uint64_t*)d_out));
+    FHE_CUDA(ctx, cudaMemcpyAsync(ct_out, d_out, ct_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_err_flag(ctx, key);  // synchronises the stream
+}
+
+// one-time distribution of the (already transformed) key buffers from `root` (no upstream analogue)
+fhe_status fhe_fhew_key_broadcast(fhe_ctx* ctx, fhe_fhew_key* key, void* nccl_comm, int root) {
+    if (!ctx || !key) return FHE_EINVAL;
+    FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_brk, key->brk_bytes));
+    FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ak, key->ak_bytes));
+    FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ksk, key->ksk_bytes));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FHE_OK;
+}
+size_t fhe_fhew_key_bytes(const fhe_fhew_key* key) { return key ? key->brk_bytes + key->ak_bytes + key->ksk_bytes : 0; }
+
+}  // extern "C"

@@ -95,6 +95,8 @@ def lib():
         L.orc_fhew_keygen.restype = C.c_void_p
         L.orc_fhew_key_free.argtypes = [C.c_void_p]
         L.orc_fhew_key_free.restype = None
+        L.orc_fhew_key_import.argtypes = [C.POINTER(FhewParamC), u64p, u64p, u64p, u64p, i64p]
+        L.orc_fhew_key_import.restype = C.c_void_p
         L.orc_fhew_key_export.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         L.orc_fhew_encrypt.argtypes = [C.c_void_p, i32p, C.c_size_t, C.c_uint64, u64p]
         L.orc_fhew_decrypt.argtypes = [C.c_void_p, u64p, C.c_size_t, i32p]
@@ -324,11 +326,18 @@ def fhew_testing_param():
 
 
 class FhewKey:
-    def __init__(self, param, seed):
+    def __init__(self, param, seed, _handle=None):
         self.param = param
-        self.h = lib().orc_fhew_keygen(C.byref(param), seed)
+        self.h = _handle if _handle is not None else lib().orc_fhew_keygen(C.byref(param), seed)
         if not self.h:
             _ck(-1)
+
+    @classmethod
+    def from_arrays(cls, param, ksk_a, ksk_b, brk, ak, ak_t):
+        """Public evaluation keys only (no secrets: encrypt/decrypt are unavailable); reference layout as in export()."""
+        h = lib().orc_fhew_key_import(C.byref(param), U(ksk_a).reshape(-1), U(ksk_b).reshape(-1), U(brk).reshape(-1),
+                                      U(ak).reshape(-1), np.ascontiguousarray(ak_t, dtype=np.int64))
+        return cls(param, 0, _handle=h)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -279,6 +279,46 @@ int orc_fhew_key_export(void* h, u64* ksk_a, u64* ksk_b, u64* brk, u64* ak, int6
         if (s) std::memcpy(s, K.s.data(), P.n_s * 8);
     })
 }
+// inverse of orc_fhew_key_export for the PUBLIC part (evaluation keys only; z and s stay empty): lets tests and
+// bench.py's checker run the oracle on arbitrary (e.g. synthetic uniformly random) key material.
+void* orc_fhew_key_import(const orc_fhew_param_c* c, const u64* ksk_a, const u64* ksk_b, const u64* brk, const u64* ak, const int64_t* ak_t) {
+    try {
+        FhewKey* K = new FhewKey();
+        K->param = to_param(*c);
+        const FhewParam& P = K->param;
+        const size_t n = P.n();
+        K->ksk.resize(n * P.ks_d);
+        for (size_t i = 0; i < K->ksk.size(); ++i) {
+            K->ksk[i].a.assign(ksk_a + i * P.n_s, ksk_a + (i + 1) * P.n_s);
+            K->ksk[i].b = ksk_b[i];
+        }
+        const size_t rg = 2 * P.rgsw_d;
+        K->brk.resize(P.n_s);
+        for (size_t j = 0; j < P.n_s; ++j) {
+            K->brk[j].resize(rg);
+            for (size_t r = 0; r < rg; ++r) {
+                const u64* base = brk + ((j * rg + r) * 2) * n;
+                K->brk[j][r].a.assign(base, base + n);
+                K->brk[j][r].b.assign(base + n, base + 2 * n);
+            }
+        }
+        K->ak.resize(P.w + 1);
+        K->ak_t.resize(P.w + 1);
+        for (size_t v = 0; v <= P.w; ++v) {
+            K->ak[v].resize(P.rlwe_d);
+            for (size_t r = 0; r < P.rlwe_d; ++r) {
+                const u64* base = ak + ((v * P.rlwe_d + r) * 2) * n;
+                K->ak[v][r].a.assign(base, base + n);
+                K->ak[v][r].b.assign(base + n, base + 2 * n);
+            }
+            K->ak_t[v] = ak_t[v];
+        }
+        return K;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 // ct layout: [a_0 .. a_{N-1}, b]
 static LweCt lwe_wrap(const u64* ct, size_t n) { return LweCt{Vec(ct, ct + n), ct[n]}; }
 static void lwe_unwrap(const LweCt& c, u64* out) {

@@ -1,0 +1,122 @@
+"""FHEW / LMKCDEY parity: every stage of Bootstrapping::bootstrap against the oracle, bit for bit (FHEW-T parameters,
+scheme/fhew/src/fhew/boolean.rs:225-239), plus the gate truth tables of boolean.rs:241-318."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bk(pkg, ctx, fhew_setup):
+    from learn_fhe_b200 import fhew
+    P, K, ex = fhew_setup
+    param = fhew.single_key_testing_param(P.big_q)
+    key = fhew.BootstrappingKey(ctx, param, ex["ksk_a"], ex["ksk_b"], ex["brk"], ex["ak"], ex["ak_t"])
+    yield key
+    key.free()
+
+
+def _inputs(K, P, count, seed):
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, size=2 * count).astype(np.int32)
+    cts = K.encrypt(bits, seed)
+    lin = (cts[:count] + cts[count:]) % np.uint64(P.big_q)
+    return bits[:count], bits[count:], lin
+
+
+def test_prologue_and_key_switch(pkg, ctx, orc, fhew_setup, bk):
+    P, K, _ = fhew_setup
+    _, _, lin = _inputs(K, P, 13, 5)
+    d_in = pkg.to_dev(lin)
+    out = torch.empty((13, P.n_s + 1), dtype=torch.int64, device="cuda")
+    ctx.call("fhe_fhew_prologue_batch", bk.h, 13, pkg.dptr(d_in), pkg.dptr(out))
+    ctx.sync()
+    assert (pkg.to_host(out) == K.prologue(lin)).all()
+    ks_in = orc.mod_switch(P.big_q, P.q_ks, lin)
+    d_ks = pkg.to_dev(ks_in)  # keep alive: a temporary would be recycled by torch's allocator before the kernel runs
+    ctx.call("fhe_lwe_key_switch_batch", bk.h, 13, pkg.dptr(d_ks), pkg.dptr(out))
+    ctx.sync()
+    assert (pkg.to_host(out) == K.key_switch(ks_in)).all()
+
+
+def test_external_product_and_automorphism(pkg, ctx, orc, fhew_setup, bk):
+    P, K, _ = fhew_setup
+    count = 12
+    acc = orc.residues(9, count * 2 * P.n, P.big_q).reshape(count, 2, P.n)
+    acc[0, 0, :3] = [0, P.big_q - 1, P.big_q // 2]
+    d_acc = pkg.to_dev(acc)
+    out = torch.empty_like(d_acc)
+    idx = np.array([0, 1, 7, 99, 50, 3, 42, 98, 11, 12, 13, 14], dtype=np.uint32)
+    d_idx = pkg.to_dev(idx)
+    ctx.call("fhe_fhew_external_product", bk.h, count, pkg.dptr(d_idx), pkg.dptr(d_acc), pkg.dptr(out))
+    ctx.sync()
+    got = pkg.to_host(out)
+    for i in range(count):
+        assert (got[i] == K.external_product(int(idx[i]), acc[i])).all(), i
+    vidx = np.array([0, 1, 2, 10, 5, 9, 3, 4, 6, 7, 8, 10], dtype=np.uint32)
+    d_vidx = pkg.to_dev(vidx)
+    ctx.call("fhe_fhew_automorphism", bk.h, count, pkg.dptr(d_vidx), pkg.dptr(d_acc), pkg.dptr(out))
+    ctx.sync()
+    got = pkg.to_host(out)
+    for i in range(count):
+        assert (got[i] == K.automorphism(int(vidx[i]), acc[i])).all(), i
+
+
+def test_blind_rotate_accumulator(pkg, ctx, orc, fhew_setup, bk):
+    from learn_fhe_b200 import fhew
+    P, K, _ = fhew_setup
+    _, _, lin = _inputs(K, P, 3, 6)
+    ct2n = K.prologue(lin)
+    f = fhew.gate_poly(bk.param, [1, 1, 1, 0])
+    out = torch.empty((3, 2, P.n), dtype=torch.int64, device="cuda")
+    d_f, d_ct2n = pkg.to_dev(f), pkg.to_dev(ct2n)
+    ctx.call("fhe_fhew_blind_rotate_batch", bk.h, pkg.dptr(d_f), 3, pkg.dptr(d_ct2n), pkg.dptr(out))
+    ctx.sync()
+    got = pkg.to_host(out)
+    for i in range(3):
+        assert (got[i] == K.blind_rotate(f, ct2n[i])).all(), i
+
+
+def test_nand_bit_exact_and_decrypts(pkg, ctx, orc, fhew_setup, bk):
+    """BASELINE config 1: FHEW NAND at the repo's test parameter set; LWE outputs bit-identical to the oracle."""
+    from learn_fhe_b200 import fhew
+    P, K, _ = fhew_setup
+    m0, m1, lin = _inputs(K, P, 16, 7)
+    got = fhew.Fhew.op(bk, [1, 1, 1, 0], lin)
+    ref = K.op([1, 1, 1, 0], lin, threads=8)
+    assert (got == ref).all()
+    assert (K.decrypt(got) == 1 - (m0 & m1)).all()
+
+
+def test_gate_truth_tables(pkg, ctx, orc, fhew_setup, bk):
+    """boolean.rs:257-286: not/and/nand/or/nor/xor/xnor/majority over all inputs (decrypt == plaintext op)."""
+    from learn_fhe_b200 import fhew
+    P, K, _ = fhew_setup
+    ops = {"and": lambda a, b: a & b, "nand": lambda a, b: 1 - (a & b), "or": lambda a, b: a | b, "nor": lambda a, b: 1 - (a | b),
+           "xor": lambda a, b: a ^ b, "xnor": lambda a, b: 1 - (a ^ b)}
+    a = np.array([0, 0, 1, 1] * 4, dtype=np.int32)
+    b = np.array([0, 1, 0, 1] * 4, dtype=np.int32)
+    ca, cb = K.encrypt(a, 100), K.encrypt(b, 200)
+    for name, fn in ops.items():
+        out = fhew.Fhew.gate(bk, name, ca, cb)
+        assert (K.decrypt(out) == fn(a, b)).all(), name
+    a3 = np.array([(i >> 2) & 1 for i in range(8)], dtype=np.int32)
+    b3 = np.array([(i >> 1) & 1 for i in range(8)], dtype=np.int32)
+    c3 = np.array([i & 1 for i in range(8)], dtype=np.int32)
+    out = fhew.Fhew.gate(bk, "majority", K.encrypt(a3, 1), K.encrypt(b3, 2), K.encrypt(c3, 3))
+    assert (K.decrypt(out) == ((a3 + b3 + c3) >= 2).astype(np.int32)).all()
+    assert (K.decrypt(fhew.Fhew.not_(bk.param, ca)) == 1 - a).all()
+
+
+def test_large_batch_consistency(pkg, ctx, orc, fhew_setup, bk):
+    """Size-independent property at a bench-like batch: identical ciphertexts give identical outputs, all decrypt right."""
+    from learn_fhe_b200 import fhew
+    P, K, _ = fhew_setup
+    m0, m1, lin = _inputs(K, P, 32, 8)
+    big = np.tile(lin, (16, 1))  # 512 gates
+    got = fhew.Fhew.op(bk, [1, 1, 1, 0], big)
+    assert (got.reshape(16, 32, -1) == got[:32][None]).all()
+    assert (K.decrypt(got[:32]) == 1 - (m0 & m1)).all()
+    ref = K.op([1, 1, 1, 0], lin[:4], threads=4)
+    assert (got[:4] == ref).all()
