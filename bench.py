@@ -157,7 +157,7 @@ def ntt_sweep(pkg, ctx, torch, hbm_peak, reps, log_ns, batch):
     """BASELINE configs[1]: forward + inverse, in place, device resident; buffers rotate through a pool larger than L2."""
     from learn_fhe_b200 import util
     out = []
-    pool_bytes = 1 << 30
+    pool_bytes = 4 << 30  # the largest case (N = 2^16, 4096 polys, u64) is 2 GiB; smaller cases rotate through the pool
     pool = torch.empty(pool_bytes // 8, dtype=torch.int64, device="cuda:%d" % ctx.device)
     stream = torch.cuda.current_stream(ctx.device)
     for log_n in log_ns:
@@ -166,7 +166,8 @@ def ntt_sweep(pkg, ctx, torch, hbm_peak, reps, log_ns, batch):
             n = 1 << log_n
             words = batch * n
             view_words = words if bits == 64 else words // 2  # int64 words backing the u32 view
-            nbuf = max(1, min(8, (pool_bytes // 8) // view_words))
+            nbuf = max(1, min(16, (pool_bytes // 8) // view_words))
+            assert view_words <= pool_bytes // 8
             bufs = [pool[i * view_words:(i + 1) * view_words] for i in range(nbuf)]
             for b in bufs:  # valid residues: zero is fine for timing (data independent), but use a pattern
                 b.random_(0, 1 << 27)

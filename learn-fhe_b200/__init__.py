@@ -200,7 +200,10 @@ class Context:
 
     def use_torch_stream(self):
         import torch
-        self.ck(self.L.fhe_ctx_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        h = torch.cuda.current_stream(self.device).cuda_stream
+        # torch's default stream has handle 0, which fhe_ctx_set_stream reads as "restore the own stream": name the
+        # legacy default stream explicitly (cudaStreamLegacy == (cudaStream_t)0x1)
+        self.ck(self.L.fhe_ctx_set_stream(self.h, C.c_void_p(h if h else 1)))
 
     def prof_begin(self):
         self.ck(self.L.fhe_prof_begin(self.h))

@@ -66,9 +66,13 @@ static fhe_status launch_ntt(fhe_ctx* ctx, uint64_t q, unsigned log_n, size_t ba
     FHE_REQUIRE(ctx, log_n <= 17, "log_n %u too large (max 17)", log_n);
     if (batch == 0) return FHE_OK;
     FHE_REQUIRE(ctx, d_a != nullptr, "null data pointer");
+    if (log_n == 0) {  // degree-1 ring: both transforms are the identity (n^-1 = 1); only the modulus is checked
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        const ModInfo* mi;
+        return get_mod_info(ctx, q, &mi);
+    }
     const NttTable* t;
     FHE_CHECK(get_ntt_table(ctx, q, A::BITS, (size_t)1 << log_n, &t));
-    if (log_n == 0) return FHE_OK;  // degree-1 ring: both transforms are the identity (n^-1 = 1)
     NttArgs<A> a;
     a.data = d_a;
     a.m = make_mod<A>(q);

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.json from tests/pyref.py (the pure-Python restatement of the reference written from the
+Rust sources).  The reference itself holds no golden vectors (every test draws from an entropy-seeded RNG, SURVEY.md
+§4) and cannot be run here (no Rust toolchain), so these fixtures pin the *restated* semantics: any later change to
+the oracle, the CUDA kernels or pyref that alters a bit shows up as a diff against the committed files.
+
+usage: python tests/golden/make_golden.py"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import pyref  # noqa: E402
+
+
+def rnd(seed, n, q):
+    return [int(x) for x in np.random.default_rng(seed).integers(0, q, size=n, dtype=np.uint64)]
+
+
+def main():
+    g = {}
+    # --- NTT (fft.rs:40-77, fft/zq.rs:58-67) ---
+    ntt = []
+    for bits, log_n in ((28, 3), (28, 6), (45, 5), (55, 7), (61, 4)):
+        q = pyref.two_adic_primes(bits, log_n + 1, 1)[0]
+        a = rnd(100 + log_n, 1 << log_n, q)
+        a[0], a[1] = 0, q - 1
+        ntt.append({"q": q, "a": a, "fwd": pyref.ntt_fwd(q, a), "generator": pyref.zq_generator(q)})
+    g["ntt"] = ntt
+    # FHEW-T modulus: root and first twiddles
+    q = pyref.two_adic_primes(28, 10, 1)[0]
+    tw, twi = pyref.compute_twiddle(q)
+    g["fhew_t_modulus"] = {"q": q, "generator": pyref.zq_generator(q), "omega": pyref.zq_two_adic_generator(q, 10),
+                           "tw_first16": tw[:16], "tw_inv_first16": twi[:16], "tw_len": len(tw)}
+    # --- negacyclic product vs schoolbook ---
+    q = pyref.two_adic_primes(45, 5, 1)[0]
+    a, b = rnd(1, 16, q), rnd(2, 16, q)
+    g["negacyclic_mul"] = {"q": q, "a": a, "b": b, "out": pyref.schoolbook_negacyclic(a, b, q)}
+    # --- decomposers (decompose.rs) ---
+    dz = []
+    for q, log_b, d in ((268409857, 7, 4), (1 << 16, 4, 4), (pyref.two_adic_primes(55, 12, 1)[0], 11, 5), (268409857, 5, 4), (97, 2, 3)):
+        v = rnd(7, 24, q) + [0, 1, q - 1, q // 2, q // 2 + 1, q // 2 - 1]
+        dz.append({"q": q, "log_b": log_b, "d": d, "v": v, "digits": [pyref.decompose_zq(q, log_b, d, x) for x in v]})
+    g["decompose_zq"] = dz
+    dt = []
+    for log_b, d in ((23, 1), (4, 5), (8, 8), (2, 8), (1, 3)):
+        v = rnd(8, 24, 1 << 64) + [0, 1, (1 << 64) - 1, 1 << 63, (1 << 63) - 1]
+        dt.append({"log_b": log_b, "d": d, "v": v, "digits": [pyref.decompose_t64(log_b, d, x) for x in v]})
+    g["decompose_t64"] = dt
+    # --- mod switches (zq.rs:128-140) ---
+    ms = []
+    for q, qp in ((268409857, 1 << 16), (1 << 16, 1024), (1024, 268409857)):
+        v = rnd(9, 40, q) + [0, 1, q - 1, q // 2]
+        ms.append({"q": q, "qp": qp, "v": v, "mod_switch": [pyref.zq_mod_switch(q, x, qp) for x in v],
+                   "mod_switch_odd": [pyref.zq_mod_switch_odd(q, x, qp) for x in v]})
+    g["mod_switch"] = ms
+    # --- automorphism / monomial (avec.rs:34-50, ring.rs:299-313) ---
+    q = 268409857
+    a = rnd(10, 16, q)
+    g["automorphism"] = [{"q": q, "a": a, "t": t, "out": pyref.automorphism(a, t, q)} for t in (5, -5, 31, 3, 33)]
+    g["monomial_mul"] = [{"q": q, "a": a, "k": k, "out": pyref.monomial_mul(a, k, q)} for k in (0, 1, 15, 16, 17, 31, -1, -17, 35)]
+    # --- RNS fast base conversion (rns.rs:331-345) ---
+    qs = pyref.two_adic_primes(55, 5, 6)
+    rns = []
+    for i in range(8):
+        x = [rnd(20 + i, 1, qi)[0] for qi in qs[:3]]
+        rns.append({"x": x, "out": pyref.rns_extend_bases(qs[:3], qs[3:], x)})
+    g["rns_extend_bases"] = {"qs": qs[:3], "ps": qs[3:], "cases": rns}
+    # --- LMKCDEY schedule + tiny FHEW bootstrap in the REFERENCE dataflow (schoolbook products) ---
+    P = {"n": 16, "log_n": 4, "big_q": pyref.two_adic_primes(20, 5, 1)[0], "q_ks": 1 << 10, "ks_log_b": 2, "ks_d": 5,
+         "rgsw_log_b": 5, "rgsw_d": 4, "rlwe_log_b": 4, "rlwe_d": 5, "n_s": 6, "w": 3, "p": 4}
+    n, q = P["n"], P["big_q"]
+    rng = np.random.default_rng(4242)
+    I = lambda hi, shape: rng.integers(0, hi, size=shape, dtype=np.uint64)  # noqa: E731
+    keys = {"ksk_a": I(P["q_ks"], (n * P["ks_d"], P["n_s"])).tolist(), "ksk_b": I(P["q_ks"], (n * P["ks_d"],)).tolist(),
+            "brk": I(q, (P["n_s"], 2 * P["rgsw_d"], 2, n)).tolist(), "ak": I(q, (P["w"] + 1, P["rlwe_d"], 2, n)).tolist(),
+            "ak_t": [2 * n - 5] + [pow(5, v, 2 * n) for v in range(1, P["w"] + 1)]}
+    f, q8 = pyref.fhew_gate_poly(P, [1, 1, 1, 0])
+    cases = []
+    for i in range(3):
+        ct = (I(q, (n,)).tolist(), int(I(q, (1,))[0]))
+        a2, b2 = ct
+        ksa = [pyref.zq_mod_switch(q, v, P["q_ks"]) for v in a2]
+        ksb = pyref.zq_mod_switch(q, b2, P["q_ks"])
+        ka, kb = pyref.lwe_key_switch(P["q_ks"], P["ks_log_b"], P["ks_d"], keys["ksk_a"], keys["ksk_b"], ksa, ksb)
+        pro = [pyref.zq_mod_switch_odd(P["q_ks"], v, 2 * n) for v in ka] + [pyref.zq_mod_switch_odd(P["q_ks"], kb, 2 * n)]
+        sched = pyref.blind_rotate_schedule(n, P["w"], pro[:-1])
+        oa, ob = pyref.fhew_bootstrap(P, keys, f, ct)
+        cases.append({"ct": ct[0] + [ct[1]], "prologue": pro, "schedule": [[0 if k == "ext" else 1, j] for k, j in sched],
+                      "out": oa + [(ob + q8) % q]})
+    g["fhew_tiny"] = {"param": P, "keys": keys, "table": [1, 1, 1, 0], "f": f, "post_add": q8, "cases": cases}
+    with open(os.path.join(HERE, "util_fhew.json"), "w") as fh:
+        json.dump(g, fh, separators=(",", ":"))
+    print("wrote", os.path.join(HERE, "util_fhew.json"), os.path.getsize(os.path.join(HERE, "util_fhew.json")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,128 @@
+"""CPU tier: the CUDA kernels' per-thread logic (the __host__ __device__ headers of learn-fhe_b200/csrc compiled with
+g++ and replayed sequentially by tests/hostsim) against the oracle — the closest a GPU-less box gets to the kernels."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+
+class SimParam(C.Structure):
+    _fields_ = [("log_n", C.c_uint), ("big_q", C.c_uint64), ("p", C.c_uint64), ("rlwe_log_b", C.c_uint), ("rlwe_d", C.c_uint),
+                ("rgsw_log_b", C.c_uint), ("rgsw_d", C.c_uint), ("n_s", C.c_uint), ("q_ks", C.c_uint64), ("ks_log_b", C.c_uint),
+                ("ks_d", C.c_uint), ("w", C.c_uint)]
+
+
+@pytest.fixture(scope="module")
+def H(hostsim):
+    hostsim.sim_ntt_u64.argtypes = [C.c_uint64, C.c_uint, C.c_int, u64p, C.c_int, C.c_uint]
+    hostsim.sim_ntt_u32.argtypes = [C.c_uint64, C.c_uint, C.c_int, u32p, C.c_int, C.c_uint]
+    hostsim.sim_fhew_key_upload.restype = C.c_void_p
+    hostsim.sim_fhew_key_upload.argtypes = [C.POINTER(SimParam), u64p, u64p, u64p, u64p, i64p]
+    hostsim.sim_fhew_key_free.argtypes = [C.c_void_p]
+    hostsim.sim_fhew_prologue.argtypes = [C.c_void_p, u64p, u64p, C.c_int, C.c_int, C.c_uint]
+    hostsim.sim_fhew_step.argtypes = [C.c_void_p, C.c_uint, u64p, u64p, C.c_uint]
+    hostsim.sim_fhew_blind_rotate_extract.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint]
+    hostsim.sim_mul_u64.restype = C.c_uint64
+    hostsim.sim_mul_u64.argtypes = [C.c_uint64] * 3
+    hostsim.sim_mul_u32.restype = C.c_uint32
+    hostsim.sim_mul_u32.argtypes = [C.c_uint32] * 3
+    hostsim.sim_swz32.restype = C.c_uint
+    hostsim.sim_swz64.restype = C.c_uint
+    return hostsim
+
+
+def sim_key(H, P, ex):
+    sp = SimParam(*[getattr(P, f[0]) for f in SimParam._fields_])
+    h = H.sim_fhew_key_upload(C.byref(sp), ex["ksk_a"].reshape(-1), ex["ksk_b"].reshape(-1), ex["brk"].reshape(-1),
+                              ex["ak"].reshape(-1), np.ascontiguousarray(ex["ak_t"], dtype=np.int64))
+    assert h
+    return h
+
+
+def test_modmul_primitives(H, orc):
+    rng = np.random.default_rng(0)
+    for q in (orc.two_adic_primes(61, 5, 1)[0], orc.two_adic_primes(55, 12, 1)[0], 268409857, (1 << 62) - 57, 3):
+        for _ in range(300):
+            a, b = int(rng.integers(0, q)), int(rng.integers(0, q))
+            assert H.sim_mul_u64(q, a, b) == a * b % q
+        assert H.sim_mul_u64(q, q - 1, q - 1) == (q - 1) * (q - 1) % q
+    for q in (268409857, (1 << 30) - 35, 12289):
+        for _ in range(300):
+            a, b = int(rng.integers(0, q)), int(rng.integers(0, q))
+            assert H.sim_mul_u32(q, a, b) == a * b % q
+
+
+def test_swizzle_is_a_permutation(H):
+    for fn, nmax in ((H.sim_swz32, 1 << 13), (H.sim_swz64, 1 << 13)):
+        assert sorted(fn(p) for p in range(nmax)) == list(range(nmax))
+
+
+@pytest.mark.parametrize("log_n", list(range(0, 17)))
+def test_kernel_logic_ntt(H, orc, log_n):
+    n = 1 << log_n
+    for bits, fn, dt in ((55, H.sim_ntt_u64, np.uint64), (28, H.sim_ntt_u32, np.uint32), (61, H.sim_ntt_u64, np.uint64),
+                         (30, H.sim_ntt_u32, np.uint32)):
+        if log_n == 0 and bits == 61:
+            continue
+        q = orc.two_adic_primes(bits, log_n + 1, 1)[0]
+        a = orc.residues(log_n, n, q)
+        ref = orc.ntt_fwd(q, a)
+        for c in ([log_n] if log_n <= 13 else [12, 13]):
+            x = a.astype(dt).copy()
+            assert fn(q, log_n, c, x, 1, 37) == 0 and (x.astype(np.uint64) == ref).all(), (log_n, bits, c, "fwd")
+            assert fn(q, log_n, c, x, 0, 64) == 0 and (x.astype(np.uint64) == a).all(), (log_n, bits, c, "inv")
+
+
+def test_kernel_logic_fhew(H, orc, fhew_setup):
+    P, K, ex = fhew_setup
+    h = sim_key(H, P, ex)
+    bits = np.array([0, 0, 1, 1, 0, 1, 0, 1], dtype=np.int32)
+    cts = K.encrypt(bits, 7)
+    lin = (cts[:4] + cts[4:]) % np.uint64(P.big_q)
+    pro = K.prologue(lin)
+    for i in range(4):
+        out = np.zeros(P.n_s + 1, dtype=np.uint64)
+        H.sim_fhew_prologue(h, lin[i], out, 1, 1, 128)
+        assert (out == pro[i]).all()
+    acc = orc.residues(9, 2 * P.n, P.big_q).reshape(2, P.n)
+    out = np.zeros_like(acc)
+    for j in (0, 5, 99):
+        H.sim_fhew_step(h, j, acc.reshape(-1), out.reshape(-1), 128)
+        assert (out == K.external_product(j, acc)).all()
+    for v in (0, 1, 10):
+        H.sim_fhew_step(h, 0x8000 | v, acc.reshape(-1), out.reshape(-1), 96)
+        assert (out == K.automorphism(v, acc)).all()
+    f = orc.fhew_gate_poly(P, [1, 1, 1, 0])
+    q8 = int(round(P.big_q / 8.0))
+    ref = K.op([1, 1, 1, 0], lin[:2], threads=2)
+    for i in range(2):
+        o = np.zeros(P.n + 1, dtype=np.uint64)
+        a = np.zeros(2 * P.n, dtype=np.uint64)
+        assert H.sim_fhew_blind_rotate_extract(h, f, pro[i], q8, o, a, 128) == 0
+        assert (o == ref[i]).all()
+        assert (a.reshape(2, -1) == K.blind_rotate(f, pro[i])).all()
+    H.sim_fhew_key_free(h)
+
+
+def test_kernel_logic_fhew_golden_tiny(H, orc):
+    """The kernel logic on the committed tiny-parameter fixture (produced by pyref in the reference dataflow)."""
+    from test_cpu_oracle import golden_fhew_tiny
+    g, P, keys = golden_fhew_tiny(orc)
+    ex = dict(ksk_a=keys[0], ksk_b=keys[1], brk=keys[2], ak=keys[3], ak_t=keys[4])
+    h = sim_key(H, P, ex)
+    f = np.array(g["f"], dtype=np.uint64)
+    for c in g["cases"]:
+        pro = np.zeros(P.n_s + 1, dtype=np.uint64)
+        H.sim_fhew_prologue(h, np.array(c["ct"], dtype=np.uint64), pro, 1, 1, 32)
+        assert [int(x) for x in pro] == c["prologue"]
+        o = np.zeros(P.n + 1, dtype=np.uint64)
+        a = np.zeros(2 * P.n, dtype=np.uint64)
+        assert H.sim_fhew_blind_rotate_extract(h, f, pro, g["post_add"], o, a, 32) == 0
+        assert [int(x) for x in o] == c["out"]
+    H.sim_fhew_key_free(h)

@@ -120,3 +120,28 @@ def test_large_batch_consistency(pkg, ctx, orc, fhew_setup, bk):
     assert (K.decrypt(got[:32]) == 1 - (m0 & m1)).all()
     ref = K.op([1, 1, 1, 0], lin[:4], threads=4)
     assert (got[:4] == ref).all()
+
+
+def test_golden_tiny_parameter_set(pkg, ctx, orc):
+    """Committed fixture (tests/golden/util_fhew.json, produced by pyref in the reference dataflow): N=16, 20-bit Q."""
+    from learn_fhe_b200 import fhew
+    from test_cpu_oracle import golden_fhew_tiny
+    g, P, keys = golden_fhew_tiny(orc)
+    param = pkg.FhewParam(**{k: g["param"][k] for k in ("log_n", "big_q", "p", "rlwe_log_b", "rlwe_d", "rgsw_log_b", "rgsw_d", "n_s",
+                                                       "q_ks", "ks_log_b", "ks_d", "w")})
+    key = fhew.BootstrappingKey(ctx, param, *keys)
+    cts = np.array([c["ct"] for c in g["cases"]], dtype=np.uint64)
+    got = fhew.Bootstrapping.bootstrap(key, np.array(g["f"], dtype=np.uint64), cts, post_add=g["post_add"])
+    assert (got == np.array([c["out"] for c in g["cases"]], dtype=np.uint64)).all()
+    key.free()
+
+
+def test_empty_batch_and_bad_parameters(pkg, ctx, orc, fhew_setup, bk):
+    from learn_fhe_b200 import fhew
+    P, K, ex = fhew_setup
+    out = fhew.Fhew.op(bk, [1, 1, 1, 0], np.zeros((0, P.n + 1), dtype=np.uint64))
+    assert out.shape == (0, P.n + 1)
+    bad = fhew.single_key_testing_param(P.big_q)
+    bad.big_q = 268409859  # not prime: the reference panics (ring.rs:258), here FHE_EINVAL
+    with pytest.raises(pkg.FheError):
+        fhew.BootstrappingKey(ctx, bad, ex["ksk_a"], ex["ksk_b"], ex["brk"], ex["ak"], ex["ak_t"])
