@@ -195,6 +195,9 @@ typedef struct fhe_tfhe_key fhe_tfhe_key;
 fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* param, const uint64_t* brk, const uint64_t* ksk_a,
                                const uint64_t* ksk_b, fhe_tfhe_key** out);
 void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key);
+/* device bytes held by the key (Fourier-domain bsk + ksk) and its one-time NCCL broadcast from `root` */
+size_t fhe_tfhe_key_bytes(const fhe_tfhe_key* key);
+fhe_status fhe_tfhe_key_broadcast(fhe_ctx* ctx, fhe_tfhe_key* key, void* nccl_comm, int root);
 /* Bootstrapping::bootstrap (tfhe/bootstrapping.rs:78-82) on `count` TLWE ciphertexts [a (n), b]; `d_lut` is the
  * already-encoded test polynomial (N torus words: Tglwe::encode(v), tglwe.rs:80-84), shared by the batch. */
 fhe_status fhe_tfhe_pbs_batch(fhe_ctx* ctx, const fhe_tfhe_key* key, const uint64_t* d_lut, size_t count, const uint64_t* d_ct_in,

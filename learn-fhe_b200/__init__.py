@@ -143,6 +143,9 @@ def lib():
         L.fhe_tfhe_key_upload.argtypes = [vp, C.POINTER(TfheParam), vp, vp, vp, C.POINTER(vp)]
         L.fhe_tfhe_key_free.argtypes = [vp, vp]
         L.fhe_tfhe_key_free.restype = None
+        L.fhe_tfhe_key_bytes.argtypes = [vp]
+        L.fhe_tfhe_key_bytes.restype = sz
+        L.fhe_tfhe_key_broadcast.argtypes = [vp, vp, vp, C.c_int]
         L.fhe_tfhe_pbs_batch.argtypes = [vp, vp, vp, sz, vp, vp]
         L.fhe_tfhe_pbs_batch_host.argtypes = [vp, vp, vp, sz, vp, vp]
         L.fhe_tfhe_external_product.argtypes = [vp, vp, sz, vp, vp, vp]

@@ -1,0 +1,519 @@
+// RNS base conversion / rescale kernels and the CKKS ciphertext pipeline on sm_100a (K14-K16 of SURVEY.md §2).
+//
+// Reference call sites replaced:
+//   RnsRq::extend_bases / switch_bases / rescale_k / round / div      util/src/ring/rns.rs:83-132, 287-345
+//   RnsRq *= RnsRq (moduli intersection, per-limb negacyclic product)  util/src/ring/rns.rs:143-158
+//   Ckks::mul / relinearize / key_switch / rotate / conjugate          scheme/ckks/src/ckks.rs:255-293
+//   CkksCiphertext::rescale / automorphism                             scheme/ckks/src/ckks.rs:123-129
+// Dataflow (differs from the reference, results identical because every step is exact modular arithmetic on canonical
+// residues; the only floating-point step, the overflow estimate of extend_bases, sees the same integers in the same
+// order): inputs are transformed once, the tensor product d0,d1,d2 and the key products are taken in the evaluation
+// domain against a key-switching key that was transformed at upload, so one Ckks::mul costs 9l+3L transforms instead of
+// the reference's 3*(4l + 2(l+L)).  Limb-batched transforms use the multi-modulus fast NTT (ntt_fast_launch.cu).
+#include <algorithm>
+#include <functional>
+#include <vector>
+
+#include "ctx.cuh"
+#include "rns_core.cuh"
+#include "rns_tables.hpp"
+
+namespace fhe {
+
+// ---- host-built tables (values computed by rns_tables.hpp, shared with tests/hostsim) --------------------------------
+template <typename T>
+static T* upload_vec(const std::vector<T>& h) {
+    T* d = nullptr;
+    if (h.empty()) return nullptr;
+    if (cudaMalloc((void**)&d, h.size() * sizeof(T)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(d);
+        return nullptr;
+    }
+    return d;
+}
+
+struct RnsExtOwned {
+    RnsExtTab tab{};
+    std::vector<void*> owned;
+    bool ok = false;
+    void build(const std::vector<uint64_t>& qs, const std::vector<uint64_t>& ps) {
+        RnsExtHost h;
+        h.build(qs, ps);
+        tab.nq = (int)qs.size();
+        tab.np = (int)ps.size();
+        tab.mq = upload_vec(h.mq);
+        tab.qhat_inv = upload_vec(h.qhat_inv);
+        tab.qhat_inv_sh = upload_vec(h.qhat_inv_sh);
+        tab.frac = upload_vec(h.frac);
+        tab.mp = upload_vec(h.mp);
+        tab.qhat_ps = upload_vec(h.qhat_ps);
+        tab.uq_ps = upload_vec(h.uq_ps);
+        owned = {(void*)tab.mq, (void*)tab.qhat_inv, (void*)tab.qhat_inv_sh, (void*)tab.frac, (void*)tab.mp, (void*)tab.qhat_ps, (void*)tab.uq_ps};
+        ok = true;
+        for (void* p : owned) ok = ok && p != nullptr;
+    }
+    void release() {
+        for (void* p : owned)
+            if (p) cudaFree(p);
+        owned.clear();
+    }
+};
+struct RescaleOwned {
+    RescaleTab tab{};
+    RnsExtOwned ext;
+    std::vector<void*> owned;
+    bool ok = false;
+    void build(const std::vector<uint64_t>& all, size_t k) {
+        RescaleHost h;
+        h.build(all, k);
+        ok = true;
+        if (k > 1) {
+            ext.build(h.dropped, h.kept);
+            ok = ext.ok;
+            tab.ext = ext.tab;
+        }
+        tab.l = (int)h.kept.size();
+        tab.k = (int)k;
+        tab.m_all = upload_vec(h.m_all);
+        tab.ph = upload_vec(h.ph);
+        tab.pinv = upload_vec(h.pinv);
+        tab.pinv_sh = upload_vec(h.pinv_sh);
+        owned = {(void*)tab.m_all, (void*)tab.ph, (void*)tab.pinv, (void*)tab.pinv_sh};
+        for (void* p : owned) ok = ok && p != nullptr;
+    }
+    void release() {
+        ext.release();
+        for (void* p : owned)
+            if (p) cudaFree(p);
+        owned.clear();
+    }
+};
+
+// ---- kernels -----------------------------------------------------------------------------------------------------------
+// in [B][in_limbs][n] (limbs in_off .. in_off+nq-1 are the source base) -> out [B][out_limbs][n] at limbs out_off..
+__global__ void __launch_bounds__(256) rns_extend_kernel(RnsExtTab T, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
+                                                         int in_limbs, int in_off, uint64_t* __restrict__ out, int out_limbs, int out_off) {
+    const unsigned long long total = batch << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const size_t n = (size_t)1 << log_n;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const unsigned long long b = idx >> log_n;
+        const size_t c = (size_t)(idx & (n - 1));
+        const uint64_t* src = in + (b * in_limbs + in_off) * n + c;
+        uint64_t x[RNS_MAXL];
+#pragma unroll
+        for (int i = 0; i < RNS_MAXL; ++i) x[i] = i < T.nq ? src[(size_t)i * n] : 0;
+        uint64_t* dst = out + (b * out_limbs + out_off) * n + c;
+        rns_extend_coeff(T, x, [&](int k, uint64_t y) { dst[(size_t)k * n] = y; });
+    }
+}
+// copy limbs [0, nq) of every batch element into a wider layout (the "input limbs copied" half of extend_bases)
+__global__ void __launch_bounds__(256) rns_copy_limbs_kernel(int log_n, unsigned long long batch, int nq, const uint64_t* __restrict__ in,
+                                                             int in_limbs, uint64_t* __restrict__ out, int out_limbs) {
+    const size_t n = (size_t)1 << log_n;
+    const unsigned long long total = batch * nq * n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const unsigned long long b = idx / ((unsigned long long)nq * n);
+        const unsigned long long r = idx - b * nq * n;
+        out[b * out_limbs * n + r] = in[b * in_limbs * n + r];
+    }
+}
+// rescale_k: in [B][l+k][n] (+ pre [B][l+k][n]) -> out [B][l][n] (+ post [B][l][n]; if post_even_only only for even b)
+__global__ void __launch_bounds__(256) rns_rescale_kernel(RescaleTab R, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
+                                                          const uint64_t* __restrict__ pre, const uint64_t* __restrict__ post, int post_even_only,
+                                                          uint64_t* __restrict__ out) {
+    const unsigned long long total = batch << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const size_t n = (size_t)1 << log_n;
+    const int l = R.l, k = R.k;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const unsigned long long b = idx >> log_n;
+        const size_t c = (size_t)(idx & (n - 1));
+        const size_t ibase = b * (size_t)(l + k) * n + c, obase = b * (size_t)l * n + c;
+        auto load = [&](int i) {
+            uint64_t v = in[ibase + (size_t)i * n];
+            if (pre) v = R.m_all[i].add(v, pre[ibase + (size_t)i * n]);
+            return v;
+        };
+        rns_rescale_coeff(R, load, [&](int i, uint64_t v) {
+            if (post && (!post_even_only || (b & 1ull) == 0)) v = R.m_all[i].add(v, post[obase + (size_t)i * n]);
+            out[obase + (size_t)i * n] = v;
+        });
+    }
+}
+
+// tensor product in the evaluation domain: e0, e1 [C][2 (b,a)][l][n] -> d01 [C][2 (d0,d1)][l][n], d2 [C][l][n]  (ckks.rs:262-266)
+__global__ void __launch_bounds__(256) ckks_tensor_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long count,
+                                                          const uint64_t* __restrict__ e0, const uint64_t* __restrict__ e1,
+                                                          uint64_t* __restrict__ d01, uint64_t* __restrict__ d2) {
+    const size_t n = (size_t)1 << log_n, ln = (size_t)l * n;
+    const unsigned long long total = count * ln, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const unsigned long long c = idx / ln;
+        const size_t r = (size_t)(idx - c * ln);
+        const Mod64 m = mods[r >> log_n];
+        const size_t o = c * 2 * ln + r;
+        const uint64_t b0 = e0[o], a0 = e0[o + ln], b1 = e1[o], a1 = e1[o + ln];
+        d01[o] = m.mul(b0, b1);
+        d01[o + ln] = m.add(m.mul(b0, a1), m.mul(a0, b1));
+        d2[c * ln + r] = m.mul(a0, a1);
+    }
+}
+// key products: x = [xq (l limbs, eval) ; xp (L limbs, eval)] against ksk [2 (b,a)][2L][n] eval -> out [C][2][l+L][n]  (ckks.rs:289-291)
+__global__ void __launch_bounds__(256) ckks_keymul_kernel(const Mod64* __restrict__ mods /* [2L]: qs then ps */, int l, int big_l, int log_n,
+                                                          unsigned long long count, const uint64_t* __restrict__ xq, const uint64_t* __restrict__ xp,
+                                                          const uint64_t* __restrict__ ksk, uint64_t* __restrict__ out) {
+    const size_t n = (size_t)1 << log_n;
+    const int le = l + big_l;
+    const unsigned long long total = count * le * n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const unsigned long long c = idx / ((unsigned long long)le * n);
+        const size_t r = (size_t)(idx - c * le * n);
+        const int j = (int)(r >> log_n);
+        const size_t x = r & (n - 1);
+        const int kl = j < l ? j : big_l + (j - l);
+        const Mod64 m = mods[kl];
+        const uint64_t v = j < l ? xq[(c * l + j) * n + x] : xp[(c * big_l + (j - l)) * n + x];
+        const size_t o = c * 2 * le * n + r;
+        out[o] = m.mul(ksk[(size_t)kl * n + x], v);
+        out[o + (size_t)le * n] = m.mul(ksk[((size_t)2 * big_l + kl) * n + x], v);
+    }
+}
+// RnsRq::automorphism (rns.rs:74-77 -> avec.rs:34-50) on [polys][n] with modulus mods[poly % l]
+__global__ void __launch_bounds__(256) rns_automorphism_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long polys, uint32_t t,
+                                                               const uint64_t* __restrict__ in, uint64_t* __restrict__ out) {
+    const uint32_t n = 1u << log_n;
+    const unsigned long long total = polys << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const unsigned long long p = idx >> log_n;
+        const uint32_t i = (uint32_t)(idx & (n - 1));
+        const uint32_t it = (uint32_t)(((unsigned long long)i * t) & (2ull * n - 1));
+        uint64_t v = in[idx];
+        if (it >= n) v = mods[p % l].neg(v);
+        out[(p << log_n) + (it & (n - 1))] = v;
+    }
+}
+
+static unsigned stream_grid(fhe_ctx* ctx, unsigned long long work) {
+    unsigned long long blocks = (work + 255) / 256, cap = (unsigned long long)ctx->sm_count * 16;
+    return (unsigned)std::max<unsigned long long>(1, std::min(blocks, cap));
+}
+
+static fhe_status check_moduli(fhe_ctx* ctx, const std::vector<uint64_t>& v) {
+    for (size_t i = 0; i < v.size(); ++i) {
+        FHE_REQUIRE(ctx, v[i] > 2 && (v[i] & 1) && v[i] < (1ull << 62), "RNS moduli must be odd and < 2^62");
+        for (size_t j = 0; j < i; ++j) FHE_REQUIRE(ctx, v[i] != v[j], "RNS moduli must be pairwise distinct (rns.rs:84)");
+    }
+    return FHE_OK;
+}
+
+// cached table lookup: key = kind, qs..., 0, ps...
+template <typename Owned, typename Build>
+static fhe_status cached_table(fhe_ctx* ctx, std::vector<uint64_t> key, Build build, const Owned** out) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->rns_tabs.find(key);
+    if (it == ctx->rns_tabs.end()) {
+        Owned* o = new Owned();
+        build(*o);
+        if (!o->ok) {
+            o->release();
+            delete o;
+            return fail(ctx, FHE_ENOMEM, "RNS table upload failed");
+        }
+        ctx->cleanup.push_back([o]() {
+            o->release();
+            delete o;
+        });
+        it = ctx->rns_tabs.emplace(key, (void*)o).first;
+    }
+    *out = (const Owned*)it->second;
+    return FHE_OK;
+}
+static fhe_status get_ext(fhe_ctx* ctx, const std::vector<uint64_t>& qs, const std::vector<uint64_t>& ps, const RnsExtOwned** out) {
+    std::vector<uint64_t> key{1};
+    key.insert(key.end(), qs.begin(), qs.end());
+    key.push_back(0);
+    key.insert(key.end(), ps.begin(), ps.end());
+    return cached_table<RnsExtOwned>(ctx, key, [&](RnsExtOwned& o) { o.build(qs, ps); }, out);
+}
+static fhe_status get_rescale(fhe_ctx* ctx, const std::vector<uint64_t>& all, size_t k, const RescaleOwned** out) {
+    std::vector<uint64_t> key{2, (uint64_t)k};
+    key.insert(key.end(), all.begin(), all.end());
+    return cached_table<RescaleOwned>(ctx, key, [&](RescaleOwned& o) { o.build(all, k); }, out);
+}
+
+static fhe_status run_extend(fhe_ctx* ctx, const std::vector<uint64_t>& qs, const std::vector<uint64_t>& ps, unsigned log_n, size_t batch,
+                             const uint64_t* d_in, int in_limbs, int in_off, uint64_t* d_out, int out_limbs, int out_off) {
+    FHE_REQUIRE(ctx, qs.size() >= 1 && qs.size() <= (size_t)RNS_MAXL, "base conversion supports 1..%d source limbs", RNS_MAXL);
+    const RnsExtOwned* t;
+    FHE_CHECK(get_ext(ctx, qs, ps, &t));
+    rns_extend_kernel<<<stream_grid(ctx, (unsigned long long)batch << log_n), 256, 0, ctx->stream>>>(t->tab, (int)log_n, batch, d_in, in_limbs,
+                                                                                                    in_off, d_out, out_limbs, out_off);
+    return after_launch(ctx, "rns_extend_kernel");
+}
+static fhe_status run_rescale(fhe_ctx* ctx, const std::vector<uint64_t>& all, size_t k, unsigned log_n, size_t batch, const uint64_t* d_in,
+                              const uint64_t* d_pre, const uint64_t* d_post, bool post_even_only, uint64_t* d_out) {
+    FHE_REQUIRE(ctx, k >= 1 && k < all.size(), "rescale_k needs 0 < k < number of limbs (rns.rs:104)");
+    FHE_REQUIRE(ctx, k <= (size_t)RNS_MAXL, "rescale_k supports dropping at most %d limbs", RNS_MAXL);
+    const RescaleOwned* t;
+    FHE_CHECK(get_rescale(ctx, all, k, &t));
+    rns_rescale_kernel<<<stream_grid(ctx, (unsigned long long)batch << log_n), 256, 0, ctx->stream>>>(t->tab, (int)log_n, batch, d_in, d_pre,
+                                                                                                     d_post, post_even_only ? 1 : 0, d_out);
+    return after_launch(ctx, "rns_rescale_kernel");
+}
+
+}  // namespace fhe
+
+using namespace fhe;
+
+struct fhe_ckks_ctx {
+    unsigned log_n = 0;
+    size_t big_l = 0;
+    std::vector<uint64_t> qs, ps;
+    Mod64* d_mods = nullptr;  // [2L]: qs then ps
+    // grow-only workspace
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+};
+struct fhe_ckks_ksk {
+    uint64_t* d_eval = nullptr;  // [2 (b,a)][2L][n] evaluation form
+};
+
+namespace fhe {
+static fhe_status ckks_ws(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t bytes, uint64_t** out) {
+    if (ck->ws_bytes < bytes) {
+        FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ck->ws) cudaFree(ck->ws);
+        ck->ws = nullptr;
+        ck->ws_bytes = 0;
+        if (cudaMalloc(&ck->ws, bytes) != cudaSuccess) return fail(ctx, FHE_ENOMEM, "CKKS workspace of %zu bytes", bytes);
+        ck->ws_bytes = bytes;
+    }
+    *out = (uint64_t*)ck->ws;
+    return FHE_OK;
+}
+static std::vector<uint64_t> level_qs(const fhe_ckks_ctx* ck, size_t l) { return std::vector<uint64_t>(ck->qs.begin(), ck->qs.begin() + l); }
+static std::vector<uint64_t> level_qps(const fhe_ckks_ctx* ck, size_t l) {
+    std::vector<uint64_t> v = level_qs(ck, l);
+    v.insert(v.end(), ck->ps.begin(), ck->ps.end());
+    return v;
+}
+
+// Ckks::key_switch core (ckks.rs:284-293) on `count` polynomials a (coefficient form [count][l][n]) whose evaluation form
+// a_eval [count][l][n] is already available: r [count][2][l][n] = rescale_k(ksk * extend(a), L) (+ post on the b half).
+// scratch: xp [count][L][n], kk [count][2][l+L][n]
+static fhe_status key_switch_core(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* ksk, size_t l, size_t count, const uint64_t* a_coeff,
+                                  const uint64_t* a_eval, uint64_t* xp, uint64_t* kk, const uint64_t* post, uint64_t* r) {
+    const unsigned log_n = ck->log_n;
+    const size_t L = ck->big_l;
+    const std::vector<uint64_t> qs = level_qs(ck, l), qps = level_qps(ck, l);
+    FHE_CHECK(run_extend(ctx, qs, ck->ps, log_n, count, a_coeff, (int)l, 0, xp, (int)L, 0));
+    FHE_CHECK(launch_ntt_rns_u64(ctx, ck->ps.data(), L, log_n, count * L, xp, true));
+    ckks_keymul_kernel<<<stream_grid(ctx, (unsigned long long)count * (l + L) << log_n), 256, 0, ctx->stream>>>(
+        ck->d_mods, (int)l, (int)L, (int)log_n, count, a_eval, xp, ksk->d_eval, kk);
+    FHE_CHECK(after_launch(ctx, "ckks_keymul_kernel"));
+    FHE_CHECK(launch_ntt_rns_u64(ctx, qps.data(), l + L, log_n, count * 2 * (l + L), kk, false));
+    return run_rescale(ctx, qps, L, log_n, count * 2, kk, nullptr, post, true, r);
+}
+}  // namespace fhe
+
+extern "C" {
+
+// ---- util-level RNS entry points ---------------------------------------------------------------------------------------
+fhe_status fhe_rns_extend_bases(fhe_ctx* ctx, const uint64_t* qs, size_t nq, const uint64_t* ps, size_t np, unsigned log_n, size_t batch,
+                                const uint64_t* d_in, uint64_t* d_out) {
+    if (!ctx || !qs || !ps) return FHE_EINVAL;
+    if (batch == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_in && d_out && log_n <= 20, "bad arguments");
+    std::vector<uint64_t> vq(qs, qs + nq), vp(ps, ps + np), all(vq);
+    all.insert(all.end(), vp.begin(), vp.end());
+    FHE_CHECK(check_moduli(ctx, all));
+    rns_copy_limbs_kernel<<<stream_grid(ctx, (unsigned long long)batch * nq << log_n), 256, 0, ctx->stream>>>((int)log_n, batch, (int)nq, d_in,
+                                                                                                             (int)nq, d_out, (int)(nq + np));
+    FHE_CHECK(after_launch(ctx, "rns_copy_limbs_kernel"));
+    return run_extend(ctx, vq, vp, log_n, batch, d_in, (int)nq, 0, d_out, (int)(nq + np), (int)nq);
+}
+fhe_status fhe_rns_rescale_k(fhe_ctx* ctx, const uint64_t* qs, size_t nq, size_t k, unsigned log_n, size_t batch, const uint64_t* d_in,
+                             uint64_t* d_out) {
+    if (!ctx || !qs) return FHE_EINVAL;
+    if (batch == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_in && d_out && log_n <= 20, "bad arguments");
+    std::vector<uint64_t> all(qs, qs + nq);
+    FHE_CHECK(check_moduli(ctx, all));
+    return run_rescale(ctx, all, k, log_n, batch, d_in, nullptr, nullptr, false, d_out);
+}
+
+// ---- CKKS ----------------------------------------------------------------------------------------------------------------
+fhe_status fhe_ckks_create(fhe_ctx* ctx, unsigned log_n, const uint64_t* qs, const uint64_t* ps, size_t big_l, fhe_ckks_ctx** out) {
+    if (!ctx || !qs || !ps || !out) return FHE_EINVAL;
+    *out = nullptr;
+    FHE_REQUIRE(ctx, log_n >= 1 && log_n <= 17, "CKKS ring degree 2^%u out of range", log_n);
+    FHE_REQUIRE(ctx, big_l >= 1 && big_l <= (size_t)RNS_MAXL, "CKKS supports 1..%d ciphertext primes", RNS_MAXL);
+    std::vector<uint64_t> all(qs, qs + big_l);
+    all.insert(all.end(), ps, ps + big_l);
+    FHE_CHECK(check_moduli(ctx, all));
+    for (uint64_t q : all) {  // every modulus must support the degree-2^log_n negacyclic NTT (panics in the reference otherwise)
+        const NttTable* t;
+        FHE_CHECK(get_ntt_table(ctx, q, 64, (size_t)1 << log_n, &t));
+    }
+    fhe_ckks_ctx* ck = new fhe_ckks_ctx();
+    ck->log_n = log_n;
+    ck->big_l = big_l;
+    ck->qs.assign(qs, qs + big_l);
+    ck->ps.assign(ps, ps + big_l);
+    std::vector<Mod64> m(2 * big_l);
+    for (size_t i = 0; i < 2 * big_l; ++i) m[i] = make_mod<Mod64>(all[i]);
+    ck->d_mods = upload_vec(m);
+    if (!ck->d_mods) {
+        delete ck;
+        return fail(ctx, FHE_ENOMEM, "CKKS modulus table upload failed");
+    }
+    *out = ck;
+    return FHE_OK;
+}
+void fhe_ckks_destroy(fhe_ctx* ctx, fhe_ckks_ctx* ck) {
+    if (!ck) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (ck->d_mods) cudaFree(ck->d_mods);
+    if (ck->ws) cudaFree(ck->ws);
+    delete ck;
+}
+fhe_status fhe_ckks_ksk_upload(fhe_ctx* ctx, fhe_ckks_ctx* ck, const uint64_t* ksk, fhe_ckks_ksk** out) {
+    if (!ctx || !ck || !ksk || !out) return FHE_EINVAL;
+    *out = nullptr;
+    const size_t n = (size_t)1 << ck->log_n, L2 = 2 * ck->big_l, words = 2 * L2 * n;
+    std::vector<uint64_t> qps = level_qps(ck, ck->big_l);
+    for (size_t h = 0; h < 2; ++h)
+        for (size_t i = 0; i < L2; ++i)
+            for (size_t c = 0; c < n; ++c) FHE_REQUIRE(ctx, ksk[(h * L2 + i) * n + c] < qps[i], "key coefficient out of range");
+    fhe_ckks_ksk* k = new fhe_ckks_ksk();
+    if (cudaMalloc((void**)&k->d_eval, words * 8) != cudaSuccess) {
+        delete k;
+        return fail(ctx, FHE_ENOMEM, "key alloc");
+    }
+    cudaError_t e = cudaMemcpyAsync(k->d_eval, ksk, words * 8, cudaMemcpyHostToDevice, ctx->stream);
+    fhe_status st = e == cudaSuccess ? FHE_OK : fail(ctx, FHE_ECUDA, "key upload: %s", cudaGetErrorString(e));
+    if (st == FHE_OK) st = launch_ntt_rns_u64(ctx, qps.data(), L2, ck->log_n, 2 * L2, k->d_eval, true);
+    if (st == FHE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, FHE_ECUDA, "key transform failed");
+    if (st != FHE_OK) {
+        cudaFree(k->d_eval);
+        delete k;
+        return st;
+    }
+    *out = k;
+    return FHE_OK;
+}
+void fhe_ckks_ksk_free(fhe_ctx* ctx, fhe_ckks_ksk* ksk) {
+    if (!ksk) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (ksk->d_eval) cudaFree(ksk->d_eval);
+    delete ksk;
+}
+
+fhe_status fhe_ckks_mul_relin_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* rlk, size_t level, size_t count,
+                                            const uint64_t* d_ct0, const uint64_t* d_ct1, uint64_t* d_out) {
+    if (!ctx || !ck || !rlk) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_ct0 && d_ct1 && d_out, "null pointer");
+    FHE_REQUIRE(ctx, level >= 2 && level <= ck->big_l, "level must be in [2, L] (rescale needs a limb to drop)");
+    const unsigned log_n = ck->log_n;
+    const size_t n = (size_t)1 << log_n, l = level, L = ck->big_l, le = l + L;
+    const std::vector<uint64_t> qs = level_qs(ck, l);
+    // per-pair workspace (words): e0, e1 (2l each) | d01 (2l) | d2 eval (l) | d2 coeff (l) | xp (L) | kk (2(l+L)) | r (2l)
+    const size_t per = (2 * l + 2 * l + 2 * l + l + l + L + 2 * le + 2 * l) * n;
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ((size_t)6 << 30) / (per * 8)));
+    uint64_t* ws;
+    FHE_CHECK(ckks_ws(ctx, ck, chunk * per * 8, &ws));
+    uint64_t* e0 = ws;
+    uint64_t* e1 = e0 + chunk * 2 * l * n;
+    uint64_t* d01 = e1 + chunk * 2 * l * n;
+    uint64_t* d2e = d01 + chunk * 2 * l * n;
+    uint64_t* d2c = d2e + chunk * l * n;
+    uint64_t* xp = d2c + chunk * l * n;
+    uint64_t* kk = xp + chunk * L * n;
+    uint64_t* r = kk + chunk * 2 * le * n;
+    for (size_t base = 0; base < count; base += chunk) {
+        const size_t c = std::min(chunk, count - base);
+        const uint64_t* in0 = d_ct0 + base * 2 * l * n;
+        const uint64_t* in1 = d_ct1 + base * 2 * l * n;
+        FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * 2 * l, in0, e0, true));
+        FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * 2 * l, in1, e1, true));
+        ckks_tensor_kernel<<<stream_grid(ctx, (unsigned long long)c * l << log_n), 256, 0, ctx->stream>>>(ck->d_mods, (int)l, (int)log_n, c, e0, e1,
+                                                                                                         d01, d2e);
+        FHE_CHECK(after_launch(ctx, "ckks_tensor_kernel"));
+        FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * l, d2e, d2c, false));
+        FHE_CHECK(key_switch_core(ctx, ck, rlk, l, c, d2c, d2e, xp, kk, nullptr, r));  // relinearize(d2): ct_b = 0
+        FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, c * 2 * l, d01, false));
+        // (d0, d1) + relin, then rescale (ckks.rs:266, 123-125)
+        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, d01, r, nullptr, false, d_out + base * 2 * (l - 1) * n));
+    }
+    return FHE_OK;
+}
+
+fhe_status fhe_ckks_mul_relin_rescale_batch_host(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* rlk, size_t level, size_t count,
+                                                 const uint64_t* ct0, const uint64_t* ct1, uint64_t* out) {
+    if (!ctx || !ck || !rlk) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, ct0 && ct1 && out, "null pointer");
+    FHE_REQUIRE(ctx, level >= 2 && level <= ck->big_l, "level must be in [2, L]");
+    const size_t n = (size_t)1 << ck->log_n;
+    const size_t in_bytes = count * 2 * level * n * 8, out_bytes = count * 2 * (level - 1) * n * 8;
+    void *d0, *d1, *dout;
+    FHE_CHECK(ensure_stage_d(ctx, 0, in_bytes, &d0));
+    FHE_CHECK(ensure_stage_d(ctx, 1, in_bytes, &d1));
+    FHE_CHECK(ensure_stage_d(ctx, 2, out_bytes, &dout));
+    FHE_CUDA(ctx, cudaMemcpyAsync(d0, ct0, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CUDA(ctx, cudaMemcpyAsync(d1, ct1, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CHECK(fhe_ckks_mul_relin_rescale_batch(ctx, ck, rlk, level, count, (const uint64_t*)d0, (const uint64_t*)d1, (uint64_t*)dout));
+    FHE_CUDA(ctx, cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FHE_OK;
+}
+
+fhe_status fhe_ckks_key_switch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* ksk, int64_t t, size_t level, size_t count,
+                               const uint64_t* d_ct, uint64_t* d_out) {
+    if (!ctx || !ck || !ksk) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_ct && d_out, "null pointer");
+    FHE_REQUIRE(ctx, level >= 1 && level <= ck->big_l, "level must be in [1, L]");
+    const unsigned log_n = ck->log_n;
+    const size_t n = (size_t)1 << log_n, l = level, L = ck->big_l, le = l + L;
+    const std::vector<uint64_t> qs = level_qs(ck, l);
+    // per-ciphertext workspace (words): ct' (2l) | a coeff (l) | a eval (l) | xp (L) | kk (2(l+L))
+    const size_t per = (2 * l + l + l + L + 2 * le) * n;
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ((size_t)6 << 30) / (per * 8)));
+    uint64_t* ws;
+    FHE_CHECK(ckks_ws(ctx, ck, chunk * per * 8, &ws));
+    uint64_t* cta = ws;
+    uint64_t* ac = cta + chunk * 2 * l * n;
+    uint64_t* ae = ac + chunk * l * n;
+    uint64_t* xp = ae + chunk * l * n;
+    uint64_t* kk = xp + chunk * L * n;
+    const int64_t m2 = 2 * (int64_t)n;
+    const uint32_t tt = (uint32_t)(((t % m2) + m2) % m2);
+    for (size_t base = 0; base < count; base += chunk) {
+        const size_t c = std::min(chunk, count - base);
+        const uint64_t* in = d_ct + base * 2 * l * n;
+        const uint64_t* ct = in;
+        if (t != 0) {  // CkksCiphertext::automorphism (ckks.rs:127-129)
+            rns_automorphism_kernel<<<stream_grid(ctx, (unsigned long long)c * 2 * l << log_n), 256, 0, ctx->stream>>>(ck->d_mods, (int)l, (int)log_n,
+                                                                                                                       c * 2 * l, tt, in, cta);
+            FHE_CHECK(after_launch(ctx, "rns_automorphism_kernel"));
+            ct = cta;
+        }
+        // gather the a halves ([c][1][l][n]) contiguously
+        FHE_CUDA(ctx, cudaMemcpy2DAsync(ac, l * n * 8, ct + l * n, 2 * l * n * 8, l * n * 8, c, cudaMemcpyDeviceToDevice, ctx->stream));
+        FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * l, ac, ae, true));
+        FHE_CHECK(key_switch_core(ctx, ck, ksk, l, c, ac, ae, xp, kk, ct, d_out + base * 2 * l * n));
+    }
+    return FHE_OK;
+}
+
+fhe_status fhe_ckks_rescale(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t count, const uint64_t* d_ct, uint64_t* d_out) {
+    if (!ctx || !ck) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_ct && d_out, "null pointer");
+    FHE_REQUIRE(ctx, level >= 2 && level <= ck->big_l, "level must be in [2, L]");
+    return run_rescale(ctx, level_qs(ck, level), 1, ck->log_n, count * 2, d_ct, nullptr, nullptr, false, d_out);
+}
+
+}  // extern "C"

@@ -36,6 +36,10 @@ fhe_status get_mod_info(fhe_ctx* ctx, uint64_t q, const ModInfo** out) {
 
 fhe_status get_ntt_table(fhe_ctx* ctx, uint64_t q, int bits, size_t len, const NttTable** out) {
     std::lock_guard<std::mutex> lock(ctx->mu);
+    return get_ntt_table_locked(ctx, q, bits, len, out);
+}
+
+fhe_status get_ntt_table_locked(fhe_ctx* ctx, uint64_t q, int bits, size_t len, const NttTable** out) {
     const ModInfo* mi;
     FHE_CHECK(get_mod_info(ctx, q, &mi));
     if (len < 2) len = 2;
@@ -50,8 +54,10 @@ fhe_status get_ntt_table(fhe_ctx* ctx, uint64_t q, int bits, size_t len, const N
     if (t.len < len) {
         // prefix property: entries [0, len) of the reference's 2^(s-1)-entry table are psi^(brev_lg(j)), psi = omega^(2^(s-1-lg))
         FHE_REQUIRE(ctx, host_build_twiddles(q, len, t.h_fwd, t.h_inv), "cannot build twiddles for q = %llu", (unsigned long long)q);
-        if (t.d_fwd) cudaFree(t.d_fwd);
-        if (t.d_inv) cudaFree(t.d_inv);
+        // older (shorter) tables stay alive until the context dies: keys and limb descriptors may still point at them
+        // (prefix property: they remain valid for the degrees they were built for)
+        if (t.d_fwd) ctx->retired.push_back(t.d_fwd);
+        if (t.d_inv) ctx->retired.push_back(t.d_inv);
         t.d_fwd = t.d_inv = nullptr;
         size_t bytes = len * (bits == 32 ? sizeof(TwPair<uint32_t>) : sizeof(TwPair<uint64_t>));
         FHE_CUDA(ctx, cudaMalloc(&t.d_fwd, bytes));
@@ -147,6 +153,9 @@ void fhe_ctx_destroy(fhe_ctx* ctx) {
     }
     for (auto& kv : ctx->fft_tables)
         if (kv.second.first) cudaFree(kv.second.first);
+    for (void* p : ctx->retired) cudaFree(p);
+    for (auto& fn : ctx->cleanup) fn();
+    for (auto& kv : ctx->fast_limbs) cudaFree(kv.second);
     if (ctx->scratch) cudaFree(ctx->scratch);
     for (int i = 0; i < 3; ++i)
         if (ctx->stage_d[i]) cudaFree(ctx->stage_d[i]);

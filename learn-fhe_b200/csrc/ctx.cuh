@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -43,6 +44,10 @@ struct fhe_ctx {
     std::map<uint64_t, fhe::ModInfo> mods;
     std::map<std::pair<uint64_t, int>, fhe::NttTable> tables;  // (q, word bits)
     std::map<int, std::pair<void*, size_t>> fft_tables;        // log_len -> (device table, bytes)   (tfhe)
+    std::map<std::vector<uint64_t>, void*> fast_limbs;         // (moduli..., log_n<<8 | bits) -> device FastLimb<L>[]
+    std::vector<void*> retired;                                // superseded twiddle tables (freed with the context)
+    std::map<std::vector<uint64_t>, void*> rns_tabs;           // RNS base-conversion / rescale tables (ckks.cu)
+    std::vector<std::function<void()>> cleanup;                // run by fhe_ctx_destroy
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     // per-launch timing log (fhe_prof_begin / fhe_prof_end): one event after every launch on the context's stream
@@ -103,6 +108,7 @@ bool host_is_prime(uint64_t n);
 fhe_status get_mod_info(fhe_ctx* ctx, uint64_t q, const ModInfo** out);
 // table with at least `len` entries for modulus q in the given word width (32 or 64)
 fhe_status get_ntt_table(fhe_ctx* ctx, uint64_t q, int bits, size_t len, const NttTable** out);
+fhe_status get_ntt_table_locked(fhe_ctx* ctx, uint64_t q, int bits, size_t len, const NttTable** out);  // ctx->mu held
 fhe_status ensure_scratch(fhe_ctx* ctx, size_t bytes, void** out);
 // grow-only device staging buffer `slot` (0..2) for the *_host entry points
 fhe_status ensure_stage_d(fhe_ctx* ctx, int slot, size_t bytes, void** out);
@@ -144,5 +150,15 @@ inline uint64_t host_invmod(uint64_t a, uint64_t q) { return host_powmod(a, q - 
 // launchers (ntt_launch.cu)
 fhe_status launch_ntt_u64(fhe_ctx* ctx, uint64_t q, unsigned log_n, size_t batch, uint64_t* d_a, bool fwd);
 fhe_status launch_ntt_u32(fhe_ctx* ctx, uint32_t q, unsigned log_n, size_t batch, uint32_t* d_a, bool fwd);
+// multi-modulus batches: polynomial p (of n_polys, contiguous) uses modulus qs[p % nl]
+fhe_status launch_ntt_rns_u64(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys, uint64_t* d_a, bool fwd);
+// out-of-place form: d_src (may be null = in place) -> d_dst
+fhe_status launch_ntt_rns_u64_oop(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys, const uint64_t* d_src,
+                                  uint64_t* d_dst, bool fwd);
+// fast path (ntt_fast_launch.cu): FHE_EUNSUPPORTED (ctx->err untouched) when its preconditions do not hold
+fhe_status launch_ntt_fast_u64(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys, const uint64_t* d_src,
+                               uint64_t* d_a, bool fwd);
+fhe_status launch_ntt_fast_u32(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys, const uint32_t* d_src,
+                               uint32_t* d_a, bool fwd);
 
 }  // namespace fhe

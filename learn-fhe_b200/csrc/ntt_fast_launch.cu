@@ -1,0 +1,250 @@
+// Fast-path batched negacyclic NTT kernels + launcher (see ntt_fast.cuh for the design).
+//   ntt_fast_tile_kernel   : PB tiles per CTA (TPP threads each); first pass global->regs->smem, radix-8 passes in
+//                            shared memory, last pass smem->regs->global.  One work item = (tile k, polynomial b),
+//                            k-major so that CTAs running together share twiddle lines in L1/L2.
+//   ntt_fast_column_kernel : register-only 2^S-point column transforms for N > 2^13 (first S forward stages / last S
+//                            inverse stages), coalesced along the row direction.
+// Replaces util/src/ring/fft/zq.rs:27-36 (+ ring/fft.rs:40-77) for every caller: fhe_ntt_*, CKKS limb batches, key
+// upload.  Moduli outside the lazy-reduction preconditions fall back to the generic kernels (ntt_launch.cu).
+#include <algorithm>
+
+#include "ctx.cuh"
+#include "ntt_fast.cuh"
+
+namespace fhe {
+
+template <typename L>
+struct FastArgs {
+    typename L::W* data;        // destination (and source unless `in` differs)
+    const typename L::W* in;    // source of the kernel launched first; == data for in-place transforms
+    const FastLimb<L>* limbs;
+    uint32_t nl;
+    uint32_t n_polys;
+    int log_n;
+    int s0;
+    uint32_t pre_red;
+    unsigned long long n_items;  // n_polys << s0
+};
+
+template <int LOGT>
+struct FastGeom {
+    static constexpr int R1 = fast_r1(LOGT);
+    static constexpr int RMAX = R1 > 3 ? R1 : 3;
+    static constexpr int TPP = 1 << (LOGT - RMAX);
+    static constexpr int PB = TPP >= 256 ? 1 : 256 / TPP;
+    static constexpr int NTHR = TPP * PB;
+    static constexpr int NP3 = (LOGT - R1) / 3;
+};
+
+template <typename L, int LOGT, bool FWD, bool FINAL>
+__global__ void __launch_bounds__(FastGeom<LOGT>::NTHR) ntt_fast_tile_kernel(FastArgs<L> a) {
+    typedef typename L::W W;
+    typedef FastGeom<LOGT> G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t pslot = threadIdx.x / G::TPP, tid = threadIdx.x % G::TPP;
+    W* s = reinterpret_cast<W*>(smem_raw) + ((size_t)pslot << LOGT);
+    const unsigned long long item = (unsigned long long)blockIdx.x * G::PB + pslot;
+    const bool active = item < a.n_items;
+    uint32_t k = 0, b = 0;
+    if (active) {
+        k = (uint32_t)(item / a.n_polys);
+        b = (uint32_t)(item - (unsigned long long)k * a.n_polys);
+    }
+    const FastLimb<L>& d = a.limbs[b % a.nl];
+    const size_t off = ((size_t)b << a.log_n) + ((size_t)k << LOGT);
+    W* g = a.data + off;
+    const W* gin = a.in + off;
+    if (FWD) {
+        if (active) fast_fwd_first<L, LOGT, G::R1, G::TPP>(d, gin, s, a.s0, k, (a.pre_red & 1u) != 0, tid);
+        __syncthreads();
+#pragma unroll 1
+        for (int i = 0; i < G::NP3 - 1; ++i) {
+            if (active) fast_fwd_mid<L, LOGT, G::TPP>(d, s, G::R1 + 3 * i, a.s0, k, ((a.pre_red >> (i + 1)) & 1u) != 0, tid);
+            __syncthreads();
+        }
+        if (active) fast_fwd_last<L, LOGT, G::TPP>(d, s, g, a.s0, k, ((a.pre_red >> G::NP3) & 1u) != 0, tid);
+    } else {
+        if (active) fast_inv_first<L, LOGT, G::TPP>(d, gin, s, a.s0, k, tid);
+        __syncthreads();
+#pragma unroll 1
+        for (int i = G::NP3 - 2; i >= 0; --i) {
+            if (active) fast_inv_mid<L, LOGT, G::TPP>(d, s, G::R1 + 3 * i, a.s0, k, tid);
+            __syncthreads();
+        }
+        if (active) fast_inv_last<L, LOGT, G::R1, G::TPP, FINAL>(d, s, g, a.s0, k, tid);
+    }
+}
+
+template <typename L, int S, bool FWD>
+__global__ void __launch_bounds__(256) ntt_fast_column_kernel(FastArgs<L> a) {
+    const int lc = a.log_n - S;
+    const unsigned long long total = (unsigned long long)a.n_polys << lc;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const uint32_t b = (uint32_t)(idx >> lc);
+        const uint32_t col = (uint32_t)(idx & ((1ull << lc) - 1ull));
+        const FastLimb<L>& d = a.limbs[b % a.nl];
+        typename L::W* g = a.data + ((size_t)b << a.log_n);
+        const typename L::W* gin = a.in + ((size_t)b << a.log_n);
+        if (FWD)
+            fast_fwd_column<L, S>(d, gin, g, lc, col);
+        else
+            fast_inv_column<L, S>(d, gin, g, lc, col);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+template <typename L>
+L make_lazy(uint64_t q);
+template <>
+Lz32 make_lazy<Lz32>(uint64_t q) {
+    Lz32 m;
+    m.q = (uint32_t)q;
+    m.q2 = (uint32_t)(2 * q);
+    m.q8 = (uint32_t)(8 * q);
+    m.mu = (uint32_t)((1ull << 32) / q);
+    return m;
+}
+template <>
+Lz64 make_lazy<Lz64>(uint64_t q) {
+    Lz64 m;
+    m.q = q;
+    m.nq = 0 - q;
+    m.q2 = 2 * q;
+    m.q4 = 4 * q;
+    m.q16 = 16 * q;
+    m.mu = (uint64_t)((((u128_t)1) << 64) / q);
+    return m;
+}
+
+template <typename L>
+static bool fast_modulus_ok(uint64_t q) {
+    return L::BITS == 32 ? (q > 2 && q < (1ull << 28)) : (q > 2 && q < (1ull << 56));
+}
+
+// device table of limb descriptors for (qs, log_n), cached in the context
+template <typename L>
+static fhe_status get_fast_limbs(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, const FastLimb<L>** out) {
+    typedef typename L::W W;
+    std::vector<uint64_t> key(qs, qs + nl);
+    key.push_back(((uint64_t)log_n << 8) | (uint64_t)L::BITS);
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto it = ctx->fast_limbs.find(key);
+    if (it != ctx->fast_limbs.end()) {
+        *out = (const FastLimb<L>*)it->second;
+        return FHE_OK;
+    }
+    std::vector<FastLimb<L>> h(nl);
+    for (size_t i = 0; i < nl; ++i) {
+        const NttTable* t;
+        FHE_CHECK(get_ntt_table_locked(ctx, qs[i], L::BITS, (size_t)1 << log_n, &t));
+        h[i].m = make_lazy<L>(qs[i]);
+        h[i].tw = (const TwPair<W>*)t->d_fwd;
+        h[i].itw = (const TwPair<W>*)t->d_inv;
+        const uint64_t ninv = host_invmod(((uint64_t)1 << log_n) % qs[i], qs[i]);
+        h[i].ninv = make_twpair<W>(ninv, qs[i]);
+        h[i].wninv = make_twpair<W>(host_mulmod(t->h_inv[1], ninv, qs[i]), qs[i]);
+    }
+    void* d = nullptr;
+    FHE_CUDA(ctx, cudaMalloc(&d, nl * sizeof(FastLimb<L>)));
+    FHE_CUDA(ctx, cudaMemcpy(d, h.data(), nl * sizeof(FastLimb<L>), cudaMemcpyHostToDevice));
+    ctx->fast_limbs[key] = d;
+    *out = (const FastLimb<L>*)d;
+    return FHE_OK;
+}
+
+template <typename L, int LOGT, bool FWD, bool FINAL>
+static fhe_status launch_fast_tile(fhe_ctx* ctx, FastArgs<L>& a) {
+    typedef FastGeom<LOGT> G;
+    auto kern = ntt_fast_tile_kernel<L, LOGT, FWD, FINAL>;
+    const size_t smem = (size_t)G::PB * sizeof(typename L::W) << LOGT;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FHE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const unsigned long long grid = (a.n_items + G::PB - 1) / G::PB;
+    if (grid == 0) return FHE_OK;
+    if (grid > 0x7FFFFFFFull) return fail(ctx, FHE_EINVAL, "batch too large for one launch");
+    kern<<<(unsigned)grid, G::NTHR, smem, ctx->stream>>>(a);
+    return after_launch(ctx, FWD ? "ntt_fast_tile_kernel<fwd>" : "ntt_fast_tile_kernel<inv>");
+}
+template <typename L, bool FWD, bool FINAL>
+static fhe_status launch_fast_tile_logt(fhe_ctx* ctx, FastArgs<L>& a, int logt) {
+    switch (logt) {
+        case 9: return launch_fast_tile<L, 9, FWD, FINAL>(ctx, a);
+        case 10: return launch_fast_tile<L, 10, FWD, FINAL>(ctx, a);
+        case 11: return launch_fast_tile<L, 11, FWD, FINAL>(ctx, a);
+        case 12: return launch_fast_tile<L, 12, FWD, FINAL>(ctx, a);
+        case 13: return launch_fast_tile<L, 13, FWD, FINAL>(ctx, a);
+        default: return fail(ctx, FHE_EUNSUPPORTED, "fast NTT: tile size 2^%d not instantiated", logt);
+    }
+}
+template <typename L, int S, bool FWD>
+static fhe_status launch_fast_column_s(fhe_ctx* ctx, FastArgs<L>& a) {
+    const unsigned long long total = (unsigned long long)a.n_polys << (a.log_n - S);
+    const unsigned long long grid = std::min<unsigned long long>((total + 255) / 256, (unsigned long long)ctx->sm_count * 32);
+    if (grid == 0) return FHE_OK;
+    ntt_fast_column_kernel<L, S, FWD><<<(unsigned)grid, 256, 0, ctx->stream>>>(a);
+    return after_launch(ctx, FWD ? "ntt_fast_column_kernel<fwd>" : "ntt_fast_column_kernel<inv>");
+}
+template <typename L, bool FWD>
+static fhe_status launch_fast_column(fhe_ctx* ctx, FastArgs<L>& a, int S) {
+    switch (S) {
+        case 1: return launch_fast_column_s<L, 1, FWD>(ctx, a);
+        case 2: return launch_fast_column_s<L, 2, FWD>(ctx, a);
+        case 3: return launch_fast_column_s<L, 3, FWD>(ctx, a);
+        case 4: return launch_fast_column_s<L, 4, FWD>(ctx, a);
+        default: return fail(ctx, FHE_EUNSUPPORTED, "fast NTT: column transform of 2^%d rows not instantiated", S);
+    }
+}
+
+// returns FHE_EUNSUPPORTED (without touching ctx->err) when the fast path does not apply
+template <typename L>
+static fhe_status launch_ntt_fast(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys,
+                                  const typename L::W* d_src, typename L::W* d_a, bool fwd) {
+    if (log_n < 9 || log_n > 17 || nl == 0) return FHE_EUNSUPPORTED;
+    for (size_t i = 0; i < nl; ++i)
+        if (!fast_modulus_ok<L>(qs[i])) return FHE_EUNSUPPORTED;
+    if (n_polys == 0) return FHE_OK;
+    if (n_polys > 0x7FFFFFFFull) return fail(ctx, FHE_EINVAL, "batch too large");
+    const int logt = log_n <= 13 ? (int)log_n : (log_n == 17 ? 13 : 12);
+    const int S = (int)log_n - logt;
+    FastArgs<L> a;
+    a.data = d_a;
+    a.in = d_src ? d_src : d_a;
+    FHE_CHECK(get_fast_limbs<L>(ctx, qs, nl, log_n, &a.limbs));
+    a.nl = (uint32_t)nl;
+    a.n_polys = (uint32_t)n_polys;
+    a.log_n = (int)log_n;
+    a.s0 = S;
+    a.n_items = (unsigned long long)n_polys << S;
+    a.pre_red = 0;
+    if (L::BITS == 32 && fwd) {
+        const int mask = fast_plan_prered32(logt, 1 + 2 * S);
+        if (mask < 0) return FHE_EUNSUPPORTED;
+        a.pre_red = (uint32_t)mask;
+    }
+    if (fwd) {
+        if (S > 0) {
+            FHE_CHECK((launch_fast_column<L, true>(ctx, a, S)));
+            a.in = a.data;
+        }
+        return launch_fast_tile_logt<L, true, true>(ctx, a, logt);
+    }
+    if (S == 0) return launch_fast_tile_logt<L, false, true>(ctx, a, logt);
+    FHE_CHECK((launch_fast_tile_logt<L, false, false>(ctx, a, logt)));
+    a.in = a.data;
+    return launch_fast_column<L, false>(ctx, a, S);
+}
+
+fhe_status launch_ntt_fast_u64(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys, const uint64_t* d_src,
+                               uint64_t* d_a, bool fwd) {
+    return launch_ntt_fast<Lz64>(ctx, qs, nl, log_n, n_polys, d_src, d_a, fwd);
+}
+fhe_status launch_ntt_fast_u32(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys, const uint32_t* d_src,
+                               uint32_t* d_a, bool fwd) {
+    return launch_ntt_fast<Lz32>(ctx, qs, nl, log_n, n_polys, d_src, d_a, fwd);
+}
+
+}  // namespace fhe

@@ -1,5 +1,6 @@
 // Launch logic + C ABI for the batched negacyclic NTT (fhe_ntt_*), host-slice wrappers included.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ctx.cuh"
 #include "ntt_kernels.cuh"
@@ -95,11 +96,49 @@ static fhe_status launch_ntt(fhe_ctx* ctx, uint64_t q, unsigned log_n, size_t ba
     }
 }
 
+static bool g_force_generic = false;  // FHE_B200_NTT_GENERIC=1: always use the first-generation kernels (A/B tests)
+static bool use_fast() {
+    static bool init = false;
+    if (!init) {
+        const char* e = getenv("FHE_B200_NTT_GENERIC");
+        g_force_generic = e && e[0] == '1';
+        init = true;
+    }
+    return !g_force_generic;
+}
+
 fhe_status launch_ntt_u64(fhe_ctx* ctx, uint64_t q, unsigned log_n, size_t batch, uint64_t* d_a, bool fwd) {
+    if (use_fast()) {
+        fhe_status st = launch_ntt_fast_u64(ctx, &q, 1, log_n, batch, nullptr, d_a, fwd);
+        if (st != FHE_EUNSUPPORTED) return st;
+    }
     return launch_ntt<Mod64>(ctx, q, log_n, batch, d_a, fwd);
 }
 fhe_status launch_ntt_u32(fhe_ctx* ctx, uint32_t q, unsigned log_n, size_t batch, uint32_t* d_a, bool fwd) {
+    if (use_fast()) {
+        uint64_t q64 = q;
+        fhe_status st = launch_ntt_fast_u32(ctx, &q64, 1, log_n, batch, nullptr, d_a, fwd);
+        if (st != FHE_EUNSUPPORTED) return st;
+    }
     return launch_ntt<Mod32>(ctx, q, log_n, batch, d_a, fwd);
+}
+fhe_status launch_ntt_rns_u64(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys, uint64_t* d_a, bool fwd) {
+    return launch_ntt_rns_u64_oop(ctx, qs, nl, log_n, n_polys, nullptr, d_a, fwd);
+}
+fhe_status launch_ntt_rns_u64_oop(fhe_ctx* ctx, const uint64_t* qs, size_t nl, unsigned log_n, size_t n_polys, const uint64_t* d_src,
+                                  uint64_t* d_a, bool fwd) {
+    if (n_polys == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, nl > 0 && n_polys % nl == 0, "polynomial count %zu is not a multiple of the limb count %zu", n_polys, nl);
+    if (use_fast()) {
+        fhe_status st = launch_ntt_fast_u64(ctx, qs, nl, log_n, n_polys, d_src, d_a, fwd);
+        if (st != FHE_EUNSUPPORTED) return st;
+    }
+    if (d_src && d_src != d_a)
+        FHE_CUDA(ctx, cudaMemcpyAsync(d_a, d_src, (n_polys << log_n) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    // generic kernels take one modulus per launch
+    for (size_t b = 0; b < n_polys / nl; ++b)
+        for (size_t i = 0; i < nl; ++i) FHE_CHECK(launch_ntt<Mod64>(ctx, qs[i], log_n, 1, d_a + ((b * nl + i) << log_n), fwd));
+    return FHE_OK;
 }
 
 static bool pow2_log(size_t n, unsigned* lg) {
@@ -146,20 +185,14 @@ fhe_status fhe_ntt_inv_u32(fhe_ctx* ctx, uint32_t q, unsigned log_n, size_t batc
     if (!ctx) return FHE_EINVAL;
     return launch_ntt_u32(ctx, q, log_n, batch, d_a, false);
 }
-// [batch][limbs][n]: one launch per limb over a strided view is avoided by transforming limb-major batches:
-// polynomial (b, i) sits at ((b*limbs)+i)*n, so limb i of every batch element is NOT contiguous; we launch per
-// (limb) with batch=1 stride handling only when batch == 1, else per polynomial group.  Simple and correct first:
+// [batch][limbs][n]: polynomial p = b*limbs + i uses modulus qs[p % limbs]; one launch for the whole batch
 fhe_status fhe_ntt_fwd_rns(fhe_ctx* ctx, const uint64_t* qs, size_t limbs, unsigned log_n, size_t batch, uint64_t* d_a) {
     if (!ctx || !qs) return FHE_EINVAL;
-    for (size_t b = 0; b < batch; ++b)
-        for (size_t i = 0; i < limbs; ++i) FHE_CHECK(launch_ntt_u64(ctx, qs[i], log_n, 1, d_a + ((b * limbs + i) << log_n), true));
-    return FHE_OK;
+    return launch_ntt_rns_u64(ctx, qs, limbs, log_n, batch * limbs, d_a, true);
 }
 fhe_status fhe_ntt_inv_rns(fhe_ctx* ctx, const uint64_t* qs, size_t limbs, unsigned log_n, size_t batch, uint64_t* d_a) {
     if (!ctx || !qs) return FHE_EINVAL;
-    for (size_t b = 0; b < batch; ++b)
-        for (size_t i = 0; i < limbs; ++i) FHE_CHECK(launch_ntt_u64(ctx, qs[i], log_n, 1, d_a + ((b * limbs + i) << log_n), false));
-    return FHE_OK;
+    return launch_ntt_rns_u64(ctx, qs, limbs, log_n, batch * limbs, d_a, false);
 }
 fhe_status fhe_ntt_fwd_host(fhe_ctx* ctx, uint64_t q, uint64_t* a, size_t n, size_t batch) {
     if (!ctx || !a) return FHE_EINVAL;

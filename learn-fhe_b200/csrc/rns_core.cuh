@@ -1,0 +1,115 @@
+// RNS base conversion / rescale building blocks (K14/K15 of SURVEY.md §2), __host__ __device__.
+// Reference: util/src/ring/rns.rs — Rns::new/with_ps (287-322), Rns::extend_bases (331-345), RnsRq::rescale_k / round / div
+// (99-132).  All integer results are canonical residues, so any exact evaluation order is bit-identical; the only
+// order-sensitive part is the f64 overflow estimate u = round(sum_i (1/q_i) * v_i), which is evaluated exactly like the
+// reference: sequential sum from 0.0, i ascending, separate multiply and add (no FMA).
+#pragma once
+#include "fhew_core.cuh"  // f64 helpers
+#include "modarith.cuh"
+
+namespace fhe {
+
+static constexpr int RNS_MAXL = 16;  // max source limbs of one base conversion (kept in registers)
+
+// device-side view of one (source base qs -> target base ps) conversion table
+struct RnsExtTab {
+    int nq, np;
+    const Mod64* mq;           // [nq]
+    const uint64_t* qhat_inv;  // [nq]  (Q/q_i)^-1 mod q_i, with Shoup companion in qhat_inv_sh
+    const uint64_t* qhat_inv_sh;
+    const double* frac;        // [nq]  1.0 / q_i
+    const Mod64* mp;           // [np]
+    const uint64_t* qhat_ps;   // [np][nq]   (Q/q_i) mod p_k
+    const uint64_t* uq_ps;     // [np][nq+1] (u*Q) mod p_k
+};
+
+// rescale_k (rns.rs:99-132) over moduli kept (l) ++ dropped (k)
+struct RescaleTab {
+    RnsExtTab ext;  // dropped -> kept (unused when k == 1)
+    int l, k;
+    const Mod64* m_all;     // [l + k]
+    const uint64_t* ph;     // [l + k]  (P >> 1) mod q_i, P = prod(dropped)
+    const uint64_t* pinv;   // [l]      P^-1 mod q_i (+ Shoup companion)
+    const uint64_t* pinv_sh;
+};
+
+// v mod m.q for an arbitrary 64-bit v
+HD uint64_t rns_reduce_u64(const Mod64& m, uint64_t v) {
+    if (v < m.q) return v;
+    if (m.s >= 32) {
+        U128 x;
+        x.lo = v;
+        x.hi = 0;
+        return m.reduce128(x);
+    }
+    return v % m.q;
+}
+HD double f64_add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+HD double u64_to_f64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __ull2double_rn(v);
+#else
+    return (double)v;
+#endif
+}
+
+// Rns::extend_bases for one coefficient (rns.rs:331-345): x[i] = residue mod q_i (i < nq) -> y[k] = residue mod p_k.
+// `emit(k, y)` receives the outputs.
+template <typename Emit>
+HD void rns_extend_coeff(const RnsExtTab& T, const uint64_t* x /* [RNS_MAXL], first nq valid */, Emit emit) {
+    uint64_t v[RNS_MAXL];
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < RNS_MAXL; ++i) {
+        if (i < T.nq) {
+            const Mod64 m = T.mq[i];
+            v[i] = m.redq(m.shoup_lazy(x[i], T.qhat_inv[i], T.qhat_inv_sh[i]));
+            acc = f64_add_rn(acc, f64_mul_rn(T.frac[i], u64_to_f64(v[i])));
+        } else {
+            v[i] = 0;
+        }
+    }
+    const uint32_t u = (uint32_t)f64_round_half_away(acc);
+    for (int k = 0; k < T.np; ++k) {
+        const Mod64 m = T.mp[k];
+        const uint64_t* qh = T.qhat_ps + (size_t)k * T.nq;
+        uint64_t s = 0;
+#pragma unroll
+        for (int i = 0; i < RNS_MAXL; ++i) {
+            if (i < T.nq) s = m.add(s, m.mul(qh[i], rns_reduce_u64(m, v[i])));
+        }
+        emit(k, m.sub(s, T.uq_ps[(size_t)k * (T.nq + 1) + u]));
+    }
+}
+
+// rescale_k for one coefficient: x(i) reads limb i of the input (already including any pre-addend, canonical);
+// emit(i, y) receives the kept limbs before any post-addend.
+template <typename Load, typename Emit>
+HD void rns_rescale_coeff(const RescaleTab& R, Load x, Emit emit) {
+    const int l = R.l, k = R.k;
+    // round(): s_i = x_i + (P >> 1) mod q_i, for every limb (rns.rs:120-125)
+    auto rounded = [&](int i) { return R.m_all[i].add(x(i), R.ph[i]); };
+    auto finish = [&](int i, uint64_t sub) {
+        const Mod64 m = R.m_all[i];
+        const uint64_t v = m.sub(rounded(i), sub);
+        emit(i, m.redq(m.shoup_lazy(v, R.pinv[i], R.pinv_sh[i])));  // div(): * P^-1 (rns.rs:127-132)
+    };
+    if (k == 1) {
+        const uint64_t vp = rounded(l);  // non-centred value of the dropped limb (rns.rs:109-111)
+        for (int i = 0; i < l; ++i) finish(i, rns_reduce_u64(R.m_all[i], vp));
+    } else {
+        uint64_t xs[RNS_MAXL];
+#pragma unroll
+        for (int j = 0; j < RNS_MAXL; ++j) xs[j] = j < k ? rounded(l + j) : 0;
+        rns_extend_coeff(R.ext, xs, [&](int i, uint64_t y) { finish(i, y); });
+    }
+}
+
+}  // namespace fhe

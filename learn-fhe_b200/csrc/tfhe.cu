@@ -1,0 +1,485 @@
+// TFHE programmable bootstrapping on sm_100a (K7, K11 (T64 form), K13 of SURVEY.md §2).
+//
+//   tfhe_fft_mul_kernel        `Rt *= &Rt` (util/src/ring.rs:315-320 -> ring/fft/c64.rs:11-56): one CTA per product
+//   tfhe_key_fft_kernel        one-time conversion of TGGSW key polynomials to the twisted Fourier domain (c64.rs:20-28 + fft)
+//   tfhe_blind_rotate_kernel   persistent CTA per ciphertext: mod_switch, acc = (0, lut).rotate(-b~), n CMUX steps with the
+//                              accumulator, digit spectra and products resident in shared memory, bsk rows streamed from
+//                              L2; epilogue sample_extract(0)          (tfhe/bootstrapping.rs:84-104, tggsw.rs:100-121,
+//                                                                         tglwe.rs:61-66,115-127)
+//   tfhe_ext_kernel            one Tggsw::external_product per TGLWE (parity tests / util-level callers)
+//   tlwe_digits_kernel +
+//   tlwe_key_switch_kernel     Tlwe::key_switch (tlwe.rs:144-153): signed digits (limb-major) x ksk, wrapping u64 GEMM
+// All per-thread logic lives in tfhe_core.cuh (shared with tests/hostsim).  The product path is the reference's own
+// floating-point algorithm evaluated in the same operation order: results are bit-identical, not merely within the
+// error bound of c64.rs:186-208.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "ctx.cuh"
+#include "tfhe_core.cuh"
+
+struct fhe_tfhe_key {
+    fhe_tfhe_param param;
+    fhe::TfheDev P;
+    fhe::DecompT64 ks_dec;
+    void* d_brk = nullptr;  // Cx [n][(k+1)d][(k+1)][N/2]
+    void* d_ksk = nullptr;  // u64 [(kN) d_ks][n+1]
+    size_t brk_bytes = 0, ksk_bytes = 0;
+};
+
+namespace fhe {
+
+static constexpr int TFHE_THREADS = 256;
+static constexpr int KS_G = 16;     // ciphertexts per key-switch CTA
+static constexpr int KS_COLS = 128; // output columns per key-switch CTA
+static constexpr int KS_CH = 256;   // digit rows staged in shared memory per iteration
+
+// f64 tables of ring degree n = 2^log_n, computed on the host exactly like compute_twiddle (c64.rs:98-108):
+// cis((i as f64 * PI) / n as f64)
+fhe_status get_fft_tab(fhe_ctx* ctx, unsigned log_n, FftTab* out) {
+    FHE_REQUIRE(ctx, log_n >= 1 && log_n <= 13, "f64 FFT path supports ring degrees 2..8192");
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const size_t n = (size_t)1 << log_n, m = n / 2, mb = std::max<size_t>(m / 2, 1);
+    auto it = ctx->fft_tables.find((int)log_n);
+    if (it == ctx->fft_tables.end()) {
+        std::vector<Cx> h(2 * m + 2 * mb);
+        for (size_t j = 0; j < m; ++j) {
+            volatile double num = (double)j * M_PI;
+            const double ang = num / (double)n;
+            h[j] = Cx{std::cos(ang), std::sin(ang)};
+            h[m + j] = Cx{h[j].re, -h[j].im};
+        }
+        // chunk twiddles: bit-reversed cis(i*pi/m), i < m; only the first m/2 entries are ever indexed
+        unsigned lgm = 0;
+        while (((size_t)1 << lgm) < m) ++lgm;
+        for (size_t c = 0; c < mb; ++c) {
+            size_t i = 0;
+            for (unsigned b = 0; b < lgm; ++b)
+                if (c & ((size_t)1 << b)) i |= (size_t)1 << (lgm - 1 - b);
+            volatile double num = (double)i * M_PI;
+            const double ang = num / (double)m;
+            const Cx t{std::cos(ang), std::sin(ang)};
+            h[2 * m + c] = t;
+            h[2 * m + mb + c] = Cx{t.re, -t.im};
+        }
+        void* d = nullptr;
+        FHE_CUDA(ctx, cudaMalloc(&d, h.size() * sizeof(Cx)));
+        FHE_CUDA(ctx, cudaMemcpy(d, h.data(), h.size() * sizeof(Cx), cudaMemcpyHostToDevice));
+        it = ctx->fft_tables.emplace((int)log_n, std::make_pair(d, h.size() * sizeof(Cx))).first;
+    }
+    const Cx* base = (const Cx*)it->second.first;
+    out->lg = (int)log_n - 1;
+    out->tw = base;
+    out->tw_inv = base + m;
+    out->tw_bo = base + 2 * m;
+    out->tw_inv_bo = base + 2 * m + mb;
+    out->m_inv = 1.0 / (double)m;
+    return FHE_OK;
+}
+
+#define TFHE_RUN                                        \
+    auto run = [&](auto phase) {                        \
+        phase((uint32_t)threadIdx.x, (uint32_t)blockDim.x); \
+        __syncthreads();                                \
+    }
+
+// a <- a * b over T64[X]/(X^n + 1)   (c64.rs:43-56)
+__global__ void __launch_bounds__(TFHE_THREADS) tfhe_fft_mul_kernel(FftTab T, unsigned long long batch, uint64_t* __restrict__ a,
+                                                                     const uint64_t* __restrict__ b) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx* s = reinterpret_cast<Cx*>(smem_raw);
+    const uint32_t m = 1u << T.lg;
+    TFHE_RUN;
+    for (unsigned long long item = blockIdx.x; item < batch; item += gridDim.x) {
+        uint64_t* pa = a + item * 2ull * m;
+        const uint64_t* pb = b + item * 2ull * m;
+        run([&](uint32_t tid, uint32_t nthr) {
+            fft_twist_in(s, T, [&](uint32_t c) { return pa[c]; }, tid, nthr);
+            fft_twist_in(s + m, T, [&](uint32_t c) { return pb[c]; }, tid, nthr);
+        });
+        fft_run<true>(s, 2, T, run);
+        run([&](uint32_t tid, uint32_t nthr) {
+            for (uint32_t p = tid; p < m; p += nthr) s[swz_cx(p)] = cx_mul(s[swz_cx(p)], s[m + swz_cx(p)]);
+        });
+        fft_run<false>(s, 1, T, run);
+        run([&](uint32_t tid, uint32_t nthr) {
+            for (uint32_t p = tid; p < m; p += nthr) {
+                uint64_t lo, hi;
+                fft_untwist_out(s, T, p, lo, hi);
+                pa[p] = lo;
+                pa[p + m] = hi;
+            }
+        });
+    }
+}
+
+// polys [count][n] u64 -> spectra [count][n/2] Cx (logical index order = fft_in_place output order)
+__global__ void __launch_bounds__(TFHE_THREADS) tfhe_key_fft_kernel(FftTab T, unsigned long long count, const uint64_t* __restrict__ polys,
+                                                                     Cx* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx* s = reinterpret_cast<Cx*>(smem_raw);
+    const uint32_t m = 1u << T.lg;
+    TFHE_RUN;
+    for (unsigned long long item = blockIdx.x; item < count; item += gridDim.x) {
+        const uint64_t* p = polys + item * 2ull * m;
+        run([&](uint32_t tid, uint32_t nthr) { fft_twist_in(s, T, [&](uint32_t c) { return p[c]; }, tid, nthr); });
+        fft_run<true>(s, 1, T, run);
+        run([&](uint32_t tid, uint32_t nthr) {
+            for (uint32_t i = tid; i < m; i += nthr) out[item * m + i] = s[swz_cx(i)];
+        });
+    }
+}
+
+// blind_rotate + sample_extract(0): ct_in [count][n_lwe+1] -> out [count][kN+1]
+__global__ void __launch_bounds__(TFHE_THREADS) tfhe_blind_rotate_kernel(TfheDev P, const uint64_t* __restrict__ lut,
+                                                                          const uint64_t* __restrict__ ct_in, unsigned long long count,
+                                                                          uint64_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t n = 1u << P.log_n, k = P.k, d = P.bs_dec.d;
+    uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);
+    Cx* F = reinterpret_cast<Cx*>(acc + (size_t)(k + 1) * n);
+    Cx* Pb = F + (size_t)(k + 1) * d * (n / 2);
+    const uint32_t rb = 64 - (P.log_n + 1);  // tfhe/bootstrapping.rs:99-104
+    TFHE_RUN;
+    for (unsigned long long ct = blockIdx.x; ct < count; ct += gridDim.x) {
+        const uint64_t* src = ct_in + ct * (P.n_lwe + 1);
+        const uint32_t bt = (uint32_t)t64_rounding_shr_dev(src[P.n_lwe], rb) & (2 * n - 1);
+        const uint32_t e0 = (2 * n - bt) & (2 * n - 1);  // rotate(-b~)
+        run([&](uint32_t tid, uint32_t nthr) {
+            for (uint32_t c = tid; c < n; c += nthr) {
+                for (uint32_t j = 0; j < k; ++j) acc[(size_t)j * n + c] = 0;
+                acc[(size_t)k * n + c] = t64_rot_coef(lut, n, e0, c);
+            }
+        });
+        for (uint32_t i = 0; i < P.n_lwe; ++i) {
+            const uint32_t e = (uint32_t)t64_rounding_shr_dev(src[i], rb) & (2 * n - 1);
+            if (e == 0) continue;  // rotate(0) - acc = 0: the external product of zero is exactly zero
+            tfhe_cmux_step(P, acc, F, Pb, i, e, run);
+        }
+        // Tglwe::sample_extract(ct, 0) (tglwe.rs:115-127)
+        uint64_t* o = out + ct * ((unsigned long long)k * n + 1);
+        for (uint32_t c = threadIdx.x; c < k * n; c += blockDim.x) {
+            const uint32_t j = c >> P.log_n, x = c & (n - 1);
+            o[c] = x == 0 ? acc[(size_t)j * n] : (uint64_t)(0 - acc[(size_t)j * n + (n - x)]);
+        }
+        if (threadIdx.x == 0) o[(size_t)k * n] = acc[(size_t)k * n];
+        __syncthreads();
+    }
+}
+
+// Tggsw::external_product(brk[idx[c]], glwe_c): glwe [count][k+1][N]
+__global__ void __launch_bounds__(TFHE_THREADS) tfhe_ext_kernel(TfheDev P, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ in,
+                                                                 unsigned long long count, uint64_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t n = 1u << P.log_n, k = P.k, d = P.bs_dec.d;
+    uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);
+    Cx* F = reinterpret_cast<Cx*>(acc + (size_t)(k + 1) * n);
+    Cx* Pb = F + (size_t)(k + 1) * d * (n / 2);
+    TFHE_RUN;
+    for (unsigned long long c = blockIdx.x; c < count; c += gridDim.x) {
+        const uint64_t* g = in + c * (unsigned long long)(k + 1) * n;
+        uint64_t* o = out + c * (unsigned long long)(k + 1) * n;
+        const Cx* key = P.brk + (((size_t)idx[c] * (k + 1) * d * (k + 1)) << P.fft.lg);
+        tfhe_external_product(
+            P, F, Pb, key, [&](uint32_t j, uint32_t x) { return g[(size_t)j * n + x]; },
+            [&](uint32_t oo, uint32_t c0, uint64_t v0, uint32_t c1, uint64_t v1) {
+                o[(size_t)oo * n + c0] = v0;
+                o[(size_t)oo * n + c1] = v1;
+            },
+            run);
+    }
+}
+
+// signed digits of the mask of `count` ciphertexts [count][len+1], limb-major (index = digit*len + coefficient,
+// tlwe.rs:106,149), packed for the GEMM kernel as dig[group][index][KS_G] (missing ciphertexts of the last group = 0)
+__global__ void __launch_bounds__(256) tlwe_digits_kernel(DecompT64 dp, uint32_t len, unsigned long long count, const uint64_t* __restrict__ ct,
+                                                          int32_t* __restrict__ dig) {
+    const unsigned long long groups = (count + KS_G - 1) / KS_G;
+    const unsigned long long total = groups * len * KS_G, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint64_t mask = (1ull << dp.log_b) - 1;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const uint32_t g = (uint32_t)(t % KS_G);
+        const unsigned long long r = t / KS_G;
+        const uint32_t coef = (uint32_t)(r % len);
+        const unsigned long long grp = r / len;
+        const unsigned long long c = grp * KS_G + g;
+        uint64_t v = c < count ? t64_rounding_shr_dev(ct[c * (len + 1) + coef], dp.rounding_bits) : 0;
+        for (uint32_t k = 0; k < dp.d; ++k) {
+            const uint64_t limb = v & mask;
+            v >>= dp.log_b;
+            const uint64_t carry = (((limb - 1) | v) & limb) >> (dp.log_b - 1);
+            v += carry;
+            dig[((grp * dp.d + k) * len + coef) * KS_G + g] = (int32_t)(int64_t)(limb - (carry << dp.log_b));
+        }
+    }
+}
+// out[c][j] = sum_idx ksk[idx][j] * dig[c][idx] (+ b_in for the body column j == n_out), wrapping mod 2^64
+__global__ void __launch_bounds__(KS_COLS) tlwe_key_switch_kernel(uint32_t rows /* len * d */, uint32_t n_out, uint32_t len,
+                                                                   unsigned long long count, const int32_t* __restrict__ dig,
+                                                                   const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ ct_in,
+                                                                   uint64_t* __restrict__ out) {
+    __shared__ __align__(16) int32_t sd[KS_CH * KS_G];
+    const uint32_t j = blockIdx.x * KS_COLS + threadIdx.x, ld = n_out + 1;
+    const unsigned long long grp = blockIdx.y;
+    const int32_t* gd = dig + grp * (unsigned long long)rows * KS_G;
+    uint64_t acc[KS_G];
+#pragma unroll
+    for (int g = 0; g < KS_G; ++g) acc[g] = 0;
+    for (uint32_t base = 0; base < rows; base += KS_CH) {
+        const uint32_t chunk = min((uint32_t)KS_CH, rows - base);
+        for (uint32_t t = threadIdx.x; t < chunk * KS_G / 4; t += blockDim.x)
+            reinterpret_cast<int4*>(sd)[t] = reinterpret_cast<const int4*>(gd + (size_t)base * KS_G)[t];
+        __syncthreads();
+        if (j < ld) {
+#pragma unroll 4
+            for (uint32_t r = 0; r < chunk; ++r) {
+                const uint64_t kv = ksk[(size_t)(base + r) * ld + j];
+                const int4* row = reinterpret_cast<const int4*>(sd + r * KS_G);
+#pragma unroll
+                for (int q4 = 0; q4 < KS_G / 4; ++q4) {
+                    const int4 dv = row[q4];
+                    acc[4 * q4 + 0] += kv * (uint64_t)(int64_t)dv.x;
+                    acc[4 * q4 + 1] += kv * (uint64_t)(int64_t)dv.y;
+                    acc[4 * q4 + 2] += kv * (uint64_t)(int64_t)dv.z;
+                    acc[4 * q4 + 3] += kv * (uint64_t)(int64_t)dv.w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (j < ld) {
+#pragma unroll
+        for (int g = 0; g < KS_G; ++g) {
+            const unsigned long long c = grp * KS_G + g;
+            if (c < count) {
+                uint64_t v = acc[g];
+                if (j == n_out) v += ct_in[c * (len + 1) + len];
+                out[c * ld + j] = v;
+            }
+        }
+    }
+}
+
+template <typename K>
+static fhe_status tfhe_grid(fhe_ctx* ctx, K kern, size_t smem, unsigned long long items, unsigned* grid) {
+    FHE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    int occ = 0;
+    FHE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TFHE_THREADS, smem));
+    if (occ < 1) return fail(ctx, FHE_EUNSUPPORTED, "TFHE kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+    *grid = (unsigned)std::min<unsigned long long>(items, (unsigned long long)ctx->sm_count * occ);
+    return FHE_OK;
+}
+
+static fhe_status run_key_switch(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t count, const uint64_t* d_in, uint64_t* d_out) {
+    const fhe_tfhe_param& pp = key->param;
+    const uint32_t len = pp.k << pp.log_big_n, rows = len * pp.ks_d;
+    const size_t groups = (count + KS_G - 1) / KS_G;
+    void* scratch;
+    FHE_CHECK(ensure_scratch(ctx, groups * rows * KS_G * sizeof(int32_t), &scratch));
+    const unsigned long long total = (unsigned long long)groups * len * KS_G;
+    const unsigned dgrid = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)ctx->sm_count * 16);
+    tlwe_digits_kernel<<<dgrid, 256, 0, ctx->stream>>>(key->ks_dec, len, count, d_in, (int32_t*)scratch);
+    FHE_CHECK(after_launch(ctx, "tlwe_digits_kernel"));
+    FHE_REQUIRE(ctx, groups <= 65535, "key-switch batch too large for one launch (max %d ciphertexts)", 65535 * KS_G);
+    dim3 grid((pp.n + 1 + KS_COLS - 1) / KS_COLS, (unsigned)groups);
+    tlwe_key_switch_kernel<<<grid, KS_COLS, 0, ctx->stream>>>(rows, pp.n, len, count, (const int32_t*)scratch, (const uint64_t*)key->d_ksk, d_in,
+                                                              d_out);
+    return after_launch(ctx, "tlwe_key_switch_kernel");
+}
+
+static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_tfhe_key* key, const uint64_t* d_lut, size_t count, const uint64_t* d_in,
+                                   uint64_t* d_out) {
+    const size_t smem = tfhe_smem_bytes(key->P.k, key->P.bs_dec.d, key->P.log_n);
+    unsigned grid;
+    FHE_CHECK(tfhe_grid(ctx, tfhe_blind_rotate_kernel, smem, count, &grid));
+    tfhe_blind_rotate_kernel<<<grid, TFHE_THREADS, smem, ctx->stream>>>(key->P, d_lut, d_in, count, d_out);
+    return after_launch(ctx, "tfhe_blind_rotate_kernel");
+}
+
+}  // namespace fhe
+
+using namespace fhe;
+
+extern "C" {
+
+fhe_status fhe_fft64_negacyclic_mul(fhe_ctx* ctx, unsigned log_n, size_t batch, uint64_t* d_a, const uint64_t* d_b) {
+    if (!ctx) return FHE_EINVAL;
+    if (batch == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_a && d_b, "null pointer");
+    if (log_n == 0) {  // c64.rs:12-15: a[0] *= b[0]
+        std::vector<uint64_t> ha(batch), hb(batch);
+        FHE_CUDA(ctx, cudaMemcpyAsync(ha.data(), d_a, batch * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FHE_CUDA(ctx, cudaMemcpyAsync(hb.data(), d_b, batch * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < batch; ++i) ha[i] *= hb[i];
+        FHE_CUDA(ctx, cudaMemcpyAsync(d_a, ha.data(), batch * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return FHE_OK;
+    }
+    FftTab T;
+    FHE_CHECK(get_fft_tab(ctx, log_n, &T));
+    const size_t smem = ((size_t)2 << T.lg) * sizeof(Cx);
+    unsigned grid;
+    FHE_CHECK(tfhe_grid(ctx, tfhe_fft_mul_kernel, smem, batch, &grid));
+    tfhe_fft_mul_kernel<<<grid, TFHE_THREADS, smem, ctx->stream>>>(T, batch, d_a, d_b);
+    return after_launch(ctx, "tfhe_fft_mul_kernel");
+}
+
+fhe_status fhe_fft64_negacyclic_mul_host(fhe_ctx* ctx, uint64_t* a, const uint64_t* b, size_t n, size_t batch) {
+    if (!ctx || !a || !b) return FHE_EINVAL;
+    FHE_REQUIRE(ctx, n >= 1 && (n & (n - 1)) == 0, "polynomial length %zu is not a power of two", n);
+    if (batch == 0) return FHE_OK;
+    unsigned lg = 0;
+    while (((size_t)1 << lg) < n) ++lg;
+    const size_t bytes = n * batch * 8;
+    void *da, *db;
+    FHE_CHECK(ensure_stage_d(ctx, 0, bytes, &da));
+    FHE_CHECK(ensure_stage_d(ctx, 1, bytes, &db));
+    FHE_CUDA(ctx, cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CUDA(ctx, cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CHECK(fhe_fft64_negacyclic_mul(ctx, lg, batch, (uint64_t*)da, (const uint64_t*)db));
+    FHE_CUDA(ctx, cudaMemcpyAsync(a, da, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FHE_OK;
+}
+
+fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uint64_t* brk, const uint64_t* ksk_a, const uint64_t* ksk_b,
+                               fhe_tfhe_key** out) {
+    if (!ctx || !pp || !out) return FHE_EINVAL;
+    *out = nullptr;
+    FHE_REQUIRE(ctx, brk && ksk_a && ksk_b, "null key pointer");
+    FHE_REQUIRE(ctx, pp->log_big_n >= 1 && pp->log_big_n <= 12, "TFHE ring degree 2^%u out of range (2..4096)", pp->log_big_n);
+    FHE_REQUIRE(ctx, pp->k >= 1 && pp->k <= 4, "GLWE dimension k must be in [1, 4]");
+    FHE_REQUIRE(ctx, pp->n >= 1 && pp->n <= 65535, "TLWE dimension out of range");
+    FHE_REQUIRE(ctx, pp->bs_log_b >= 1 && pp->bs_d >= 1 && pp->bs_log_b * pp->bs_d <= 64 && pp->bs_log_b <= 52,
+                "TGGSW decomposor out of range (log_b * d <= 64)");
+    FHE_REQUIRE(ctx, pp->ks_log_b >= 1 && pp->ks_d >= 1 && pp->ks_log_b * pp->ks_d <= 64 && pp->ks_log_b <= 31,
+                "TLWE key-switch decomposor out of range (log_b <= 31, log_b * d <= 64)");
+    FHE_REQUIRE(ctx, pp->log_p + pp->padding < 64, "log_p + padding must be < 64");
+    const size_t n = (size_t)1 << pp->log_big_n, m = n / 2;
+    const size_t smem = tfhe_smem_bytes(pp->k, pp->bs_d, (int)pp->log_big_n);
+    FHE_REQUIRE(ctx, smem <= 220 * 1024, "TFHE parameters need %zu bytes of shared memory per ciphertext (max 220 KiB)", smem);
+    fhe_tfhe_key* key = new fhe_tfhe_key();
+    key->param = *pp;
+    key->ks_dec = make_decomp_t64(pp->ks_log_b, pp->ks_d);
+    TfheDev& P = key->P;
+    P.log_n = (int)pp->log_big_n;
+    P.k = pp->k;
+    P.n_lwe = pp->n;
+    P.bs_dec = make_decomp_t64(pp->bs_log_b, pp->bs_d);
+    fhe_status st = get_fft_tab(ctx, pp->log_big_n, &P.fft);
+    // brk: [n][(k+1)d][(k+1)][N] torus words -> Fourier domain
+    const size_t polys = (size_t)pp->n * (pp->k + 1) * pp->bs_d * (pp->k + 1);
+    uint64_t* d_tmp = nullptr;
+    if (st == FHE_OK && cudaMalloc((void**)&d_tmp, polys * n * 8) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "bsk staging alloc");
+    key->brk_bytes = polys * m * sizeof(Cx);
+    if (st == FHE_OK && cudaMalloc(&key->d_brk, key->brk_bytes) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "bsk alloc");
+    if (st == FHE_OK && cudaMemcpyAsync(d_tmp, brk, polys * n * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        st = fail(ctx, FHE_ECUDA, "bsk upload");
+    if (st == FHE_OK) {
+        unsigned grid;
+        st = tfhe_grid(ctx, tfhe_key_fft_kernel, m * sizeof(Cx), polys, &grid);
+        if (st == FHE_OK) {
+            tfhe_key_fft_kernel<<<grid, TFHE_THREADS, m * sizeof(Cx), ctx->stream>>>(P.fft, polys, d_tmp, (Cx*)key->d_brk);
+            st = after_launch(ctx, "tfhe_key_fft_kernel");
+        }
+    }
+    if (st == FHE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, FHE_ECUDA, "bsk transform failed");
+    if (d_tmp) cudaFree(d_tmp);
+    // ksk: [(kN) d_ks][n] + [(kN) d_ks] -> [(kN) d_ks][n+1]
+    if (st == FHE_OK) {
+        const size_t rows = (size_t)pp->k * n * pp->ks_d, ld = pp->n + 1;
+        std::vector<uint64_t> h(rows * ld);
+        for (size_t r = 0; r < rows; ++r) {
+            for (size_t j = 0; j < pp->n; ++j) h[r * ld + j] = ksk_a[r * pp->n + j];
+            h[r * ld + pp->n] = ksk_b[r];
+        }
+        key->ksk_bytes = h.size() * 8;
+        if (cudaMalloc(&key->d_ksk, key->ksk_bytes) != cudaSuccess ||
+            cudaMemcpy(key->d_ksk, h.data(), key->ksk_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            st = fail(ctx, FHE_ECUDA, "ksk upload failed");
+    }
+    if (st != FHE_OK) {
+        fhe_tfhe_key_free(ctx, key);
+        return st;
+    }
+    P.brk = (const Cx*)key->d_brk;
+    *out = key;
+    return FHE_OK;
+}
+
+void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key) {
+    if (!key) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (key->d_brk) cudaFree(key->d_brk);
+    if (key->d_ksk) cudaFree(key->d_ksk);
+    delete key;
+}
+size_t fhe_tfhe_key_bytes(const fhe_tfhe_key* key) { return key ? key->brk_bytes + key->ksk_bytes : 0; }
+fhe_status fhe_tfhe_key_broadcast(fhe_ctx* ctx, fhe_tfhe_key* key, void* nccl_comm, int root) {
+    if (!ctx || !key) return FHE_EINVAL;
+    FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_brk, key->brk_bytes));
+    FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ksk, key->ksk_bytes));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FHE_OK;
+}
+
+fhe_status fhe_tfhe_blind_rotate_extract_batch(fhe_ctx* ctx, const fhe_tfhe_key* key, const uint64_t* d_lut, size_t count,
+                                               const uint64_t* d_ct_in, uint64_t* d_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_lut && d_ct_in && d_out, "null pointer");
+    return run_blind_rotate(ctx, key, d_lut, count, d_ct_in, d_out);
+}
+
+fhe_status fhe_tlwe_key_switch_batch(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t count, const uint64_t* d_ct_in, uint64_t* d_ct_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_ct_in && d_ct_out, "null pointer");
+    return run_key_switch(ctx, key, count, d_ct_in, d_ct_out);
+}
+
+fhe_status fhe_tfhe_pbs_batch(fhe_ctx* ctx, const fhe_tfhe_key* key, const uint64_t* d_lut, size_t count, const uint64_t* d_ct_in,
+                              uint64_t* d_ct_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_lut && d_ct_in && d_ct_out, "null pointer");
+    const size_t ext_words = ((size_t)key->param.k << key->param.log_big_n) + 1;
+    void* mid;
+    FHE_CHECK(ensure_stage_d(ctx, 2, count * ext_words * 8, &mid));
+    FHE_CHECK(run_blind_rotate(ctx, key, d_lut, count, d_ct_in, (uint64_t*)mid));
+    return run_key_switch(ctx, key, count, (const uint64_t*)mid, d_ct_out);
+}
+
+fhe_status fhe_tfhe_pbs_batch_host(fhe_ctx* ctx, const fhe_tfhe_key* key, const uint64_t* lut, size_t count, const uint64_t* ct_in,
+                                   uint64_t* ct_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, lut && ct_in && ct_out, "null pointer");
+    const size_t n = (size_t)1 << key->param.log_big_n, ct_bytes = count * (key->param.n + 1) * 8;
+    void *d_in, *d_out;
+    FHE_CHECK(ensure_stage_d(ctx, 0, ct_bytes + n * 8, &d_in));
+    FHE_CHECK(ensure_stage_d(ctx, 1, ct_bytes, &d_out));
+    uint64_t* d_lut = (uint64_t*)d_in + count * (key->param.n + 1);
+    FHE_CUDA(ctx, cudaMemcpyAsync(d_in, ct_in, ct_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CUDA(ctx, cudaMemcpyAsync(d_lut, lut, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FHE_CHECK(fhe_tfhe_pbs_batch(ctx, key, d_lut, count, (const uint64_t*)d_in, (uint64_t*)d_out));
+    FHE_CUDA(ctx, cudaMemcpyAsync(ct_out, d_out, ct_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FHE_OK;
+}
+
+fhe_status fhe_tfhe_external_product(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t count, const uint32_t* d_idx, const uint64_t* d_glwe_in,
+                                     uint64_t* d_glwe_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_idx && d_glwe_in && d_glwe_out && d_glwe_in != d_glwe_out, "null or aliased pointer");
+    const size_t smem = tfhe_smem_bytes(key->P.k, key->P.bs_dec.d, key->P.log_n);
+    unsigned grid;
+    FHE_CHECK(tfhe_grid(ctx, tfhe_ext_kernel, smem, count, &grid));
+    tfhe_ext_kernel<<<grid, TFHE_THREADS, smem, ctx->stream>>>(key->P, d_idx, d_glwe_in, count, d_glwe_out);
+    return after_launch(ctx, "tfhe_ext_kernel");
+}
+
+}  // extern "C"

@@ -13,6 +13,7 @@
 #include "../../learn-fhe_b200/csrc/host_tables.hpp"
 #include "../../learn-fhe_b200/csrc/modarith.cuh"
 #include "../../learn-fhe_b200/csrc/ntt_core.cuh"
+#include "../../learn-fhe_b200/csrc/ntt_fast.cuh"
 
 using namespace fhe;
 
@@ -150,4 +151,5 @@ unsigned sim_swz64(unsigned p) { return swz<uint64_t>(p); }
 
 }  // extern "C"
 
+#include "hostsim_fast.inc"
 #include "hostsim_fhew.inc"

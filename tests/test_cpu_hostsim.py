@@ -126,3 +126,73 @@ def test_kernel_logic_fhew_golden_tiny(H, orc):
         assert H.sim_fhew_blind_rotate_extract(h, f, pro, g["post_add"], o, a, 32) == 0
         assert [int(x) for x in o] == c["out"]
     H.sim_fhew_key_free(h)
+
+
+@pytest.mark.parametrize("log_n", list(range(9, 18)))
+def test_kernel_logic_ntt_fast(H, orc, log_n):
+    """Second-generation (lazy-reduction) NTT passes of ntt_fast.cuh, replayed with the launcher's geometry."""
+    H.sim_ntt_fast_u64.argtypes = [C.c_uint64, C.c_uint, C.c_int, u64p, C.c_int]
+    H.sim_ntt_fast_u32.argtypes = [C.c_uint64, C.c_uint, C.c_int, u32p, C.c_int]
+    n = 1 << log_n
+    cases = [(55, H.sim_ntt_fast_u64, np.uint64), (28, H.sim_ntt_fast_u32, np.uint32)]
+    if log_n <= 13:
+        cases += [(40, H.sim_ntt_fast_u64, np.uint64), (20, H.sim_ntt_fast_u32, np.uint32)]
+    for bits, fn, dt in cases:
+        q = orc.two_adic_primes(bits, log_n + 1, 1)[0]
+        a = orc.residues(100 + log_n, n, q)
+        a[:4] = [0, q - 1, 1, q - 1]  # extremes
+        ref = orc.ntt_fwd(q, a)
+        logts = [-1] if log_n <= 13 or log_n == 17 else [-1, 13]
+        for logt in logts:
+            x = a.astype(dt).copy()
+            assert fn(q, log_n, logt, x, 1) == 0 and (x.astype(np.uint64) == ref).all(), (log_n, bits, logt, "fwd")
+            assert fn(q, log_n, logt, x, 0) == 0 and (x.astype(np.uint64) == a).all(), (log_n, bits, logt, "inv")
+
+
+def test_fast_swizzle(H):
+    H.sim_swz2_32.restype = C.c_uint
+    H.sim_swz2_64.restype = C.c_uint
+    for fn, lanes_per_phase, words_per_bank in ((H.sim_swz2_32, 32, 1), (H.sim_swz2_64, 16, 1)):
+        assert sorted(fn(p) for p in range(1 << 13)) == list(range(1 << 13))
+        # linear over XOR
+        for a, b in ((5, 64), (0x1234, 0x0F00), (777, 8)):
+            assert fn(a ^ b) == fn(a) ^ fn(b)
+        # radix-8 pass at stride 8 (LL = 3): lanes = consecutive groups; every j must be bank-conflict-free per phase
+        nb = lanes_per_phase
+        for j in range(8):
+            for first in (0, lanes_per_phase, 5 * lanes_per_phase):
+                banks = set()
+                for lane in range(lanes_per_phase):
+                    g = first + lane
+                    lo, hi = g & 7, g >> 3
+                    banks.add(fn((hi << 6) | (j << 3) | lo) % nb)
+                assert len(banks) == lanes_per_phase, (fn, j, first)
+
+
+def test_kernel_logic_rns(H, orc):
+    """rns_core.cuh (extend_bases / rescale_k per-coefficient device logic) against the oracle (rns.rs:83-132, 331-345)."""
+    H.sim_rns_extend.argtypes = [u64p, C.c_size_t, u64p, C.c_size_t, u64p, u64p, C.c_size_t]
+    H.sim_rns_rescale.argtypes = [u64p, C.c_size_t, C.c_size_t, u64p, u64p, C.c_size_t]
+    primes = orc.two_adic_primes(55, 10, 16)
+    n = 64
+    U = lambda v: np.ascontiguousarray(v, dtype=np.uint64)
+    for nq, np_ in ((8, 8), (1, 2), (5, 1), (12, 4)):
+        qs, ps = primes[:nq], primes[nq:nq + np_]
+        x = np.stack([orc.residues(3 * nq + i, n, q) for i, q in enumerate(qs)])
+        x[:, 0] = 0
+        x[:, 1] = [q - 1 for q in qs]
+        out = np.zeros((np_, n), dtype=np.uint64)
+        assert H.sim_rns_extend(U(qs), nq, U(ps), np_, x.reshape(-1), out.reshape(-1), n) == 0
+        assert (out == orc.rns_extend_bases(qs, ps, x)[nq:]).all(), (nq, np_)
+    for nq, k in ((8, 1), (2, 1), (16, 8), (9, 8), (3, 2)):
+        qs = primes[:nq]
+        x = np.stack([orc.residues(7 * nq + i, n, q) for i, q in enumerate(qs)])
+        out = np.zeros((nq - k, n), dtype=np.uint64)
+        assert H.sim_rns_rescale(U(qs), nq, k, x.reshape(-1), out.reshape(-1), n) == 0
+        assert (out == orc.rns_rescale_k(qs, k, x)).all(), (nq, k)
+    # mixed-width moduli (source residues larger than the target modulus)
+    qs, ps = orc.two_adic_primes(55, 8, 3), orc.two_adic_primes(30, 8, 2) + orc.two_adic_primes(40, 8, 1)
+    x = np.stack([orc.residues(99 + i, n, q) for i, q in enumerate(qs)])
+    out = np.zeros((3, n), dtype=np.uint64)
+    assert H.sim_rns_extend(U(qs), 3, U(ps), 3, x.reshape(-1), out.reshape(-1), n) == 0
+    assert (out == orc.rns_extend_bases(qs, ps, x)[3:]).all()
