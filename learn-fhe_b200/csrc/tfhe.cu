@@ -18,6 +18,7 @@
 
 #include "ctx.cuh"
 #include "tfhe_core.cuh"
+#include "tfhe_tables.hpp"
 
 struct fhe_tfhe_key {
     fhe_tfhe_param param;
@@ -40,41 +41,20 @@ static constexpr int KS_CH = 256;   // digit rows staged in shared memory per it
 fhe_status get_fft_tab(fhe_ctx* ctx, unsigned log_n, FftTab* out) {
     FHE_REQUIRE(ctx, log_n >= 1 && log_n <= 13, "f64 FFT path supports ring degrees 2..8192");
     std::lock_guard<std::mutex> lock(ctx->mu);
-    const size_t n = (size_t)1 << log_n, m = n / 2, mb = std::max<size_t>(m / 2, 1);
+    FftTabHost h;
     auto it = ctx->fft_tables.find((int)log_n);
     if (it == ctx->fft_tables.end()) {
-        std::vector<Cx> h(2 * m + 2 * mb);
-        for (size_t j = 0; j < m; ++j) {
-            volatile double num = (double)j * M_PI;
-            const double ang = num / (double)n;
-            h[j] = Cx{std::cos(ang), std::sin(ang)};
-            h[m + j] = Cx{h[j].re, -h[j].im};
-        }
-        // chunk twiddles: bit-reversed cis(i*pi/m), i < m; only the first m/2 entries are ever indexed
-        unsigned lgm = 0;
-        while (((size_t)1 << lgm) < m) ++lgm;
-        for (size_t c = 0; c < mb; ++c) {
-            size_t i = 0;
-            for (unsigned b = 0; b < lgm; ++b)
-                if (c & ((size_t)1 << b)) i |= (size_t)1 << (lgm - 1 - b);
-            volatile double num = (double)i * M_PI;
-            const double ang = num / (double)m;
-            const Cx t{std::cos(ang), std::sin(ang)};
-            h[2 * m + c] = t;
-            h[2 * m + mb + c] = Cx{t.re, -t.im};
-        }
+        h.build(log_n);
         void* d = nullptr;
-        FHE_CUDA(ctx, cudaMalloc(&d, h.size() * sizeof(Cx)));
-        FHE_CUDA(ctx, cudaMemcpy(d, h.data(), h.size() * sizeof(Cx), cudaMemcpyHostToDevice));
-        it = ctx->fft_tables.emplace((int)log_n, std::make_pair(d, h.size() * sizeof(Cx))).first;
+        FHE_CUDA(ctx, cudaMalloc(&d, h.data.size() * sizeof(Cx)));
+        FHE_CUDA(ctx, cudaMemcpy(d, h.data.data(), h.data.size() * sizeof(Cx), cudaMemcpyHostToDevice));
+        it = ctx->fft_tables.emplace((int)log_n, std::make_pair(d, h.data.size() * sizeof(Cx))).first;
+    } else {
+        h.log_n = log_n;
+        h.m = ((size_t)1 << log_n) / 2;
+        h.mb = h.m / 2 > 1 ? h.m / 2 : 1;
     }
-    const Cx* base = (const Cx*)it->second.first;
-    out->lg = (int)log_n - 1;
-    out->tw = base;
-    out->tw_inv = base + m;
-    out->tw_bo = base + 2 * m;
-    out->tw_inv_bo = base + 2 * m + mb;
-    out->m_inv = 1.0 / (double)m;
+    *out = h.view((const Cx*)it->second.first);
     return FHE_OK;
 }
 

@@ -196,3 +196,60 @@ def test_kernel_logic_rns(H, orc):
     out = np.zeros((3, n), dtype=np.uint64)
     assert H.sim_rns_extend(U(qs), 3, U(ps), 3, x.reshape(-1), out.reshape(-1), n) == 0
     assert (out == orc.rns_extend_bases(qs, ps, x)[3:]).all()
+
+
+def _tfhe_small_param(orc, n=24, big_n=64, k=1, bs_log_b=8, bs_d=3, ks_log_b=4, ks_d=5):
+    P = orc.tfhe_testing_param()
+    P.n, P.big_n, P.k, P.bs_log_b, P.bs_d, P.ks_log_b, P.ks_d = n, big_n, k, bs_log_b, bs_d, ks_log_b, ks_d
+    return P
+
+
+def test_kernel_logic_fft64_mul(H, orc):
+    """tfhe_core.cuh f64 FFT product (twist, radix passes, untwist, f64_mod_u64) is bit-identical to the oracle's restatement
+    of util/src/ring/fft/c64.rs:11-108 — full-range torus words times signed digits, the case of c64.rs:186-208."""
+    H.sim_fft64_mul.argtypes = [u64p, u64p, C.c_uint, C.c_uint]
+    for log_n in range(1, 12):
+        n = 1 << log_n
+        a = orc.splitmix64(31 + log_n, n)
+        digits = (orc.splitmix64(77 + log_n, n) % np.uint64(1 << 17)).astype(np.int64) - (1 << 16)
+        b = digits.astype(np.uint64)
+        ref = orc.fft64_mul(a, b)
+        x = a.copy()
+        assert H.sim_fft64_mul(x, b, log_n, 37) == 0
+        assert (x == ref).all(), log_n
+        # small operands: exact == schoolbook (c64.rs:169-184)
+        sa = (orc.splitmix64(5 + log_n, n) % np.uint64(64)).astype(np.uint64)
+        sb = (orc.splitmix64(6 + log_n, n) % np.uint64(64)).astype(np.uint64)
+        y = sa.copy()
+        H.sim_fft64_mul(y, sb, log_n, 8)
+        assert (y == orc.schoolbook_t64(sa, sb)).all()
+
+
+@pytest.mark.parametrize("k,bs_d", [(1, 1), (1, 3), (2, 2)])
+def test_kernel_logic_tfhe(H, orc, k, bs_d):
+    """TGGSW external product and the CMUX blind rotation (+ sample extract) of tfhe_core.cuh against the oracle
+    (tggsw.rs:100-121, tfhe/bootstrapping.rs:84-104), reduced parameters, every torus word bit-identical."""
+    H.sim_tfhe_key.restype = C.c_void_p
+    H.sim_tfhe_key.argtypes = [C.c_uint] * 5 + [u64p]
+    H.sim_tfhe_key_free.argtypes = [C.c_void_p]
+    H.sim_tfhe_external_product.argtypes = [C.c_void_p, C.c_uint, u64p, u64p, C.c_uint]
+    H.sim_tfhe_blind_rotate_extract.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_uint]
+    P = _tfhe_small_param(orc, k=k, bs_d=bs_d, bs_log_b=23 if bs_d == 1 else 8)
+    K = orc.TfheKey(P, 0x5EED0003)
+    ex = K.export()
+    log_n = P.big_n.bit_length() - 1
+    h = H.sim_tfhe_key(log_n, P.k, P.n, P.bs_log_b, P.bs_d, ex["brk"].reshape(-1))
+    glwe = orc.splitmix64(9, (P.k + 1) * P.big_n).reshape(P.k + 1, P.big_n)
+    for i in (0, 7, P.n - 1):
+        out = np.zeros_like(glwe)
+        H.sim_tfhe_external_product(h, i, glwe.reshape(-1), out.reshape(-1), 48)
+        assert (out == K.external_product(i, glwe)).all(), i
+    cts = K.encrypt(np.arange(3, dtype=np.uint64), 5)
+    cts[0, 3] = 0  # a zero mask word: the kernel skips that CMUX
+    v = K.lut_poly(np.arange(1 << P.log_p, dtype=np.uint64))
+    lut = (v << np.uint64(64 - (P.log_p + P.padding))).astype(np.uint64)
+    for ct in cts:
+        out = np.zeros(P.k * P.big_n + 1, dtype=np.uint64)
+        H.sim_tfhe_blind_rotate_extract(h, lut, ct, out, 40)
+        assert (out == K.blind_rotate_extract(v, ct)).all()
+    H.sim_tfhe_key_free(h)
