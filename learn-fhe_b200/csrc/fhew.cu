@@ -9,10 +9,12 @@
 //   fhew_step_kernel          one external product / automorphism per accumulator (parity tests, util-level callers)
 // All per-thread logic lives in fhew_core.cuh (shared with tests/hostsim).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "ctx.cuh"
 #include "fhew_core.cuh"
+#include "fhew_fast.cuh"
 
 struct fhe_fhew_key {
     fhe_fhew_param param;
@@ -25,6 +27,11 @@ struct fhe_fhew_key {
     void* d_dlog = nullptr;
     int* d_err = nullptr;
     size_t brk_bytes = 0, ak_bytes = 0, ksk_bytes = 0;
+    // fast path (fhew_fast.cuh): N = 512, Q < 2^28, small digits, instantiated (d_g, d_r)
+    bool fast = false;
+    fhe::FhewFastDev F;
+    void* d_brk4 = nullptr;
+    void* d_ak4 = nullptr;
 };
 
 namespace fhe {
@@ -145,6 +152,78 @@ __global__ void __launch_bounds__(BR_THREADS) fhew_step_kernel(FhewDev P, uint32
     }
 }
 
+// {a,b}[rows][N] (uint2) -> [rows][128][2] uint4: {a(4t..4t+3)}, {b(4t..4t+3)}
+__global__ void fhew_pack4_kernel(const uint2* __restrict__ ab, uint4* __restrict__ out, unsigned long long rows) {
+    const unsigned long long total = rows * FF_THREADS;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint2* src = ab + i * 4;
+        out[i * 2] = make_uint4(src[0].x, src[1].x, src[2].x, src[3].x);
+        out[i * 2 + 1] = make_uint4(src[0].y, src[1].y, src[2].y, src[3].y);
+    }
+}
+
+// Fast path (fhew_fast.cuh).  mode 0: out = LWE ciphertext [N+1] (sample_extract + post_add); mode 1: accumulator [2][N]
+template <typename FT, typename OT>
+__global__ void __launch_bounds__(FF_THREADS) fhew_blind_rotate_fast_kernel(FhewFastDev P, const FT* __restrict__ f,
+                                                                             const uint32_t* __restrict__ ct2n, uint32_t post_add,
+                                                                             unsigned long long count, OT* __restrict__ out, int mode,
+                                                                             int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* words = reinterpret_cast<uint32_t*>(smem_raw);
+    FhewFastSmem S;
+    S.acc = words;
+    S.dig = words + 4 * FF_N;
+    S.tw = reinterpret_cast<TwPair<uint32_t>*>(words + 12 * FF_N);
+    S.itw = S.tw + FF_N;
+    uint16_t* steps = reinterpret_cast<uint16_t*>(words + ff_fixed_words());
+    const uint32_t max_steps = P.n_s + FF_N + 2;
+    uint32_t* a2n = reinterpret_cast<uint32_t*>(steps + ((max_steps + 1) & ~1u));
+    __shared__ uint32_t ns_sh;
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(S.dig);  // schedule scratch aliases the digit region
+    uint16_t* sorted = cnt + FF_N;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < (uint32_t)FF_N; i += FF_THREADS) {
+        S.tw[i] = P.tw[i];
+        S.itw[i] = P.itw[i];
+    }
+    auto run = [&](auto phase) {
+        phase(tid);
+        __syncthreads();
+    };
+    for (unsigned long long ct = blockIdx.x; ct < count; ct += gridDim.x) {
+        const uint32_t* src = ct2n + ct * (P.n_s + 1);
+        for (uint32_t j = tid; j <= P.n_s; j += FF_THREADS) a2n[j] = src[j];
+        __syncthreads();
+        if (tid == 0) ns_sh = build_schedule((uint32_t)FF_N, P.n_s, P.w, a2n, P.dlog, cnt, sorted, steps);
+        ff_init(P, S.acc, f, a2n[P.n_s], tid);
+        __syncthreads();
+        uint32_t ns = ns_sh;
+        if (ns == 0xFFFFFFFFu) {  // reference: unreachable!() (bootstrapping.rs:221)
+            if (tid == 0) atomicExch(err, 1);
+            ns = 0;
+        }
+        uint32_t cur = 0;
+        for (uint32_t s = 0; s < ns; ++s) {
+            ff_step(P, S, steps[s], cur, run);
+            cur ^= 1u;
+        }
+        const uint32_t* acc = S.acc + (size_t)cur * 2 * FF_N;
+        if (mode == 0) {
+            ff_extract(P, acc, post_add, out + ct * (FF_N + 1), tid);
+        } else {
+            OT* o = out + ct * 2ull * FF_N;
+            for (uint32_t i = tid; i < 2u * FF_N; i += FF_THREADS) o[i] = (OT)acc[i];
+        }
+        __syncthreads();
+    }
+}
+
+static size_t br_fast_smem_bytes(const fhe_fhew_key* key) {
+    const uint32_t max_steps = key->F.n_s + FF_N + 2;
+    return ff_fixed_words() * 4 + (size_t)((max_steps + 1) & ~1u) * 2 + (size_t)(key->F.n_s + 1) * 4 + 16;
+}
+
 static size_t br_smem_bytes(const fhe_fhew_key* key) {
     const uint32_t n = 1u << key->P.log_n;
     const uint32_t max_steps = key->P.n_s + n + 2;
@@ -211,9 +290,33 @@ static fhe_status run_prologue(fhe_ctx* ctx, const fhe_fhew_key* key, size_t cou
     return after_launch(ctx, "fhew_prologue_kernel");
 }
 
+static bool fhew_force_generic() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FHE_B200_FHEW_GENERIC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+template <typename OT>
+static fhe_status run_blind_rotate_fast(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n,
+                                        uint32_t post_add, size_t count, OT* d_out, int mode) {
+    const size_t smem = br_fast_smem_bytes(key);
+    auto kern = fhew_blind_rotate_fast_kernel<uint64_t, OT>;
+    unsigned grid;
+    FHE_CHECK(persistent_grid(ctx, kern, FF_THREADS, smem, count, &grid));
+    FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
+    kern<<<grid, FF_THREADS, smem, ctx->stream>>>(key->F, d_f, d_ct2n, post_add, count, d_out, mode, key->d_err);
+    return after_launch(ctx, "fhew_blind_rotate_kernel");
+}
+static bool fhew_fast_instantiated(unsigned dg, unsigned dr) { return dg >= 1 && dg <= 4 && dr >= 1 && dr <= 8; }
+
 template <typename OT>
 static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n, uint32_t post_add,
                                    size_t count, OT* d_out, int mode) {
+    if (key->fast && !fhew_force_generic()) {
+        return run_blind_rotate_fast<OT>(ctx, key, d_f, d_ct2n, post_add, count, d_out, mode);
+    }
     const size_t smem = br_smem_bytes(key);
     auto kern = fhew_blind_rotate_kernel<uint64_t, OT>;
     unsigned grid;
@@ -310,6 +413,51 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     P.brk = (const uint2*)key->d_brk;
     P.ak = (const uint2*)key->d_ak;
     P.dlog = (const uint16_t*)key->d_dlog;
+    // fast path structures
+    if (pp->log_n == FF_LOGN && q < (1ull << 28) && P.small_digits && fhew_fast_instantiated(pp->rgsw_d, pp->rlwe_d)) {
+        FhewFastDev& F = key->F;
+        F.m.q = (uint32_t)q;
+        F.m.q2 = (uint32_t)(2 * q);
+        F.m.q8 = (uint32_t)(8 * q);
+        F.m.mu = (uint32_t)((1ull << 32) / q);
+        F.mu64 = (uint64_t)((((u128_t)1) << 64) / q);
+        F.n_s = pp->n_s;
+        F.w = pp->w;
+        F.g_dec = P.g_dec;
+        F.r_dec = P.r_dec;
+        F.dlog = P.dlog;
+        F.tw = P.tw;
+        F.itw = P.itw;
+        F.ninv = P.ninv;
+        F.wninv = P.wninv;
+        for (unsigned v = 0; v <= pp->w; ++v) {
+            F.ak_t[v] = P.ak_t[v];
+            uint32_t inv = 1;  // t^-1 mod 2N by Newton iteration (t odd)
+            for (int it = 0; it < 5; ++it) inv = inv * (2u - P.ak_t[v] * inv);
+            F.ak_tinv[v] = inv & (2 * n - 1);
+        }
+        const size_t brk_rows = (size_t)pp->n_s * 2 * pp->rgsw_d, ak_rows = (size_t)(pp->w + 1) * pp->rlwe_d;
+        if (cudaMalloc(&key->d_brk4, brk_rows * n * 8) != cudaSuccess || cudaMalloc(&key->d_ak4, ak_rows * n * 8) != cudaSuccess) {
+            fhe_fhew_key_free(ctx, key);
+            return fail(ctx, FHE_ENOMEM, "fast key alloc");
+        }
+        fhew_pack4_kernel<<<(unsigned)std::min<size_t>((brk_rows * FF_THREADS + 255) / 256, 4096), 256, 0, ctx->stream>>>(
+            (const uint2*)key->d_brk, (uint4*)key->d_brk4, brk_rows);
+        fhe_status st2 = after_launch(ctx, "fhew_pack4_kernel");
+        if (st2 == FHE_OK) {
+            fhew_pack4_kernel<<<(unsigned)std::min<size_t>((ak_rows * FF_THREADS + 255) / 256, 4096), 256, 0, ctx->stream>>>(
+                (const uint2*)key->d_ak, (uint4*)key->d_ak4, ak_rows);
+            st2 = after_launch(ctx, "fhew_pack4_kernel");
+        }
+        if (st2 == FHE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st2 = fail(ctx, FHE_ECUDA, "fast key packing failed");
+        if (st2 != FHE_OK) {
+            fhe_fhew_key_free(ctx, key);
+            return st2;
+        }
+        F.brk4 = (const uint4*)key->d_brk4;
+        F.ak4 = (const uint4*)key->d_ak4;
+        key->fast = true;
+    }
     *out = key;
     return FHE_OK;
 }
@@ -320,6 +468,8 @@ void fhe_fhew_key_free(fhe_ctx* ctx, fhe_fhew_key* key) {
     if (key->d_brk) cudaFree(key->d_brk);
     if (key->d_ak) cudaFree(key->d_ak);
     if (key->d_ksk) cudaFree(key->d_ksk);
+    if (key->d_brk4) cudaFree(key->d_brk4);
+    if (key->d_ak4) cudaFree(key->d_ak4);
     if (key->d_dlog) cudaFree(key->d_dlog);
     if (key->d_err) cudaFree(key->d_err);
     delete key;
@@ -412,6 +562,10 @@ fhe_status fhe_fhew_key_broadcast(fhe_ctx* ctx, fhe_fhew_key* key, void* nccl_co
     FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_brk, key->brk_bytes));
     FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ak, key->ak_bytes));
     FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ksk, key->ksk_bytes));
+    if (key->fast) {
+        FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_brk4, key->brk_bytes));
+        FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ak4, key->ak_bytes));
+    }
     FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FHE_OK;
 }

@@ -1,0 +1,279 @@
+// FHEW / LMKCDEY blind rotation, fast path for N = 512, Q < 2^28 (the reference's single-key parameter set,
+// scheme/fhew/src/fhew/boolean.rs:225-239).  Same reference call sites and the same exact arithmetic as fhew_core.cuh
+// (rgsw.rs:116-128, rlwe.rs:177-202, bootstrapping.rs:158-231); what changes is the schedule inside one step:
+//
+//   128 threads per ciphertext.  Forward transforms are split 3 + 4 + 2 stages:
+//     P1  thread (g, h): reads acc_h[g + 64 j] (or the permuted a(X^t)), decomposes in registers and runs the first
+//         radix-8 pass of its digit polynomials before anything is written: digits never exist untransformed in memory;
+//     P2  radix-16 pass in shared memory;
+//     P3  thread t owns evaluation points 4t..4t+3 of EVERY digit polynomial: last radix-4 pass, multiply-accumulate against
+//         the key rows (two coalesced 16-byte loads per row), Barrett, and the first radix-4 pass of BOTH inverse transforms,
+//         all in registers: no exchange of partial sums, no separate MAC pass;
+//     P4  inverse radix-16 pass (2 polynomials); P5 inverse radix-8 pass with n^-1 folded in, (+ b(X^t)), canonical result
+//         written to the other accumulator buffer (ping-pong, so permuted reads of the old accumulator stay valid).
+//   5 barriers per step (the first generation needs 9) and about a third of its instructions: lazy forward butterflies
+//   (values < 16 Q, one min() before P3), twiddles in shared memory, swizzled addresses formed as swz(base) ^ const_j.
+// __host__ __device__ so tests/hostsim can replay it.
+#pragma once
+#include "fhew_core.cuh"
+#include "ntt_fast.cuh"
+
+namespace fhe {
+
+static constexpr int FF_LOGN = 9;
+static constexpr int FF_N = 1 << FF_LOGN;
+static constexpr int FF_THREADS = 128;
+
+struct FhewFastDev {
+    Lz32 m;
+    uint64_t mu64;  // floor(2^64 / Q): Barrett constant for the 64-bit MAC accumulators
+    uint32_t n_s, w;
+    DecompParam g_dec;  // RGSW decomposor (log_b * d <= 32, d <= 4)
+    DecompParam r_dec;  // RLWE key-switch decomposor
+    const uint4* brk4;  // [n_s][2 d_g rows][128][2]: {a(4t..4t+3)}, {b(4t..4t+3)} evaluation form
+    const uint4* ak4;   // [w+1][d_r rows][128][2]
+    const uint16_t* dlog;
+    const TwPair<uint32_t>* tw;   // global tables (copied to shared memory when the kernel starts)
+    const TwPair<uint32_t>* itw;
+    TwPair<uint32_t> ninv, wninv;
+    uint32_t ak_t[40];     // automorphism exponents t mod 2N for ak[0..w]
+    uint32_t ak_tinv[40];  // t^-1 mod 2N
+};
+
+// shared memory (32-bit words): acc[2 buf][2 (a,b)][N] | dig[8][N] | tw[N pairs] | itw[N pairs] | steps | a2n
+struct FhewFastSmem {
+    uint32_t* acc;
+    uint32_t* dig;
+    TwPair<uint32_t>* tw;
+    TwPair<uint32_t>* itw;
+};
+HD constexpr size_t ff_fixed_words() { return (size_t)4 * FF_N + 8 * FF_N + 4 * FF_N; }
+
+// swizzle of the digit polynomials: bits 5,6,7 -> 2,3,4 and bit 8 -> 2 (the radix-16 pass at stride 4 needs bit 8)
+HD uint32_t swzf(uint32_t p) { return p ^ ((p >> 3) & 0x1Cu) ^ ((p >> 6) & 4u); }
+
+HD uint32_t ff_reduce64(const FhewFastDev& P, uint64_t x) {  // any x -> [0, Q)
+    const uint64_t qh = mulhi_u64(x, P.mu64);
+    const uint32_t r = (uint32_t)(x - qh * (uint64_t)P.m.q);  // [0, 2Q)
+    return umin_(r, r - P.m.q);
+}
+
+// ---- P1: decompose + first forward radix-8 pass (stages 0..2, stride 64) --------------------------------------------------------
+// Signed-digit state of one coefficient (decompose.rs:92-111 with zq.rs:83-89), 32-bit working word (log_b * d <= 32):
+// start: x = centred(rounding_shr(v)); step: emits the next digit as a residue mod Q and advances x.
+HD uint32_t ff_dec_start(const FhewFastDev& P, const DecompParam& dp, uint32_t v) {
+    uint32_t r = v + (uint32_t)dp.half;
+    r = umin_(r, r - P.m.q);
+    const uint32_t sh = r >> dp.rounding_bits;
+    return sh < (P.m.q >> 1) ? sh : sh - P.m.q;
+}
+HD uint32_t ff_dec_step(const FhewFastDev& P, const DecompParam& dp, uint32_t& x) {
+    const uint32_t mask = (1u << dp.log_b) - 1u, b_by_2 = 1u << (dp.log_b - 1);
+    const uint32_t limb = x & mask;
+    const uint32_t carry = (limb + (x & 1u) > b_by_2) ? 1u : 0u;
+    x = (x >> dp.log_b) + carry;
+    return limb + (carry ? (uint32_t)dp.neg_b : 0u);
+}
+// Thread (g, h) holds the 8 coefficients at positions g + 64 j (values from acc_in[h] for an external product, from the
+// permuted a(X^t) for an automorphism) and walks the digits; digit k becomes polynomial `pbase + k` if lo <= k < hi.
+HD void ff_p1(const FhewFastDev& P, const FhewFastSmem& S, const DecompParam& dp, const uint32_t* acc_in, bool is_auto, uint32_t tinv,
+              uint32_t g, uint32_t h, uint32_t lo, uint32_t hi, uint32_t pbase) {
+    uint32_t st[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t c = g + 64u * j;
+        uint32_t v;
+        if (is_auto) {
+            const uint32_t i = (c * tinv) & (2 * FF_N - 1);  // a(X^t)[c] = +-a[c * t^-1 mod 2N]   (avec.rs:34-50)
+            v = acc_in[i & (FF_N - 1)];
+            if (i >= (uint32_t)FF_N) v = v == 0 ? 0 : P.m.q - v;
+        } else {
+            v = acc_in[(h << FF_LOGN) + c];
+        }
+        st[j] = ff_dec_start(P, dp, v);
+    }
+    const uint32_t P0 = swzf(g);
+#pragma unroll 1
+    for (uint32_t k = 0; k < dp.d; ++k) {
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = ff_dec_step(P, dp, st[j]);
+        if (k >= lo && k < hi) {
+            fast_fwd_regs<Lz32, 3, false>(P.m, x, S.tw, 1u);
+            uint32_t* d = S.dig + ((pbase + k) << FF_LOGN);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[P0 ^ swzf((uint32_t)j << 6)] = x[j];
+        }
+    }
+}
+// ---- P2: forward radix-16 pass (stages 3..6, stride 4) on polynomial `poly`, group `grp` in [0, 32) ------------------------------
+HD void ff_p2(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32_t grp) {
+    const uint32_t lo = grp & 3u, hi = grp >> 2;
+    const uint32_t P0 = swzf((hi << 6) | lo);
+    uint32_t* d = S.dig + (poly << FF_LOGN);
+    uint32_t x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = d[P0 ^ swzf((uint32_t)j << 2)];
+    fast_fwd_regs<Lz32, 4, false>(P.m, x, S.tw, 8u + hi);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[P0 ^ swzf((uint32_t)j << 2)] = x[j];
+}
+// ---- P3: last forward radix-4 pass (stages 7, 8) of `rows` digit polynomials + MAC + first inverse radix-4 pass -------------------
+HD void ff_ld4(const uint32_t* d, uint32_t P0, uint32_t* x) {
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4*>(d + P0);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+#else
+    for (int i = 0; i < 4; ++i) x[i] = d[P0 + i];
+#endif
+}
+HD void ff_st4(uint32_t* d, uint32_t P0, const uint32_t* x) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(d + P0) = make_uint4(x[0], x[1], x[2], x[3]);
+#else
+    for (int i = 0; i < 4; ++i) d[P0 + i] = x[i];
+#endif
+}
+HD uint4 ff_ldg4(const uint4* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+HD void ff_p3(const FhewFastDev& P, const FhewFastSmem& S, const uint4* __restrict__ key /* [rows][128][2] */, uint32_t rows, uint32_t t) {
+    const uint32_t P0 = swzf(t << 2);
+    uint64_t sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+    const TwPair<uint32_t> t0 = S.tw[128u + t], t1 = S.tw[256u + 2u * t], t2 = S.tw[257u + 2u * t];
+#pragma unroll 2
+    for (uint32_t k = 0; k < rows; ++k) {
+        uint32_t x[4];
+        ff_ld4(S.dig + (k << FF_LOGN), P0, x);
+        const uint4 ka = ff_ldg4(key + ((size_t)k * FF_THREADS + t) * 2), kb = ff_ldg4(key + ((size_t)k * FF_THREADS + t) * 2 + 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = P.m.pre_red(x[i]);  // < 15 Q after 7 stages -> < 8 Q
+        P.m.bf_fwd(x[0], x[2], t0);                              // stages 7, 8: < 12 Q < 2^32
+        P.m.bf_fwd(x[1], x[3], t0);
+        P.m.bf_fwd(x[0], x[1], t1);
+        P.m.bf_fwd(x[2], x[3], t2);
+        sa[0] += (uint64_t)ka.x * x[0]; sa[1] += (uint64_t)ka.y * x[1]; sa[2] += (uint64_t)ka.z * x[2]; sa[3] += (uint64_t)ka.w * x[3];
+        sb[0] += (uint64_t)kb.x * x[0]; sb[1] += (uint64_t)kb.y * x[1]; sb[2] += (uint64_t)kb.z * x[2]; sb[3] += (uint64_t)kb.w * x[3];
+    }
+    uint32_t y[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        y[i] = ff_reduce64(P, sa[i]);
+        y[4 + i] = ff_reduce64(P, sb[i]);
+    }
+    const TwPair<uint32_t> i0 = S.itw[128u + t], i1 = S.itw[256u + 2u * t], i2 = S.itw[257u + 2u * t];
+#pragma unroll
+    for (int o = 0; o < 8; o += 4) {  // first inverse radix-4 pass (stages 8, 7) of a then b
+        P.m.bf_inv(y[o + 0], y[o + 1], i1, 0);
+        P.m.bf_inv(y[o + 2], y[o + 3], i2, 0);
+        P.m.bf_inv(y[o + 0], y[o + 2], i0, 1);
+        P.m.bf_inv(y[o + 1], y[o + 3], i0, 1);
+    }
+    ff_st4(S.dig, P0, y);
+    ff_st4(S.dig + FF_N, P0, y + 4);
+}
+// ---- P4: inverse radix-16 pass (stages 6..3) on result polynomial `poly` (0 = a, 1 = b) ---------------------------------------------
+HD void ff_p4(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32_t grp) {
+    const uint32_t lo = grp & 3u, hi = grp >> 2;
+    const uint32_t P0 = swzf((hi << 6) | lo);
+    uint32_t* d = S.dig + (poly << FF_LOGN);
+    uint32_t x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = d[P0 ^ swzf((uint32_t)j << 2)];
+    fast_inv_regs<Lz32, 4, false, false>(P.m, x, S.itw, 8u + hi, P.ninv, P.wninv);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[P0 ^ swzf((uint32_t)j << 2)] = x[j];
+}
+// ---- P5: inverse radix-8 pass (stages 2..0, n^-1 folded) of polynomial h, canonical result (+ add(j)) -> acc_out[h][g + 64 j] -------
+template <typename Add>
+HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, uint32_t g, uint32_t h, bool do_add, Add add) {
+    const uint32_t P0 = swzf(g);
+    const uint32_t* d = S.dig + (h << FF_LOGN);
+    uint32_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = d[P0 ^ swzf((uint32_t)j << 6)];
+    fast_inv_regs<Lz32, 3, true, false>(P.m, x, S.itw, 1u, P.ninv, P.wninv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t v = P.m.inv_canon(x[j]);
+        if (do_add) {
+            v += add(j);
+            v = umin_(v, v - P.m.q);
+        }
+        acc_out[(h << FF_LOGN) + g + 64u * j] = v;
+    }
+}
+
+// value of poly(X^t) at coefficient c, read from the canonical polynomial `src`: +-src[c * tinv mod 2N]  (avec.rs:34-50)
+HD uint32_t ff_perm_coef(const FhewFastDev& P, const uint32_t* src, uint32_t tinv, uint32_t c) {
+    const uint32_t i = (c * tinv) & (2 * FF_N - 1);
+    const uint32_t v = src[i & (FF_N - 1)];
+    return i >= (uint32_t)FF_N ? P.m.q - v - (v == 0 ? P.m.q : 0) : v;  // neg(0) = 0
+}
+
+// One full step; `cur` = index of the accumulator buffer holding the input (the result goes to the other one).
+// run(phase): phase(tid) for every thread of the CTA followed by a barrier.
+template <typename Run>
+HD void ff_step(const FhewFastDev& P, const FhewFastSmem& S, uint32_t step, uint32_t cur, Run run) {
+    const bool is_auto = (step & FHEW_STEP_AUTO) != 0;
+    const uint32_t idx = step & 0x7FFFu;
+    const uint32_t* acc_in = S.acc + (size_t)cur * 2 * FF_N;
+    uint32_t* acc_out = S.acc + (size_t)(cur ^ 1u) * 2 * FF_N;
+    const DecompParam& dp = is_auto ? P.r_dec : P.g_dec;
+    const uint32_t d = dp.d, rows = is_auto ? d : 2 * d;
+    const uint4* key = is_auto ? P.ak4 + (size_t)idx * d * FF_THREADS * 2 : P.brk4 + (size_t)idx * (2 * d) * FF_THREADS * 2;
+    const uint32_t tinv = is_auto ? P.ak_tinv[idx] : 0;
+    // external product: digits of acc.a -> polynomials [0, d), digits of acc.b -> [d, 2d)   (rgsw.rs:122-124)
+    // automorphism:     digits of a(X^t) -> polynomials [0, d); half h transforms digits [h * ceil(d/2), ...)   (rlwe.rs:182)
+    run([&](uint32_t tid) {
+        const uint32_t g = tid & 63u, h = tid >> 6;
+        const uint32_t half = (d + 1) / 2;
+        const uint32_t lo = is_auto ? h * half : 0u, hi = is_auto ? (h == 0 ? half : d) : d;
+        ff_p1(P, S, dp, acc_in, is_auto, tinv, g, h, lo, hi, is_auto ? 0u : h * d);
+    });
+    run([&](uint32_t tid) {
+#pragma unroll 1
+        for (uint32_t u = tid; u < rows * 32u; u += FF_THREADS) ff_p2(P, S, u >> 5, u & 31u);
+    });
+    run([&](uint32_t tid) { ff_p3(P, S, key, rows, tid); });
+    run([&](uint32_t tid) {
+        if (tid < 64u) ff_p4(P, S, tid >> 5, tid & 31u);
+    });
+    run([&](uint32_t tid) {
+        const uint32_t g = tid & 63u, h = tid >> 6;
+        // key switch adds the (permuted) body: b' = sum ksk.b_k * limb_k + b(X^t)   (rlwe.rs:184)
+        ff_p5(P, S, acc_out, g, h, is_auto && h == 1, [&](int j) { return ff_perm_coef(P, acc_in + FF_N, tinv, g + 64u * j); });
+    });
+}
+
+// acc init (bootstrapping.rs:158-169): acc = (0, f(X^-g) * X^(b*g))
+template <typename FT>
+HD void ff_init(const FhewFastDev& P, uint32_t* acc, const FT* __restrict__ f, uint32_t b2n, uint32_t tid) {
+    const uint32_t m2 = 2 * FF_N - 1;
+    const uint32_t t = (2 * FF_N - 5) & m2, e = (b2n * 5) & m2;
+    for (uint32_t i = tid; i < (uint32_t)FF_N; i += FF_THREADS) {
+        const uint32_t pos = (i * t + e) & m2;
+        uint32_t v = (uint32_t)f[i];
+        if (pos >= (uint32_t)FF_N) v = v == 0 ? 0 : P.m.q - v;
+        acc[i] = 0;
+        acc[FF_N + (pos & (FF_N - 1))] = v;
+    }
+}
+// Rlwe::sample_extract(ct, 0) (rlwe.rs:193-202) + post_add on the body
+template <typename OT>
+HD void ff_extract(const FhewFastDev& P, const uint32_t* acc, uint32_t post_add, OT* out, uint32_t tid) {
+    for (uint32_t k = tid; k < (uint32_t)FF_N; k += FF_THREADS) {
+        const uint32_t v = k == 0 ? acc[0] : acc[FF_N - k];
+        out[k] = (OT)(k == 0 || v == 0 ? v : P.m.q - v);
+    }
+    if (tid == 0) {
+        uint32_t b = acc[FF_N] + post_add;
+        out[FF_N] = (OT)umin_(b, b - P.m.q);
+    }
+}
+
+}  // namespace fhe

@@ -22,6 +22,9 @@ struct uint2 {
 struct double2 {
     double x, y;
 };
+struct uint4 {
+    unsigned int x, y, z, w;
+};
 #endif
 
 namespace fhe {

@@ -143,14 +143,15 @@ HD TwPair<uint64_t> ld_tw(const TwPair<uint64_t>* p) {
 // ---- register passes ---------------------------------------------------------------------------------------------------
 // element j of a group sits at tile position (hi << (L+R)) | (j << L) | lo; the pass covers global stages
 // l0 .. l0+R-1; tb = 2^l0 + (position >> (logN - l0)); twiddle of sub-stage u, pair prefix `top`: tw[(tb << u) + top].
-template <typename L, int R>
+// NC: twiddles are in global memory and fetched through the read-only path; false: plain loads (shared-memory tables)
+template <typename L, int R, bool NC = true>
 HD void fast_fwd_regs(const L& m, typename L::W* x, const TwPair<typename L::W>* __restrict__ tw, uint32_t tb) {
 #pragma unroll
     for (int u = 0; u < R; ++u) {
         const int h = 1 << (R - 1 - u);
 #pragma unroll
         for (int top = 0; top < (1 << u); ++top) {
-            const TwPair<typename L::W> t = ld_tw(tw + ((tb << u) + top));
+            const TwPair<typename L::W> t = NC ? ld_tw(tw + ((tb << u) + top)) : tw[(tb << u) + top];
 #pragma unroll
             for (int low = 0; low < h; ++low) {
                 const int j = (top << (R - u)) | low;
@@ -160,7 +161,7 @@ HD void fast_fwd_regs(const L& m, typename L::W* x, const TwPair<typename L::W>*
     }
 }
 // LAST: global stage 0 is part of this pass and is the final stage of the transform: fold n^-1.
-template <typename L, int R, bool LAST>
+template <typename L, int R, bool LAST, bool NC = true>
 HD void fast_inv_regs(const L& m, typename L::W* x, const TwPair<typename L::W>* __restrict__ itw, uint32_t tb,
                       TwPair<typename L::W> ninv, TwPair<typename L::W> wninv) {
 #pragma unroll
@@ -173,7 +174,7 @@ HD void fast_inv_regs(const L& m, typename L::W* x, const TwPair<typename L::W>*
 #pragma unroll
                 for (int low = 0; low < h; ++low) m.bf_inv_last(x[low], x[low + h], ninv, wninv, stage);
             } else {
-                const TwPair<typename L::W> t = ld_tw(itw + ((tb << u) + top));
+                const TwPair<typename L::W> t = NC ? ld_tw(itw + ((tb << u) + top)) : itw[(tb << u) + top];
 #pragma unroll
                 for (int low = 0; low < h; ++low) {
                     const int j = (top << (R - u)) | low;

@@ -7,6 +7,7 @@
 // path (libfhe_b200.so has no CPU fallback).
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../learn-fhe_b200/csrc/fhew_core.cuh"

@@ -253,3 +253,36 @@ def test_kernel_logic_tfhe(H, orc, k, bs_d):
         H.sim_tfhe_blind_rotate_extract(h, lut, ct, out, 40)
         assert (out == K.blind_rotate_extract(v, ct)).all()
     H.sim_tfhe_key_free(h)
+
+
+def test_kernel_logic_fhew_fast(H, orc, fhew_setup):
+    """Fast blind-rotation path (fhew_fast.cuh: 3+4+2 passes, MAC fused with the first inverse pass) against the oracle:
+    single steps and whole gate bootstraps, bit-exact."""
+    P, K, ex = fhew_setup
+    H.sim_fhew_fast_step.argtypes = [C.c_void_p, C.c_uint, u64p, u64p]
+    H.sim_fhew_fast_blind_rotate_extract.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u64p, u64p]
+    h = sim_key(H, P, ex)
+    acc = orc.residues(9, 2 * P.n, P.big_q).reshape(2, P.n)
+    acc[0, :3] = [0, P.big_q - 1, (P.big_q - 1) // 2]
+    acc[1, :3] = [P.big_q - 1, 0, (P.big_q + 1) // 2]
+    out = np.zeros_like(acc)
+    for j in (0, 5, 99):
+        assert H.sim_fhew_fast_step(h, j, acc.reshape(-1), out.reshape(-1)) == 0
+        assert (out == K.external_product(j, acc)).all(), j
+    for v in (0, 1, 10):
+        assert H.sim_fhew_fast_step(h, 0x8000 | v, acc.reshape(-1), out.reshape(-1)) == 0
+        assert (out == K.automorphism(v, acc)).all(), v
+    bits = np.array([0, 0, 1, 1, 0, 1, 0, 1], dtype=np.int32)
+    cts = K.encrypt(bits, 7)
+    lin = (cts[:4] + cts[4:]) % np.uint64(P.big_q)
+    pro = K.prologue(lin)
+    f = orc.fhew_gate_poly(P, [1, 1, 1, 0])
+    q8 = int(round(P.big_q / 8.0))
+    ref = K.op([1, 1, 1, 0], lin[:2], threads=2)
+    for i in range(2):
+        o = np.zeros(P.n + 1, dtype=np.uint64)
+        a = np.zeros(2 * P.n, dtype=np.uint64)
+        assert H.sim_fhew_fast_blind_rotate_extract(h, f, pro[i], q8, o, a) == 0
+        assert (a.reshape(2, -1) == K.blind_rotate(f, pro[i])).all()
+        assert (o == ref[i]).all()
+    H.sim_fhew_key_free(h)
