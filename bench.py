@@ -197,6 +197,116 @@ def ntt_sweep(pkg, ctx, torch, hbm_peak, reps, log_ns, batch):
     return out
 
 
+def device_ms(torch, stream, fn, warmup, steps):
+    """Device time of `steps` calls of fn (CUDA events on the launching stream, after `warmup` untimed calls)."""
+    for _ in range(warmup):
+        fn()
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def max_over_ranks(torch, dist, world, dev, x):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def tfhe_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps):
+    """BASELINE configs[2]: TFHE programmable bootstrapping at the reference parameter set (tfhe/bootstrapping.rs:141-152:
+    n=1024, N=2048, k=1, TGGSW B=2^23 d=1, key switch B=2^4 d=5), `batch` synthetic LWE ciphertexts per GPU, keys uploaded on
+    rank 0 and broadcast once.  Timing is value independent; parity (bit-exact vs the oracle) is in tests/test_gpu_tfhe.py."""
+    from learn_fhe_b200 import tfhe
+    dev = "cuda:%d" % local
+    stream = torch.cuda.current_stream(local)
+    P = tfhe.bootstrapping_testing_param()
+    n, N, k = P.n, P.big_n, P.k
+    rng = np.random.default_rng(0x5EED0002)
+    shapes = [(n, (k + 1) * P.bs_d, k + 1, N), (k * N * P.ks_d, n), (k * N * P.ks_d,)]
+    if rank == 0:
+        key_np = [rng.integers(0, 1 << 63, size=sh, dtype=np.uint64) for sh in shapes]
+    else:
+        key_np = [np.zeros(sh, dtype=np.uint64) for sh in shapes]
+    bk = tfhe.BootstrappingKey(ctx, P, *key_np)
+    del key_np
+    if world > 1:
+        bk.broadcast(dist, root=0)
+    lut = pkg.to_dev(np.random.default_rng(5).integers(0, 1 << 63, size=N, dtype=np.uint64), local)
+    cts = torch.randint(-(1 << 62), 1 << 62, (batch, n + 1), dtype=torch.int64, device=dev)
+    out = torch.empty_like(cts)
+    tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out)  # warm-up (allocations, tables)
+    ctx.prof_begin()
+    ms = device_ms(torch, stream, lambda: tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out), 0, steps)
+    prof = ctx.prof_end()
+    ms = max_over_ranks(torch, dist, world, dev, ms)
+    br = prof.get("tfhe_blind_rotate_kernel", {"ms": 0.0, "launches": 1})
+    br_ms = br["ms"] / max(1, br["launches"])
+    # f64 operations of the reference dataflow per PBS: n CMUX x [(k+1)d forward + (k+1)^2 d inverse] FFTs of N/2 points,
+    # 10 flops per radix-2 butterfly (4 mul + 6 add, never fused) + twist / pointwise / untwist
+    m, lg, nl = N // 2, (N // 2).bit_length() - 1, (k + 1) * P.bs_d
+    ffts = n * (nl + (k + 1) * nl)
+    flops = ffts * (m // 2) * lg * 10 + n * (nl * m * 6 + (k + 1) * nl * m * (6 + 8))
+    fp64_peak = 148 * 64 * 2 * 1.965e9  # nominal: 64 FP64 FMA lanes per SM per clock (no measured f64 peak in MEASURED_PEAKS.json)
+    res = {"metric": "tfhe_pbs_per_sec", "value": batch * world * steps / (ms * 1e-3), "unit": "PBS/s", "batch_per_gpu": batch,
+           "steps": steps, "ms_per_step": ms / steps,
+           "config": "TFHE-T (tfhe/bootstrapping.rs:141-152): n=1024 N=2048 k=1 B=2^23 d=1, ks B=2^4 d=5; bit-exact f64 FFT dataflow",
+           "key_bytes": bk.nbytes,
+           "kernels": {kk: {"ms_per_launch": v["ms"] / v["launches"], "launches": v["launches"]} for kk, v in prof.items()},
+           "roofline": {"bound": "fp64", "kernel": "tfhe_blind_rotate_kernel", "achieved": flops * batch / (br_ms * 1e-3) / 1e12 if br_ms else None,
+                        "peak": fp64_peak / 1e12, "unit": "TFLOP/s f64 (algorithmic, unfused mul/add; peak nominal 64 FMA lanes/SM/clk)",
+                        "frac": flops * batch / (br_ms * 1e-3) / fp64_peak if br_ms else None, "traffic": None,
+                        "flops_per_pbs": flops}}
+    bk.free()
+    del cts, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def ckks_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps):
+    """BASELINE configs[3]: Ckks::mul (tensor product + relinearise + rescale, ckks.rs:255-272) at N=2^16, log_qi=55, L=8,
+    full level, `batch` ciphertext pairs per GPU.  Parity (bit-exact vs the oracle) is in tests/test_gpu_ckks.py."""
+    from learn_fhe_b200 import ckks
+    dev = "cuda:%d" % local
+    stream = torch.cuda.current_stream(local)
+    log_n, L = 16, 8
+    P = ckks.CkksParam.new(ctx, log_n, 55, L)
+    rng = np.random.default_rng(0x5EED0003)
+    ksk = np.stack([np.stack([rng.integers(0, q, size=P.n, dtype=np.uint64) for q in P.qs + P.ps]) for _ in range(2)])
+    rlk = ckks.CkksKeySwitchingKey(P, ksk)
+
+    def rand_ct():
+        t = torch.empty((batch, 2, L, P.n), dtype=torch.int64, device=dev)
+        for i, q in enumerate(P.qs):
+            t[:, :, i, :].random_(0, q)
+        return t
+
+    ct0, ct1 = rand_ct(), rand_ct()
+    out = torch.empty((batch, 2, L - 1, P.n), dtype=torch.int64, device=dev)
+    for _ in range(2):
+        ckks.Ckks.mul_dev(P, rlk, L, ct0, ct1, out)  # warm-up (workspace allocation, tables)
+    ctx.prof_begin()
+    ms = device_ms(torch, stream, lambda: ckks.Ckks.mul_dev(P, rlk, L, ct0, ct1, out), 0, steps)
+    prof = ctx.prof_end()
+    ms = max_over_ranks(torch, dist, world, dev, ms)
+    io_bytes = batch * (2 * 2 * L + 2 * (L - 1)) * P.n * 8
+    res = {"metric": "ckks_mul_relin_rescale_per_sec", "value": batch * world * steps / (ms * 1e-3), "unit": "mult/s",
+           "batch_per_gpu": batch, "steps": steps, "ms_per_step": ms / steps,
+           "config": "CKKS-T: N=2^16, log_qi=55, L=8 (+8 special primes), level 8 -> 7, rlk resident",
+           "compulsory_hbm_gbs": io_bytes * steps / (ms * 1e-3) / 1e9, "ntt_per_mult": 9 * L + 3 * L,
+           "kernels": {kk: {"ms_per_step": v["ms"] / steps, "launches": v["launches"]} for kk, v in prof.items()}}
+    rlk.free()
+    P.free()
+    del ct0, ct1, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +318,10 @@ def main():
     ap.add_argument("--no-ntt", action="store_true", help="skip the NTT sweep leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ntt-reps", type=int, default=20)
+    ap.add_argument("--no-tfhe", action="store_true", help="skip the TFHE PBS leg (BASELINE configs[2])")
+    ap.add_argument("--no-ckks", action="store_true", help="skip the CKKS hom-mult leg (BASELINE configs[3])")
+    ap.add_argument("--tfhe-batch", type=int, default=16384, help="PBS per GPU per step")
+    ap.add_argument("--ckks-batch", type=int, default=512, help="ciphertext pairs per GPU per step")
     args = ap.parse_args()
     args.warmup_ref = max(1, min(args.warmup, 1))
     rank = int(os.environ.get("RANK", "0"))
@@ -329,6 +443,12 @@ def main():
     if rank == 0 and not args.no_ntt:
         ntt = ntt_sweep(pkg, ctx, torch, hbm_peak, args.ntt_reps, list(range(10, 17)), 4096)
 
+    # free the FHEW batch buffers before the wider legs
+    del ins, outs
+    torch.cuda.empty_cache()
+    tfhe_res = None if args.no_tfhe else tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, max(1, min(args.steps, 2)))
+    ckks_res = None if args.no_ckks else ckks_leg(pkg, ctx, torch, dist, world, rank, local, args.ckks_batch, max(1, min(args.steps, 3)))
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         from oracle import orc  # cpu_baseline leg: the oracle as the timed CPU port + bit-exact checker of a GPU sample
@@ -368,6 +488,10 @@ def main():
                         "d2h_bytes_per_step": int(ct_words * 8)},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": kt["roofline"], "kernels": kt["kernels"], "cpu_baseline": cpu, "peak_source": peak_src}
+        if tfhe_res is not None:
+            line["tfhe_pbs"] = tfhe_res
+        if ckks_res is not None:
+            line["ckks_mul"] = ckks_res
         if ntt is not None:
             line["ntt"] = ntt
             best = max(ntt, key=lambda r: (r["log_n"], r["word_bits"]))

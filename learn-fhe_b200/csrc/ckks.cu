@@ -48,8 +48,11 @@ struct RnsExtOwned {
         tab.frac = upload_vec(h.frac);
         tab.mp = upload_vec(h.mp);
         tab.qhat_ps = upload_vec(h.qhat_ps);
+        tab.qhat_ps_sh = upload_vec(h.qhat_ps_sh);
+        tab.lazy = h.lazy;
         tab.uq_ps = upload_vec(h.uq_ps);
-        owned = {(void*)tab.mq, (void*)tab.qhat_inv, (void*)tab.qhat_inv_sh, (void*)tab.frac, (void*)tab.mp, (void*)tab.qhat_ps, (void*)tab.uq_ps};
+        owned = {(void*)tab.mq, (void*)tab.qhat_inv, (void*)tab.qhat_inv_sh, (void*)tab.frac, (void*)tab.mp, (void*)tab.qhat_ps,
+                 (void*)tab.qhat_ps_sh, (void*)tab.uq_ps};
         ok = true;
         for (void* p : owned) ok = ok && p != nullptr;
     }

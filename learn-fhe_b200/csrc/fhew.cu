@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(FF_THREADS) fhew_blind_rotate_fast_kernel(Fhew
     uint32_t* words = reinterpret_cast<uint32_t*>(smem_raw);
     FhewFastSmem S;
     S.acc = words;
-    S.dig = words + 4 * FF_N;
-    S.tw = reinterpret_cast<TwPair<uint32_t>*>(words + 12 * FF_N);
+    S.dig = words + 2 * FF_N;
+    S.tw = reinterpret_cast<TwPair<uint32_t>*>(words + 10 * FF_N);
     S.itw = S.tw + FF_N;
     uint16_t* steps = reinterpret_cast<uint16_t*>(words + ff_fixed_words());
     const uint32_t max_steps = P.n_s + FF_N + 2;
@@ -203,12 +203,8 @@ __global__ void __launch_bounds__(FF_THREADS) fhew_blind_rotate_fast_kernel(Fhew
             if (tid == 0) atomicExch(err, 1);
             ns = 0;
         }
-        uint32_t cur = 0;
-        for (uint32_t s = 0; s < ns; ++s) {
-            ff_step(P, S, steps[s], cur, run);
-            cur ^= 1u;
-        }
-        const uint32_t* acc = S.acc + (size_t)cur * 2 * FF_N;
+        for (uint32_t s = 0; s < ns; ++s) ff_step(P, S, steps[s], run);
+        const uint32_t* acc = S.acc;
         if (mode == 0) {
             ff_extract(P, acc, post_add, out + ct * (FF_N + 1), tid);
         } else {
@@ -309,7 +305,7 @@ static fhe_status run_blind_rotate_fast(fhe_ctx* ctx, const fhe_fhew_key* key, c
     kern<<<grid, FF_THREADS, smem, ctx->stream>>>(key->F, d_f, d_ct2n, post_add, count, d_out, mode, key->d_err);
     return after_launch(ctx, "fhew_blind_rotate_kernel");
 }
-static bool fhew_fast_instantiated(unsigned dg, unsigned dr) { return dg >= 1 && dg <= 4 && dr >= 1 && dr <= 8; }
+static bool fhew_fast_instantiated(unsigned dg, unsigned dr) { return dg >= 1 && dg <= 4 && dr >= 1 && dr <= 4; }
 
 template <typename OT>
 static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n, uint32_t post_add,
@@ -414,7 +410,8 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     P.ak = (const uint2*)key->d_ak;
     P.dlog = (const uint16_t*)key->d_dlog;
     // fast path structures
-    if (pp->log_n == FF_LOGN && q < (1ull << 28) && P.small_digits && fhew_fast_instantiated(pp->rgsw_d, pp->rlwe_d)) {
+    if (pp->log_n == FF_LOGN && q < (1ull << 28) && P.small_digits && pp->rgsw_log_b >= 2 && pp->rlwe_log_b >= 2 &&
+        fhew_fast_instantiated(pp->rgsw_d, pp->rlwe_d)) {
         FhewFastDev& F = key->F;
         F.m.q = (uint32_t)q;
         F.m.q2 = (uint32_t)(2 * q);

@@ -12,7 +12,7 @@
 //     P4  inverse radix-16 pass (2 polynomials); P5 inverse radix-8 pass with n^-1 folded in, (+ b(X^t)), canonical result
 //         written to the other accumulator buffer (ping-pong, so permuted reads of the old accumulator stay valid).
 //   5 barriers per step (the first generation needs 9) and about a third of its instructions: lazy forward butterflies
-//   (values < 16 Q, one min() before P3), twiddles in shared memory, swizzled addresses formed as swz(base) ^ const_j.
+//   (digits enter as digit + Q < 2 Q, values stay < 16 Q < 2^32, one min() before P3), twiddles in shared memory, swizzled addresses formed as swz(base) ^ const_j.
 // __host__ __device__ so tests/hostsim can replay it.
 #pragma once
 #include "fhew_core.cuh"
@@ -40,14 +40,15 @@ struct FhewFastDev {
     uint32_t ak_tinv[40];  // t^-1 mod 2N
 };
 
-// shared memory (32-bit words): acc[2 buf][2 (a,b)][N] | dig[8][N] | tw[N pairs] | itw[N pairs] | steps | a2n
+// shared memory (32-bit words): acc[2 (a,b)][N] | dig[8][N] | tw[N pairs] | itw[N pairs] | steps | a2n
+// (during an automorphism step dig[7] parks b(X^t): its digit polynomials occupy dig[0..d_r), d_r <= 4)
 struct FhewFastSmem {
     uint32_t* acc;
     uint32_t* dig;
     TwPair<uint32_t>* tw;
     TwPair<uint32_t>* itw;
 };
-HD constexpr size_t ff_fixed_words() { return (size_t)4 * FF_N + 8 * FF_N + 4 * FF_N; }
+HD constexpr size_t ff_fixed_words() { return (size_t)2 * FF_N + 8 * FF_N + 4 * FF_N; }
 
 // swizzle of the digit polynomials: bits 5,6,7 -> 2,3,4 and bit 8 -> 2 (the radix-16 pass at stride 4 needs bit 8)
 HD uint32_t swzf(uint32_t p) { return p ^ ((p >> 3) & 0x1Cu) ^ ((p >> 6) & 4u); }
@@ -56,6 +57,13 @@ HD uint32_t ff_reduce64(const FhewFastDev& P, uint64_t x) {  // any x -> [0, Q)
     const uint64_t qh = mulhi_u64(x, P.mu64);
     const uint32_t r = (uint32_t)(x - qh * (uint64_t)P.m.q);  // [0, 2Q)
     return umin_(r, r - P.m.q);
+}
+
+// value of poly(X^t) at coefficient c, read from the canonical polynomial `src`: +-src[c * tinv mod 2N]  (avec.rs:34-50)
+HD uint32_t ff_perm_coef(const FhewFastDev& P, const uint32_t* src, uint32_t tinv, uint32_t c) {
+    const uint32_t i = (c * tinv) & (2 * FF_N - 1);
+    const uint32_t v = src[i & (FF_N - 1)];
+    return i >= (uint32_t)FF_N ? P.m.q - v - (v == 0 ? P.m.q : 0) : v;  // neg(0) = 0
 }
 
 // ---- P1: decompose + first forward radix-8 pass (stages 0..2, stride 64) --------------------------------------------------------
@@ -67,12 +75,15 @@ HD uint32_t ff_dec_start(const FhewFastDev& P, const DecompParam& dp, uint32_t v
     const uint32_t sh = r >> dp.rounding_bits;
     return sh < (P.m.q >> 1) ? sh : sh - P.m.q;
 }
+// For log_b >= 2 the reference's carry rule `limb + (x & 1) > B/2` is `limb > B/2` (B/2 is even, so the tie limb = B/2 has
+// an even limb and never carries), hence with h = B/2 - 1: signed digit = ((x + h) & (B-1)) - h, next x = (x + h) >> log_b
+// (bits above the log_b * d consumed ones are irrelevant).  The digit is returned as the representative digit + Q in
+// (0, 2Q): the forward butterflies are lazy, so no canonical form is needed.
 HD uint32_t ff_dec_step(const FhewFastDev& P, const DecompParam& dp, uint32_t& x) {
-    const uint32_t mask = (1u << dp.log_b) - 1u, b_by_2 = 1u << (dp.log_b - 1);
-    const uint32_t limb = x & mask;
-    const uint32_t carry = (limb + (x & 1u) > b_by_2) ? 1u : 0u;
-    x = (x >> dp.log_b) + carry;
-    return limb + (carry ? (uint32_t)dp.neg_b : 0u);
+    const uint32_t mask = (1u << dp.log_b) - 1u, hb = (1u << (dp.log_b - 1)) - 1u;
+    const uint32_t t = x + hb;
+    x = t >> dp.log_b;
+    return (t & mask) + (P.m.q - hb);
 }
 // Thread (g, h) holds the 8 coefficients at positions g + 64 j (values from acc_in[h] for an external product, from the
 // permuted a(X^t) for an automorphism) and walks the digits; digit k becomes polynomial `pbase + k` if lo <= k < hi.
@@ -91,6 +102,10 @@ HD void ff_p1(const FhewFastDev& P, const FhewFastSmem& S, const DecompParam& dp
             v = acc_in[(h << FF_LOGN) + c];
         }
         st[j] = ff_dec_start(P, dp, v);
+    }
+    if (is_auto && h == 1) {  // park b(X^t) for P5: the accumulator is updated in place
+#pragma unroll
+        for (int j = 0; j < 8; ++j) S.dig[7 * FF_N + g + 64u * j] = ff_perm_coef(P, acc_in + FF_N, tinv, g + 64u * j);
     }
     const uint32_t P0 = swzf(g);
 #pragma unroll 1
@@ -208,21 +223,14 @@ HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, ui
     }
 }
 
-// value of poly(X^t) at coefficient c, read from the canonical polynomial `src`: +-src[c * tinv mod 2N]  (avec.rs:34-50)
-HD uint32_t ff_perm_coef(const FhewFastDev& P, const uint32_t* src, uint32_t tinv, uint32_t c) {
-    const uint32_t i = (c * tinv) & (2 * FF_N - 1);
-    const uint32_t v = src[i & (FF_N - 1)];
-    return i >= (uint32_t)FF_N ? P.m.q - v - (v == 0 ? P.m.q : 0) : v;  // neg(0) = 0
-}
-
-// One full step; `cur` = index of the accumulator buffer holding the input (the result goes to the other one).
+// One full step on the accumulator S.acc (updated in place).
 // run(phase): phase(tid) for every thread of the CTA followed by a barrier.
 template <typename Run>
-HD void ff_step(const FhewFastDev& P, const FhewFastSmem& S, uint32_t step, uint32_t cur, Run run) {
+HD void ff_step(const FhewFastDev& P, const FhewFastSmem& S, uint32_t step, Run run) {
     const bool is_auto = (step & FHEW_STEP_AUTO) != 0;
     const uint32_t idx = step & 0x7FFFu;
-    const uint32_t* acc_in = S.acc + (size_t)cur * 2 * FF_N;
-    uint32_t* acc_out = S.acc + (size_t)(cur ^ 1u) * 2 * FF_N;
+    const uint32_t* acc_in = S.acc;
+    uint32_t* acc_out = S.acc;
     const DecompParam& dp = is_auto ? P.r_dec : P.g_dec;
     const uint32_t d = dp.d, rows = is_auto ? d : 2 * d;
     const uint4* key = is_auto ? P.ak4 + (size_t)idx * d * FF_THREADS * 2 : P.brk4 + (size_t)idx * (2 * d) * FF_THREADS * 2;
@@ -246,7 +254,7 @@ HD void ff_step(const FhewFastDev& P, const FhewFastSmem& S, uint32_t step, uint
     run([&](uint32_t tid) {
         const uint32_t g = tid & 63u, h = tid >> 6;
         // key switch adds the (permuted) body: b' = sum ksk.b_k * limb_k + b(X^t)   (rlwe.rs:184)
-        ff_p5(P, S, acc_out, g, h, is_auto && h == 1, [&](int j) { return ff_perm_coef(P, acc_in + FF_N, tinv, g + 64u * j); });
+        ff_p5(P, S, acc_out, g, h, is_auto && h == 1, [&](int j) { return S.dig[7 * FF_N + g + 64u * j]; });
     });
 }
 

@@ -276,10 +276,10 @@ HD void fast_fwd_first(const FastLimb<L>& d, const typename L::W* g, typename L:
     }
 }
 // forward middle pass (radix-8, shared -> shared); local stages t0 .. t0+2, LL = LOGT - t0 - 3 >= 3
-template <typename L, int LOGT, int TPP>
-HD void fast_fwd_mid(const FastLimb<L>& d, typename L::W* s, int t0, int s0, uint32_t k, bool pre_red, uint32_t tid) {
+template <typename L, int LOGT, int TPP, int t0>
+HD void fast_fwd_mid(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {
     typedef typename L::W W;
-    const int LL = LOGT - t0 - 3;
+    constexpr int LL = LOGT - t0 - 3;
 #pragma unroll 1
     for (uint32_t grp = tid; grp < (1u << (LOGT - 3)); grp += TPP) {
         const uint32_t lo = grp & ((1u << LL) - 1u), hi = grp >> LL;
@@ -333,10 +333,10 @@ HD void fast_inv_first(const FastLimb<L>& d, const typename L::W* g, typename L:
         st_vec8(s, swz2<W>(grp << 3), x);
     }
 }
-template <typename L, int LOGT, int TPP>
-HD void fast_inv_mid(const FastLimb<L>& d, typename L::W* s, int t0, int s0, uint32_t k, uint32_t tid) {
+template <typename L, int LOGT, int TPP, int t0>
+HD void fast_inv_mid(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, uint32_t tid) {
     typedef typename L::W W;
-    const int LL = LOGT - t0 - 3;
+    constexpr int LL = LOGT - t0 - 3;
 #pragma unroll 1
     for (uint32_t grp = tid; grp < (1u << (LOGT - 3)); grp += TPP) {
         const uint32_t lo = grp & ((1u << LL) - 1u), hi = grp >> LL;

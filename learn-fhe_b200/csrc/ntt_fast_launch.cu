@@ -57,18 +57,25 @@ __global__ void __launch_bounds__(FastGeom<LOGT>::NTHR) ntt_fast_tile_kernel(Fas
     if (FWD) {
         if (active) fast_fwd_first<L, LOGT, G::R1, G::TPP>(d, gin, s, a.s0, k, (a.pre_red & 1u) != 0, tid);
         __syncthreads();
-#pragma unroll 1
-        for (int i = 0; i < G::NP3 - 1; ++i) {
-            if (active) fast_fwd_mid<L, LOGT, G::TPP>(d, s, G::R1 + 3 * i, a.s0, k, ((a.pre_red >> (i + 1)) & 1u) != 0, tid);
+        if (G::NP3 > 1) {
+            if (active) fast_fwd_mid<L, LOGT, G::TPP, G::R1>(d, s, a.s0, k, ((a.pre_red >> 1) & 1u) != 0, tid);
             __syncthreads();
         }
+        if (G::NP3 > 2) {
+            if (active) fast_fwd_mid<L, LOGT, G::TPP, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, s, a.s0, k, ((a.pre_red >> 2) & 1u) != 0, tid);
+            __syncthreads();
+        }
+        static_assert(G::NP3 <= 3, "at most two middle passes");
         if (active) fast_fwd_last<L, LOGT, G::TPP>(d, s, g, a.s0, k, ((a.pre_red >> G::NP3) & 1u) != 0, tid);
     } else {
         if (active) fast_inv_first<L, LOGT, G::TPP>(d, gin, s, a.s0, k, tid);
         __syncthreads();
-#pragma unroll 1
-        for (int i = G::NP3 - 2; i >= 0; --i) {
-            if (active) fast_inv_mid<L, LOGT, G::TPP>(d, s, G::R1 + 3 * i, a.s0, k, tid);
+        if (G::NP3 > 2) {
+            if (active) fast_inv_mid<L, LOGT, G::TPP, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, s, a.s0, k, tid);
+            __syncthreads();
+        }
+        if (G::NP3 > 1) {
+            if (active) fast_inv_mid<L, LOGT, G::TPP, G::R1>(d, s, a.s0, k, tid);
             __syncthreads();
         }
         if (active) fast_inv_last<L, LOGT, G::R1, G::TPP, FINAL>(d, s, g, a.s0, k, tid);

@@ -20,7 +20,9 @@ struct RnsExtTab {
     const double* frac;        // [nq]  1.0 / q_i
     const Mod64* mp;           // [np]
     const uint64_t* qhat_ps;   // [np][nq]   (Q/q_i) mod p_k
+    const uint64_t* qhat_ps_sh;  // [np][nq] Shoup companions floor(qhat_ps * 2^64 / p_k)
     const uint64_t* uq_ps;     // [np][nq+1] (u*Q) mod p_k
+    int lazy;                  // 1: every p_k < 2^59, so nq <= 16 lazy Shoup products ([0, 2 p_k) each) sum below 2^64
 };
 
 // rescale_k (rns.rs:99-132) over moduli kept (l) ++ dropped (k)
@@ -81,9 +83,20 @@ HD void rns_extend_coeff(const RnsExtTab& T, const uint64_t* x /* [RNS_MAXL], fi
         const Mod64 m = T.mp[k];
         const uint64_t* qh = T.qhat_ps + (size_t)k * T.nq;
         uint64_t s = 0;
+        if (T.lazy) {
+            // constant * variable products by Shoup (valid for ANY 64-bit v, so v_i needs no reduction mod p_k first); the
+            // canonical value of the sum is what the reference's per-term canonical Zq arithmetic yields
+            const uint64_t* qs = T.qhat_ps_sh + (size_t)k * T.nq;
 #pragma unroll
-        for (int i = 0; i < RNS_MAXL; ++i) {
-            if (i < T.nq) s = m.add(s, m.mul(qh[i], rns_reduce_u64(m, v[i])));
+            for (int i = 0; i < RNS_MAXL; ++i) {
+                if (i < T.nq) s += m.shoup_lazy(v[i], qh[i], qs[i]);
+            }
+            s = rns_reduce_u64(m, s);
+        } else {
+#pragma unroll
+            for (int i = 0; i < RNS_MAXL; ++i) {
+                if (i < T.nq) s = m.add(s, m.mul(qh[i], rns_reduce_u64(m, v[i])));
+            }
         }
         emit(k, m.sub(s, T.uq_ps[(size_t)k * (T.nq + 1) + u]));
     }

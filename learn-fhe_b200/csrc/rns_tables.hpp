@@ -45,7 +45,8 @@ inline uint64_t host_inv_any(uint64_t a, uint64_t q) {  // extended Euclid: q ne
 
 struct RnsExtHost {
     std::vector<Mod64> mq, mp;
-    std::vector<uint64_t> qhat_inv, qhat_inv_sh, qhat_ps, uq_ps;
+    std::vector<uint64_t> qhat_inv, qhat_inv_sh, qhat_ps, qhat_ps_sh, uq_ps;
+    int lazy = 1;
     std::vector<double> frac;
     void build(const std::vector<uint64_t>& qs, const std::vector<uint64_t>& ps) {
         const size_t nq = qs.size(), np = ps.size();
@@ -55,6 +56,8 @@ struct RnsExtHost {
         qhat_inv_sh.resize(nq);
         frac.resize(nq);
         qhat_ps.resize(np * nq);
+        qhat_ps_sh.resize(np * nq);
+        lazy = nq <= 16 ? 1 : 0;
         uq_ps.resize(np * (nq + 1));
         for (size_t i = 0; i < nq; ++i) {
             mq[i] = host_make_mod64(qs[i]);
@@ -64,7 +67,11 @@ struct RnsExtHost {
         }
         for (size_t k = 0; k < np; ++k) {
             mp[k] = host_make_mod64(ps[k]);
-            for (size_t i = 0; i < nq; ++i) qhat_ps[k * nq + i] = host_prod_mod(qs, ps[k], i);
+            if (ps[k] >= (1ull << 59)) lazy = 0;
+            for (size_t i = 0; i < nq; ++i) {
+                qhat_ps[k * nq + i] = host_prod_mod(qs, ps[k], i);
+                qhat_ps_sh[k * nq + i] = host_shoup64(qhat_ps[k * nq + i], ps[k]);
+            }
             const uint64_t qmod = host_prod_mod(qs, ps[k]);
             for (size_t u = 0; u <= nq; ++u) uq_ps[k * (nq + 1) + u] = host_mulmod(u % ps[k], qmod, ps[k]);
         }
@@ -79,6 +86,8 @@ struct RnsExtHost {
         t.frac = frac.data();
         t.mp = mp.data();
         t.qhat_ps = qhat_ps.data();
+        t.qhat_ps_sh = qhat_ps_sh.data();
+        t.lazy = lazy;
         t.uq_ps = uq_ps.data();
         return t;
     }

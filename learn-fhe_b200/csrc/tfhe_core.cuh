@@ -24,7 +24,7 @@ HD double f64_sub_rn(double a, double b) {
     return r;
 #endif
 }
-struct Cx {
+struct alignas(16) Cx {  // 16-byte aligned: one LDS.128 / LDG.128 per complex point
     double re, im;
 };
 HD Cx cx_mul(Cx a, Cx b) {
@@ -213,11 +213,12 @@ namespace fhe {
 template <bool FWD, typename Run>
 HD void fft_run(Cx* s, uint32_t nf, const FftTab& T, Run run) {
     const int lg = T.lg;
-    const FftPlan plan = make_fft_plan(lg);
+    // pass plan in closed form (no arrays: they would live in local memory): pass 0 has fft_r1(lg) stages, the rest 3
+    const int r1 = fft_r1(lg), npass = lg == 0 ? 0 : 1 + (lg - r1) / 3;
     const Cx* tw = FWD ? T.tw_bo : T.tw_inv_bo;
-    for (int pp = 0; pp < plan.n; ++pp) {
-        const int pi = FWD ? pp : plan.n - 1 - pp;
-        const int r = plan.r[pi], l0 = plan.l0[pi];
+    for (int pp = 0; pp < npass; ++pp) {
+        const int pi = FWD ? pp : npass - 1 - pp;
+        const int r = pi == 0 ? r1 : 3, l0 = pi == 0 ? 0 : r1 + 3 * (pi - 1);
         const uint32_t lgroups = (uint32_t)(lg - r);
         run([&](uint32_t tid, uint32_t nthr) {
             const uint32_t total = nf << lgroups;
