@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(TFHE_THREADS) tfhe_key_fft_kernel(FftTab T, un
 }
 
 // blind_rotate + sample_extract(0): ct_in [count][n_lwe+1] -> out [count][kN+1]
-__global__ void __launch_bounds__(TFHE_THREADS) tfhe_blind_rotate_kernel(TfheDev P, const uint64_t* __restrict__ lut,
+__global__ void __launch_bounds__(TFHE_THREADS, 2) tfhe_blind_rotate_kernel(TfheDev P, const uint64_t* __restrict__ lut,
                                                                           const uint64_t* __restrict__ ct_in, unsigned long long count,
                                                                           uint64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(TFHE_THREADS) tfhe_blind_rotate_kernel(TfheDev
 }
 
 // Tggsw::external_product(brk[idx[c]], glwe_c): glwe [count][k+1][N]
-__global__ void __launch_bounds__(TFHE_THREADS) tfhe_ext_kernel(TfheDev P, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ in,
+__global__ void __launch_bounds__(TFHE_THREADS, 2) tfhe_ext_kernel(TfheDev P, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ in,
                                                                  unsigned long long count, uint64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t n = 1u << P.log_n, k = P.k, d = P.bs_dec.d;
@@ -163,9 +163,9 @@ __global__ void __launch_bounds__(TFHE_THREADS) tfhe_ext_kernel(TfheDev P, const
         const Cx* key = P.brk + (((size_t)idx[c] * (k + 1) * d * (k + 1)) << P.fft.lg);
         tfhe_external_product(
             P, F, Pb, key, [&](uint32_t j, uint32_t x) { return g[(size_t)j * n + x]; },
-            [&](uint32_t oo, uint32_t c0, uint64_t v0, uint32_t c1, uint64_t v1) {
-                o[(size_t)oo * n + c0] = v0;
-                o[(size_t)oo * n + c1] = v1;
+            [&](uint32_t oo, uint32_t c0, uint64_t v0, uint32_t c1, uint64_t v1, bool first) {
+                o[(size_t)oo * n + c0] = first ? v0 : o[(size_t)oo * n + c0] + v0;
+                o[(size_t)oo * n + c1] = first ? v1 : o[(size_t)oo * n + c1] + v1;
             },
             run);
     }

