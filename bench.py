@@ -342,6 +342,8 @@ def main():
     dev = "cuda:%d" % local
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     hbm_peak, peak_src, peak_json = peaks()
     ctx = pkg.Context(local)

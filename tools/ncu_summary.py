@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Condense an .ncu-rep (ncu --set full) into the per-launch CSV kept under profiles/: duration, DRAM traffic, pipe and
+issue utilisation, occupancy limiters, shared-memory conflicts, top stall reasons.
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_ncu_<what>.csv"""
+import csv
+import subprocess
+import sys
+
+KEYS = [("duration", "gpu__time_duration.sum"), ("regs", "launch__registers_per_thread"),
+        ("warp_inst", "smsp__inst_executed.sum"), ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        ("pipe_alu_pct", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+        ("pipe_fmaheavy_pct", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+        ("pipe_fp64_inst_pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+        ("lsu_wavefronts_pct", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+        ("dram_read", "dram__bytes_read.sum"), ("dram_write", "dram__bytes_write.sum"),
+        ("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        ("l2_pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+        ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+        ("occ_limit_regs", "launch__occupancy_limit_registers"), ("occ_limit_smem", "launch__occupancy_limit_shared_mem"),
+        ("smem_bank_conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+        ("smem_wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")]
+
+
+def main():
+    rep = sys.argv[1]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    w = csv.writer(sys.stdout)
+    w.writerow(["kernel", "block", "grid"] + ["%s [%s]" % (k, units[col[m]]) if m in col else k for k, m in KEYS] + ["top_stalls"])
+    for r in rows[2:]:
+        st = [(h.replace("smsp__pcsamp_warps_issue_stalled_", ""), float(r[i])) for i, h in enumerate(hdr)
+              if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued") and r[i] not in ("", "0")]
+        st.sort(key=lambda x: -x[1])
+        tot = sum(v for _, v in st) or 1.0
+        w.writerow([r[col["Kernel Name"]], r[col["Block Size"]], r[col["Grid Size"]]] + [r[col[m]] if m in col else "" for _, m in KEYS] +
+                   [" ".join("%s=%.0f%%" % (k, 100 * v / tot) for k, v in st[:6])])
+
+
+if __name__ == "__main__":
+    main()
