@@ -11,6 +11,7 @@
 // domain against a key-switching key that was transformed at upload, so one Ckks::mul costs 9l+3L transforms instead of
 // the reference's 3*(4l + 2(l+L)).  Limb-batched transforms use the multi-modulus fast NTT (ntt_fast_launch.cu).
 #include <algorithm>
+#include <cstring>
 #include <functional>
 #include <vector>
 
@@ -21,6 +22,8 @@
 namespace fhe {
 
 // ---- host-built tables (values computed by rns_tables.hpp, shared with tests/hostsim) --------------------------------
+// The tables travel BY VALUE as kernel parameters (RnsExtTabV / RescaleTabV, 7.5 / 9.3 KiB: CUDA 12 large kernel
+// parameters), so they live in the constant bank; nothing is uploaded.
 template <typename T>
 static T* upload_vec(const std::vector<T>& h) {
     T* d = nullptr;
@@ -32,70 +35,50 @@ static T* upload_vec(const std::vector<T>& h) {
     }
     return d;
 }
-
 struct RnsExtOwned {
-    RnsExtTab tab{};
-    std::vector<void*> owned;
+    RnsExtTabV tab;
     bool ok = false;
     void build(const std::vector<uint64_t>& qs, const std::vector<uint64_t>& ps) {
+        ok = qs.size() <= (size_t)RNS_MAXL && ps.size() <= (size_t)RNS_MAXL;
+        if (!ok) return;
         RnsExtHost h;
         h.build(qs, ps);
-        tab.nq = (int)qs.size();
-        tab.np = (int)ps.size();
-        tab.mq = upload_vec(h.mq);
-        tab.qhat_inv = upload_vec(h.qhat_inv);
-        tab.qhat_inv_sh = upload_vec(h.qhat_inv_sh);
-        tab.frac = upload_vec(h.frac);
-        tab.mp = upload_vec(h.mp);
-        tab.qhat_ps = upload_vec(h.qhat_ps);
-        tab.qhat_ps_sh = upload_vec(h.qhat_ps_sh);
-        tab.lazy = h.lazy;
-        tab.uq_ps = upload_vec(h.uq_ps);
-        owned = {(void*)tab.mq, (void*)tab.qhat_inv, (void*)tab.qhat_inv_sh, (void*)tab.frac, (void*)tab.mp, (void*)tab.qhat_ps,
-                 (void*)tab.qhat_ps_sh, (void*)tab.uq_ps};
-        ok = true;
-        for (void* p : owned) ok = ok && p != nullptr;
+        memset(&tab, 0, sizeof tab);
+        h.fill(tab);
     }
-    void release() {
-        for (void* p : owned)
-            if (p) cudaFree(p);
-        owned.clear();
-    }
+    void release() {}
 };
 struct RescaleOwned {
-    RescaleTab tab{};
-    RnsExtOwned ext;
-    std::vector<void*> owned;
+    RescaleTabV tab;
     bool ok = false;
     void build(const std::vector<uint64_t>& all, size_t k) {
         RescaleHost h;
         h.build(all, k);
-        ok = true;
+        ok = h.kept.size() <= (size_t)RNS_MAXL && k <= (size_t)RNS_MAXL;
+        if (!ok) return;
+        memset(&tab, 0, sizeof tab);
         if (k > 1) {
-            ext.build(h.dropped, h.kept);
-            ok = ext.ok;
-            tab.ext = ext.tab;
+            RnsExtHost e;
+            e.build(h.dropped, h.kept);
+            e.fill(tab.ext);
         }
         tab.l = (int)h.kept.size();
         tab.k = (int)k;
-        tab.m_all = upload_vec(h.m_all);
-        tab.ph = upload_vec(h.ph);
-        tab.pinv = upload_vec(h.pinv);
-        tab.pinv_sh = upload_vec(h.pinv_sh);
-        owned = {(void*)tab.m_all, (void*)tab.ph, (void*)tab.pinv, (void*)tab.pinv_sh};
-        for (void* p : owned) ok = ok && p != nullptr;
+        for (size_t i = 0; i < all.size(); ++i) {
+            tab.m_all[i] = h.m_all[i];
+            tab.ph[i] = h.ph[i];
+        }
+        for (size_t i = 0; i < h.kept.size(); ++i) {
+            tab.pinv[i] = h.pinv[i];
+            tab.pinv_sh[i] = h.pinv_sh[i];
+        }
     }
-    void release() {
-        ext.release();
-        for (void* p : owned)
-            if (p) cudaFree(p);
-        owned.clear();
-    }
+    void release() {}
 };
 
 // ---- kernels -----------------------------------------------------------------------------------------------------------
 // in [B][in_limbs][n] (limbs in_off .. in_off+nq-1 are the source base) -> out [B][out_limbs][n] at limbs out_off..
-__global__ void __launch_bounds__(256) rns_extend_kernel(RnsExtTab T, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
+__global__ void __launch_bounds__(256) rns_extend_kernel(const __grid_constant__ RnsExtTabV T, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
                                                          int in_limbs, int in_off, uint64_t* __restrict__ out, int out_limbs, int out_off) {
     const unsigned long long total = batch << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
     const size_t n = (size_t)1 << log_n;
@@ -122,7 +105,7 @@ __global__ void __launch_bounds__(256) rns_copy_limbs_kernel(int log_n, unsigned
     }
 }
 // rescale_k: in [B][l+k][n] (+ pre [B][l+k][n]) -> out [B][l][n] (+ post [B][l][n]; if post_even_only only for even b)
-__global__ void __launch_bounds__(256) rns_rescale_kernel(RescaleTab R, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
+__global__ void __launch_bounds__(256) rns_rescale_kernel(const __grid_constant__ RescaleTabV R, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
                                                           const uint64_t* __restrict__ pre, const uint64_t* __restrict__ post, int post_even_only,
                                                           uint64_t* __restrict__ out) {
     const unsigned long long total = batch << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -220,7 +203,7 @@ static fhe_status cached_table(fhe_ctx* ctx, std::vector<uint64_t> key, Build bu
         if (!o->ok) {
             o->release();
             delete o;
-            return fail(ctx, FHE_ENOMEM, "RNS table upload failed");
+            return fail(ctx, FHE_EINVAL, "RNS table: at most %d source / target limbs per conversion", RNS_MAXL);
         }
         ctx->cleanup.push_back([o]() {
             o->release();

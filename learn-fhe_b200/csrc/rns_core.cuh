@@ -11,18 +11,31 @@ namespace fhe {
 
 static constexpr int RNS_MAXL = 16;  // max source limbs of one base conversion (kept in registers)
 
-// device-side view of one (source base qs -> target base ps) conversion table
+// Conversion table of one (source base qs -> target base ps) pair.  Two layouts with identical member names so the
+// per-coefficient code is shared: RnsExtTab (pointers; tests/hostsim) and RnsExtTabV (fixed-size arrays, passed BY VALUE as a
+// kernel parameter so every constant is a uniform constant-bank operand instead of a global load).  2-D tables use the fixed
+// strides RNS_MAXL / RNS_MAXL + 1.
 struct RnsExtTab {
     int nq, np;
+    int lazy;                  // 1: every p_k < 2^58, so nq <= 16 lazy Shoup products ([0, 4 p_k) each) sum below 2^64
     const Mod64* mq;           // [nq]
     const uint64_t* qhat_inv;  // [nq]  (Q/q_i)^-1 mod q_i, with Shoup companion in qhat_inv_sh
     const uint64_t* qhat_inv_sh;
     const double* frac;        // [nq]  1.0 / q_i
     const Mod64* mp;           // [np]
-    const uint64_t* qhat_ps;   // [np][nq]   (Q/q_i) mod p_k
-    const uint64_t* qhat_ps_sh;  // [np][nq] Shoup companions floor(qhat_ps * 2^64 / p_k)
-    const uint64_t* uq_ps;     // [np][nq+1] (u*Q) mod p_k
-    int lazy;                  // 1: every p_k < 2^59, so nq <= 16 lazy Shoup products ([0, 2 p_k) each) sum below 2^64
+    const uint64_t* qhat_ps;   // [np][RNS_MAXL]     (Q/q_i) mod p_k
+    const uint64_t* qhat_ps_sh;  // [np][RNS_MAXL]   Shoup companions floor(qhat_ps * 2^64 / p_k)
+    const uint64_t* uq_ps;     // [np][RNS_MAXL + 1] (u*Q) mod p_k
+};
+struct RnsExtTabV {
+    int nq, np;
+    int lazy, pad_;
+    Mod64 mq[RNS_MAXL];
+    uint64_t qhat_inv[RNS_MAXL], qhat_inv_sh[RNS_MAXL];
+    double frac[RNS_MAXL];
+    Mod64 mp[RNS_MAXL];
+    uint64_t qhat_ps[RNS_MAXL * RNS_MAXL], qhat_ps_sh[RNS_MAXL * RNS_MAXL];
+    uint64_t uq_ps[RNS_MAXL * (RNS_MAXL + 1)];
 };
 
 // rescale_k (rns.rs:99-132) over moduli kept (l) ++ dropped (k)
@@ -33,6 +46,13 @@ struct RescaleTab {
     const uint64_t* ph;     // [l + k]  (P >> 1) mod q_i, P = prod(dropped)
     const uint64_t* pinv;   // [l]      P^-1 mod q_i (+ Shoup companion)
     const uint64_t* pinv_sh;
+};
+struct RescaleTabV {
+    RnsExtTabV ext;
+    int l, k;
+    Mod64 m_all[2 * RNS_MAXL];
+    uint64_t ph[2 * RNS_MAXL];
+    uint64_t pinv[RNS_MAXL], pinv_sh[RNS_MAXL];
 };
 
 // v mod m.q for an arbitrary 64-bit v
@@ -64,8 +84,8 @@ HD double u64_to_f64(uint64_t v) {
 
 // Rns::extend_bases for one coefficient (rns.rs:331-345): x[i] = residue mod q_i (i < nq) -> y[k] = residue mod p_k.
 // `emit(k, y)` receives the outputs.
-template <typename Emit>
-HD void rns_extend_coeff(const RnsExtTab& T, const uint64_t* x /* [RNS_MAXL], first nq valid */, Emit emit) {
+template <typename Tab, typename Emit>
+HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq valid */, Emit emit) {
     uint64_t v[RNS_MAXL];
     double acc = 0.0;
 #pragma unroll
@@ -81,15 +101,15 @@ HD void rns_extend_coeff(const RnsExtTab& T, const uint64_t* x /* [RNS_MAXL], fi
     const uint32_t u = (uint32_t)f64_round_half_away(acc);
     for (int k = 0; k < T.np; ++k) {
         const Mod64 m = T.mp[k];
-        const uint64_t* qh = T.qhat_ps + (size_t)k * T.nq;
+        const uint64_t* qh = T.qhat_ps + (size_t)k * RNS_MAXL;
         uint64_t s = 0;
         if (T.lazy) {
             // constant * variable products by Shoup (valid for ANY 64-bit v, so v_i needs no reduction mod p_k first); the
             // canonical value of the sum is what the reference's per-term canonical Zq arithmetic yields
-            const uint64_t* qs = T.qhat_ps_sh + (size_t)k * T.nq;
+            const uint64_t* qs = T.qhat_ps_sh + (size_t)k * RNS_MAXL;
 #pragma unroll
             for (int i = 0; i < RNS_MAXL; ++i) {
-                if (i < T.nq) s += m.shoup_lazy(v[i], qh[i], qs[i]);
+                if (i < T.nq) s += qh[i] * v[i] - mulhi_u64_approx(qs[i], v[i]) * m.q;  // [0, 4 p_k): quotient off by <= 2
             }
             s = rns_reduce_u64(m, s);
         } else {
@@ -98,14 +118,14 @@ HD void rns_extend_coeff(const RnsExtTab& T, const uint64_t* x /* [RNS_MAXL], fi
                 if (i < T.nq) s = m.add(s, m.mul(qh[i], rns_reduce_u64(m, v[i])));
             }
         }
-        emit(k, m.sub(s, T.uq_ps[(size_t)k * (T.nq + 1) + u]));
+        emit(k, m.sub(s, T.uq_ps[(size_t)k * (RNS_MAXL + 1) + u]));
     }
 }
 
 // rescale_k for one coefficient: x(i) reads limb i of the input (already including any pre-addend, canonical);
 // emit(i, y) receives the kept limbs before any post-addend.
-template <typename Load, typename Emit>
-HD void rns_rescale_coeff(const RescaleTab& R, Load x, Emit emit) {
+template <typename Tab, typename Load, typename Emit>
+HD void rns_rescale_coeff(const Tab& R, Load x, Emit emit) {
     const int l = R.l, k = R.k;
     // round(): s_i = x_i + (P >> 1) mod q_i, for every limb (rns.rs:120-125)
     auto rounded = [&](int i) { return R.m_all[i].add(x(i), R.ph[i]); };

@@ -55,10 +55,10 @@ struct RnsExtHost {
         qhat_inv.resize(nq);
         qhat_inv_sh.resize(nq);
         frac.resize(nq);
-        qhat_ps.resize(np * nq);
-        qhat_ps_sh.resize(np * nq);
+        qhat_ps.assign(np * RNS_MAXL, 0);
+        qhat_ps_sh.assign(np * RNS_MAXL, 0);
         lazy = nq <= 16 ? 1 : 0;
-        uq_ps.resize(np * (nq + 1));
+        uq_ps.assign(np * (RNS_MAXL + 1), 0);
         for (size_t i = 0; i < nq; ++i) {
             mq[i] = host_make_mod64(qs[i]);
             qhat_inv[i] = host_inv_any(host_prod_mod(qs, qs[i], i), qs[i]);
@@ -67,14 +67,33 @@ struct RnsExtHost {
         }
         for (size_t k = 0; k < np; ++k) {
             mp[k] = host_make_mod64(ps[k]);
-            if (ps[k] >= (1ull << 59)) lazy = 0;
+            if (ps[k] >= (1ull << 58)) lazy = 0;
             for (size_t i = 0; i < nq; ++i) {
-                qhat_ps[k * nq + i] = host_prod_mod(qs, ps[k], i);
-                qhat_ps_sh[k * nq + i] = host_shoup64(qhat_ps[k * nq + i], ps[k]);
+                qhat_ps[k * RNS_MAXL + i] = host_prod_mod(qs, ps[k], i);
+                qhat_ps_sh[k * RNS_MAXL + i] = host_shoup64(qhat_ps[k * RNS_MAXL + i], ps[k]);
             }
             const uint64_t qmod = host_prod_mod(qs, ps[k]);
-            for (size_t u = 0; u <= nq; ++u) uq_ps[k * (nq + 1) + u] = host_mulmod(u % ps[k], qmod, ps[k]);
+            for (size_t u = 0; u <= nq; ++u) uq_ps[k * (RNS_MAXL + 1) + u] = host_mulmod(u % ps[k], qmod, ps[k]);
         }
+    }
+    // by-value form (kernel parameter); requires nq, np <= RNS_MAXL
+    void fill(RnsExtTabV& t) const {
+        t.nq = (int)mq.size();
+        t.np = (int)mp.size();
+        t.lazy = lazy;
+        t.pad_ = 0;
+        for (size_t i = 0; i < mq.size(); ++i) {
+            t.mq[i] = mq[i];
+            t.qhat_inv[i] = qhat_inv[i];
+            t.qhat_inv_sh[i] = qhat_inv_sh[i];
+            t.frac[i] = frac[i];
+        }
+        for (size_t k = 0; k < mp.size(); ++k) t.mp[k] = mp[k];
+        for (size_t i = 0; i < qhat_ps.size(); ++i) {
+            t.qhat_ps[i] = qhat_ps[i];
+            t.qhat_ps_sh[i] = qhat_ps_sh[i];
+        }
+        for (size_t i = 0; i < uq_ps.size(); ++i) t.uq_ps[i] = uq_ps[i];
     }
     RnsExtTab view() const {
         RnsExtTab t;

@@ -95,6 +95,25 @@ HD uint64_t t64_digit(const DecompT64& dp, uint64_t v, uint32_t which) {
     return dig;
 }
 
+// global loads of complex values: `ld_cx` for tables that should stay in L1 (read-only path), `ld_cx_stream` for the key
+// spectra, which are read once per CMUX and must not evict the twiddle tables from L1 (L2 only: ld.global.cg)
+HD Cx ld_cx(const Cx* p) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    return Cx{v.x, v.y};
+#else
+    return *p;
+#endif
+}
+HD Cx ld_cx_stream(const Cx* p) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return Cx{v.x, v.y};
+#else
+    return *p;
+#endif
+}
+
 // ---- shared-memory swizzle for 16-byte complex elements -------------------------------------------------------------------
 HD uint32_t swz_cx(uint32_t p) { return p ^ ((p >> 3) & 7u); }
 
@@ -110,7 +129,7 @@ HD void fft_fwd_regs(Cx* x, const Cx* __restrict__ tw_bo, uint32_t hi) {
         const int h = 1 << (R - 1 - u);
 #pragma unroll
         for (int top = 0; top < (1 << u); ++top) {
-            const Cx t = tw_bo[(hi << u) + top];
+            const Cx t = ld_cx(tw_bo + ((hi << u) + top));
 #pragma unroll
             for (int low = 0; low < h; ++low) {
                 const int j = (top << (R - u)) | low;
@@ -130,7 +149,7 @@ HD void fft_inv_regs(Cx* x, const Cx* __restrict__ tw_inv_bo, uint32_t hi) {
         const int h = 1 << (R - 1 - u);
 #pragma unroll
         for (int top = 0; top < (1 << u); ++top) {
-            const Cx t = tw_inv_bo[(hi << u) + top];
+            const Cx t = ld_cx(tw_inv_bo + ((hi << u) + top));
 #pragma unroll
             for (int low = 0; low < h; ++low) {
                 const int j = (top << (R - u)) | low;
@@ -236,14 +255,14 @@ HD void fft_run(Cx* s, uint32_t nf, const FftTab& T, Run run) {
 template <typename Coef>
 HD void fft_twist_in(Cx* f, const FftTab& T, Coef coef, uint32_t tid, uint32_t nthr) {
     const uint32_t m = 1u << T.lg;
-    for (uint32_t p = tid; p < m; p += nthr) f[swz_cx(p)] = cx_mul(Cx{t64_to_f64(coef(p)), t64_to_f64(coef(p + m))}, T.tw[p]);
+    for (uint32_t p = tid; p < m; p += nthr) f[swz_cx(p)] = cx_mul(Cx{t64_to_f64(coef(p)), t64_to_f64(coef(p + m))}, ld_cx(T.tw + p));
 }
 // tail of ifft_in_place (`*= 1/len`, fft.rs:32-34) + assign_from_c64_twisted (c64.rs:31-41) for element p: (lo, hi) words
 HD void fft_untwist_out(const Cx* f, const FftTab& T, uint32_t p, uint64_t& lo, uint64_t& hi) {
     Cx c = f[swz_cx(p)];
     c.re = f64_mul_rn(c.re, T.m_inv);
     c.im = f64_mul_rn(c.im, T.m_inv);
-    const Cx x = cx_mul(c, T.tw_inv[p]);
+    const Cx x = cx_mul(c, ld_cx(T.tw_inv + p));
     lo = f64_mod_u64_dev(x.re);
     hi = f64_mod_u64_dev(x.im);
 }
@@ -290,7 +309,7 @@ HD void tfhe_external_product(const TfheDev& P, Cx* F, Cx* Pb, const Cx* __restr
 #pragma unroll 4
             for (uint32_t u = tid; u < nl * m; u += nthr) {
                 const uint32_t r = u >> lg, p = u & (m - 1);
-                Pb[((size_t)r << lg) + swz_cx(p)] = cx_mul(F[((size_t)r << lg) + swz_cx(p)], key[((size_t)(r * (P.k + 1) + o) << lg) + p]);
+                Pb[((size_t)r << lg) + swz_cx(p)] = cx_mul(F[((size_t)r << lg) + swz_cx(p)], ld_cx_stream(key + (((size_t)(r * (P.k + 1) + o) << lg) + p)));
             }
         });
         fft_run<false>(Pb, nl, P.fft, run);
