@@ -109,13 +109,15 @@ HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq
             const uint64_t* qs = T.qhat_ps_sh + (size_t)k * RNS_MAXL;
 #pragma unroll
             for (int i = 0; i < RNS_MAXL; ++i) {
-                if (i < T.nq) s += qh[i] * v[i] - mulhi_u64_approx(qs[i], v[i]) * m.q;  // [0, 4 p_k): quotient off by <= 2
+                if (i >= T.nq) break;  // uniform early exit: predicated-off iterations would still cost issue slots
+                s += qh[i] * v[i] - mulhi_u64_approx(qs[i], v[i]) * m.q;  // [0, 4 p_k): quotient off by <= 2
             }
             s = rns_reduce_u64(m, s);
         } else {
 #pragma unroll
             for (int i = 0; i < RNS_MAXL; ++i) {
-                if (i < T.nq) s = m.add(s, m.mul(qh[i], rns_reduce_u64(m, v[i])));
+                if (i >= T.nq) break;
+                s = m.add(s, m.mul(qh[i], rns_reduce_u64(m, v[i])));
             }
         }
         emit(k, m.sub(s, T.uq_ps[(size_t)k * (RNS_MAXL + 1) + u]));

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TFHE_THREADS, 2) tfhe_ext_kernel(TfheDev P, co
         const uint64_t* g = in + c * (unsigned long long)(k + 1) * n;
         uint64_t* o = out + c * (unsigned long long)(k + 1) * n;
         const Cx* key = P.brk + (((size_t)idx[c] * (k + 1) * d * (k + 1)) << P.fft.lg);
-        tfhe_external_product(
+        tfhe_external_product_any(
             P, F, Pb, key, [&](uint32_t j, uint32_t x) { return g[(size_t)j * n + x]; },
             [&](uint32_t oo, uint32_t c0, uint64_t v0, uint32_t c1, uint64_t v1, bool first) {
                 o[(size_t)oo * n + c0] = first ? v0 : o[(size_t)oo * n + c0] + v0;
