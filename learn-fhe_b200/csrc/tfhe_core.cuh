@@ -423,8 +423,10 @@ HD void tfhe_external_product_any(const TfheDev& P, Cx* F, Cx* Pb, const Cx* __r
 // Measured alternatives (B200, TFHE-T, batch 2048): folding the twist into the first forward pass, the pointwise
 // product into the first inverse pass and the untwist into the last inverse pass removes up to 4 shared-memory round trips
 // and 5 barriers per CMUX but leaves passes with half of the threads idle; it ran at 10.5k (fully fused) and 11.9k (radix-8
-// fused passes only) PBS/s against 12.3k for this plain schedule: the kernel is latency-bound at 16 warps per SM, not
-// shared-memory-bandwidth-bound, so the plain schedule stays.
+// fused passes only) PBS/s against 12.3k for this plain schedule; repeated on top of the compile-time specialisation below
+// (3+4+3 passes with twist and pointwise product fused into the radix-8 end passes): 12.7k against 14.2k.  Longer
+// per-thread dependency chains cost more than the saved shared-memory round trips at 16 warps per SM, so the plain
+// schedule stays.
 // acc <- cmux(brk_i, acc, acc.rotate(e)) = acc + external_product(brk_i, acc.rotate(e) - acc)   (tggsw.rs:114-121)
 template <typename Run>
 HD void tfhe_cmux_step(const TfheDev& P, uint64_t* acc, Cx* F, Cx* Pb, uint32_t i, uint32_t e, Run run) {
