@@ -161,6 +161,8 @@ void fhe_ctx_destroy(fhe_ctx* ctx) {
         if (ctx->stage_d[i]) cudaFree(ctx->stage_d[i]);
     for (auto& pe : ctx->prof_events) cudaEventDestroy(pe.second);
     if (ctx->prof_start) cudaEventDestroy(ctx->prof_start);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

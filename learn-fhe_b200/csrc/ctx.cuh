@@ -37,6 +37,8 @@ struct fhe_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    // copy streams of the pipelined *_host entry points (created on first use)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
     int sm_count = 0;
     std::string err;
     uint64_t launches = 0;

@@ -296,12 +296,12 @@ static bool fhew_force_generic() {
 }
 template <typename OT>
 static fhe_status run_blind_rotate_fast(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n,
-                                        uint32_t post_add, size_t count, OT* d_out, int mode) {
+                                        uint32_t post_add, size_t count, OT* d_out, int mode, bool reset_err) {
     const size_t smem = br_fast_smem_bytes(key);
     auto kern = fhew_blind_rotate_fast_kernel<uint64_t, OT>;
     unsigned grid;
     FHE_CHECK(persistent_grid(ctx, kern, FF_THREADS, smem, count, &grid));
-    FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
+    if (reset_err) FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
     kern<<<grid, FF_THREADS, smem, ctx->stream>>>(key->F, d_f, d_ct2n, post_add, count, d_out, mode, key->d_err);
     return after_launch(ctx, "fhew_blind_rotate_kernel");
 }
@@ -309,15 +309,15 @@ static bool fhew_fast_instantiated(unsigned dg, unsigned dr) { return dg >= 1 &&
 
 template <typename OT>
 static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n, uint32_t post_add,
-                                   size_t count, OT* d_out, int mode) {
+                                   size_t count, OT* d_out, int mode, bool reset_err = true) {
     if (key->fast && !fhew_force_generic()) {
-        return run_blind_rotate_fast<OT>(ctx, key, d_f, d_ct2n, post_add, count, d_out, mode);
+        return run_blind_rotate_fast<OT>(ctx, key, d_f, d_ct2n, post_add, count, d_out, mode, reset_err);
     }
     const size_t smem = br_smem_bytes(key);
     auto kern = fhew_blind_rotate_kernel<uint64_t, OT>;
     unsigned grid;
     FHE_CHECK(persistent_grid(ctx, kern, BR_THREADS, smem, count, &grid));
-    FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
+    if (reset_err) FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
     kern<<<grid, BR_THREADS, smem, ctx->stream>>>(key->P, key->kmax, d_f, d_ct2n, post_add, count, d_out, mode, key->d_err);
     return after_launch(ctx, "fhew_blind_rotate_kernel");
 }
@@ -410,7 +410,8 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     P.ak = (const uint2*)key->d_ak;
     P.dlog = (const uint16_t*)key->d_dlog;
     // fast path structures
-    if (pp->log_n == FF_LOGN && q < (1ull << 28) && P.small_digits && pp->rgsw_log_b >= 2 && pp->rlwe_log_b >= 2 &&
+    if (pp->log_n == FF_LOGN && q < (1ull << 28) && P.small_digits && pp->rgsw_log_b >= 2 && pp->rlwe_log_b >= 2 && pp->rgsw_log_b * pp->rgsw_d <= 30 &&
+        pp->rlwe_log_b * pp->rlwe_d <= 30 &&
         fhew_fast_instantiated(pp->rgsw_d, pp->rlwe_d)) {
         FhewFastDev& F = key->F;
         F.m.q = (uint32_t)q;
@@ -546,11 +547,46 @@ fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, 
     FHE_CHECK(ensure_stage_d(ctx, 0, ct_bytes, &d_in));
     FHE_CHECK(ensure_stage_d(ctx, 1, ct_bytes, &d_out));
     FHE_CHECK(ensure_stage_d(ctx, 2, f_bytes, &d_f));
-    FHE_CUDA(ctx, cudaMemcpyAsync(d_in, ct_in, ct_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    FHE_CUDA(ctx, cudaMemcpyAsync(d_f, f, f_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    FHE_CHECK(fhe_fhew_bootstrap_batch(ctx, key, (const uint64_t*)d_f, post_add, count, (const uint64_t*)d_in, (uint64_t*)d_out));
-    FHE_CUDA(ctx, cudaMemcpyAsync(ct_out, d_out, ct_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    return check_err_flag(ctx, key);  // synchronises the stream
+    FHE_REQUIRE(ctx, post_add < key->param.big_q, "post_add out of range");
+    // Pipelined over chunks: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c (two copy streams + events)
+    const size_t nchunk = count >= 8192 ? 4 : (count >= 2048 ? 2 : 1);
+    const size_t cs = (count + nchunk - 1) / nchunk, row = (size_t)n + 1;
+    if (!ctx->copy_in) FHE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    if (!ctx->copy_out) FHE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    void* scratch;
+    FHE_CHECK(ensure_scratch(ctx, count * (key->P.n_s + 1) * 4, &scratch));
+    cudaEvent_t ev[9];
+    for (auto& e : ev) FHE_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    fhe_status st = FHE_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && st == FHE_OK) st = fail(ctx, FHE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaMemcpyAsync(d_f, f, f_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D f");
+    cu(cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream), "memset");
+    cu(cudaEventRecord(ev[8], ctx->stream), "event");  // staging buffers are free once earlier work on the stream is done
+    cu(cudaStreamWaitEvent(ctx->copy_in, ev[8], 0), "wait");
+    for (size_t c = 0; c < nchunk && st == FHE_OK; ++c) {
+        const size_t off = c * cs, cnt = std::min(cs, count - off);
+        if (off >= count) break;
+        const uint64_t* h_in = ct_in + off * row;
+        uint64_t* dd_in = (uint64_t*)d_in + off * row;
+        uint64_t* dd_out = (uint64_t*)d_out + off * row;
+        uint32_t* sc = (uint32_t*)scratch + off * (key->P.n_s + 1);
+        cu(cudaMemcpyAsync(dd_in, h_in, cnt * row * 8, cudaMemcpyHostToDevice, ctx->copy_in), "H2D");
+        cu(cudaEventRecord(ev[2 * c], ctx->copy_in), "event");
+        cu(cudaStreamWaitEvent(ctx->stream, ev[2 * c], 0), "wait");
+        if (st == FHE_OK) st = run_prologue(ctx, key, cnt, dd_in, true, true, sc, nullptr);
+        if (st == FHE_OK) st = run_blind_rotate<uint64_t>(ctx, key, (const uint64_t*)d_f, sc, (uint32_t)post_add, cnt, dd_out, 0, false);
+        cu(cudaEventRecord(ev[2 * c + 1], ctx->stream), "event");
+        cu(cudaStreamWaitEvent(ctx->copy_out, ev[2 * c + 1], 0), "wait");
+        cu(cudaMemcpyAsync(ct_out + off * row, dd_out, cnt * row * 8, cudaMemcpyDeviceToHost, ctx->copy_out), "D2H");
+    }
+    cu(cudaEventRecord(ev[8], ctx->copy_out), "event");
+    cu(cudaStreamWaitEvent(ctx->stream, ev[8], 0), "wait");
+    if (st == FHE_OK) st = check_err_flag(ctx, key);  // synchronises the stream (which now waits for the last D2H)
+    else cudaDeviceSynchronize();
+    for (auto& e : ev) cudaEventDestroy(e);
+    return st;
 }
 
 // one-time distribution of the (already transformed) key buffers from `root` (no upstream analogue)

@@ -69,11 +69,14 @@ HD uint32_t ff_perm_coef(const FhewFastDev& P, const uint32_t* src, uint32_t tin
 // ---- P1: decompose + first forward radix-8 pass (stages 0..2, stride 64) --------------------------------------------------------
 // Signed-digit state of one coefficient (decompose.rs:92-111 with zq.rs:83-89), 32-bit working word (log_b * d <= 32):
 // start: x = centred(rounding_shr(v)); step: emits the next digit as a residue mod Q and advances x.
+// The centred value is offset by K = B^d (log_b * d <= 30): the d digits only depend on x mod B^d, and with the offset every
+// intermediate is a small non-negative number, so the two-operand adds cannot wrap and can be pinned to the ALU pipe.
 HD uint32_t ff_dec_start(const FhewFastDev& P, const DecompParam& dp, uint32_t v) {
-    uint32_t r = v + (uint32_t)dp.half;
+    uint32_t r = alu_add(v, (uint32_t)dp.half);
     r = umin_(r, r - P.m.q);
     const uint32_t sh = r >> dp.rounding_bits;
-    return sh < (P.m.q >> 1) ? sh : sh - P.m.q;
+    const uint32_t k = 1u << (dp.log_b * dp.d);
+    return sh < (P.m.q >> 1) ? sh + k : sh + (k - P.m.q);
 }
 // For log_b >= 2 the reference's carry rule `limb + (x & 1) > B/2` is `limb > B/2` (B/2 is even, so the tie limb = B/2 has
 // an even limb and never carries), hence with h = B/2 - 1: signed digit = ((x + h) & (B-1)) - h, next x = (x + h) >> log_b
@@ -81,9 +84,9 @@ HD uint32_t ff_dec_start(const FhewFastDev& P, const DecompParam& dp, uint32_t v
 // (0, 2Q): the forward butterflies are lazy, so no canonical form is needed.
 HD uint32_t ff_dec_step(const FhewFastDev& P, const DecompParam& dp, uint32_t& x) {
     const uint32_t mask = (1u << dp.log_b) - 1u, hb = (1u << (dp.log_b - 1)) - 1u;
-    const uint32_t t = x + hb;
+    const uint32_t t = alu_add(x, hb);
     x = t >> dp.log_b;
-    return (t & mask) + (P.m.q - hb);
+    return alu_add(t & mask, P.m.q - hb);
 }
 // Thread (g, h) holds the 8 coefficients at positions g + 64 j (values from acc_in[h] for an external product, from the
 // permuted a(X^t) for an automorphism) and walks the digits; digit k becomes polynomial `pbase + k` if lo <= k < hi.
@@ -216,7 +219,7 @@ HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, ui
     for (int j = 0; j < 8; ++j) {
         uint32_t v = P.m.inv_canon(x[j]);
         if (do_add) {
-            v += add(j);
+            v = alu_add(v, add(j));
             v = umin_(v, v - P.m.q);
         }
         acc_out[(h << FF_LOGN) + g + 64u * j] = v;

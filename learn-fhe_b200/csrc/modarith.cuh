@@ -53,6 +53,16 @@ HD uint64_t mulhi_u64_approx(uint64_t a, uint64_t b) {
     return (uint64_t)ah * bh + (t >> 32) + (u >> 32);
 }
 HD uint32_t umin_(uint32_t a, uint32_t b) { return a < b ? a : b; }
+// a + b for sums that cannot wrap (a + b < 2^32), forced onto the ALU pipe (VIADDMNMX).  ptxas otherwise places many
+// two-operand integer adds on the IMAD pipe as IMAD.IADD, and that pipe is the measured bottleneck of every modular kernel
+// here (64 lanes/clk/SM on B200; ncu: sm__pipe_fmaheavy_cycles_active 58-66 %).
+HD uint32_t alu_add(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __viaddmin_u32(a, b, 0xFFFFFFFFu);
+#else
+    return a + b;
+#endif
+}
 HD uint64_t umin_(uint64_t a, uint64_t b) { return a < b ? a : b; }
 
 // ------------------------------------------------------------------------------------------------

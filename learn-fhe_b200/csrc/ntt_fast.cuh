@@ -45,15 +45,13 @@ struct Lz32 {
     static constexpr int FWD_LIMIT = 16;  // values must stay < FWD_LIMIT * q
     uint32_t q, q2, q8, mu;               // mu = floor(2^32 / q)
     HD uint32_t mul_lazy(uint32_t y, uint32_t w, uint32_t wp) const { return w * y - mulhi_u32(wp, y) * q; }  // [0,2q), any y
-    // x' = x + t*y, y' = x + 2q - t*y with the addition folded into the multiply-add chain (x' = (w*y + x) - hi*q) and y'
-    // derived from x' (y' = 2x + 2q - x'): 4 issue slots on the IMAD pipe (IMAD, IMAD.HI, IMAD) and two ALU adds, instead
-    // of 5 + 1 when the compiler places x + ty on the IMAD pipe as IMAD.IADD - that pipe is the measured bottleneck.
+    // x' = x + t*y, y' = x + 2q - t*y; the two-operand add is pinned to the ALU pipe (alu_add) so that the butterfly costs
+    // exactly its 4 algorithmic slots on the IMAD pipe, the measured bottleneck.
     HD void bf_fwd(uint32_t& x, uint32_t& y, TwPair<uint32_t> t) const {
         const uint32_t x0 = x;
-        const uint32_t hi = mulhi_u32(t.wp, y);
-        const uint32_t xn = (t.w * y + x0) - hi * q;
-        x = xn;
-        y = (x0 + x0 + q2) - xn;
+        const uint32_t ty = t.w * y - mulhi_u32(t.wp, y) * q;  // IMAD, IMAD.HI, IMAD: 4 slots on the IMAD pipe
+        x = alu_add(x0, ty);                                   // VIADDMNMX (ALU)
+        y = x0 + q2 - ty;                                      // IADD3 (ALU)
     }
     HD uint32_t pre_red(uint32_t x) const { return umin_(x, x - q8); }  // [0,16q) -> [0,8q)
     HD uint32_t canon(uint32_t x) const {                               // any x -> [0,q)
@@ -62,12 +60,12 @@ struct Lz32 {
     }
     // inverse: x,y in [0,2q) -> [0,2q)
     HD void bf_inv(uint32_t& x, uint32_t& y, TwPair<uint32_t> t, int /*stage*/) const {
-        const uint32_t s = x + y, d = x + q2 - y;
+        const uint32_t s = alu_add(x, y), d = x + q2 - y;
         x = umin_(s, s - q2);
         y = mul_lazy(d, t.w, t.wp);
     }
     HD void bf_inv_last(uint32_t& x, uint32_t& y, TwPair<uint32_t> ninv, TwPair<uint32_t> wninv, int /*stage*/) const {
-        const uint32_t s = x + y, d = x + q2 - y;
+        const uint32_t s = alu_add(x, y), d = x + q2 - y;
         x = mul_lazy(s, ninv.w, ninv.wp);
         y = mul_lazy(d, wninv.w, wninv.wp);
     }

@@ -145,3 +145,29 @@ def test_empty_batch_and_bad_parameters(pkg, ctx, orc, fhew_setup, bk):
     bad.big_q = 268409859  # not prime: the reference panics (ring.rs:258), here FHE_EINVAL
     with pytest.raises(pkg.FheError):
         fhew.BootstrappingKey(ctx, bad, ex["ksk_a"], ex["ksk_b"], ex["brk"], ex["ak"], ex["ak_t"])
+
+
+def test_host_path_pipelining_matches_device_path(pkg, ctx, orc, fhew_setup):
+    """fhe_fhew_bootstrap_batch_host splits large batches into chunks (copy streams overlapped with the kernels): every
+    ciphertext must equal the device-resident path, chunk boundaries included (9001 is not a multiple of the chunk size)."""
+    import torch
+    from learn_fhe_b200 import fhew
+    P, K, ex = fhew_setup
+    param = fhew.single_key_testing_param(P.big_q)
+    bk = fhew.BootstrappingKey(ctx, param, ex["ksk_a"], ex["ksk_b"], ex["brk"], ex["ak"], ex["ak_t"])
+    count = 9001
+    bits = np.random.default_rng(8).integers(0, 2, size=64).astype(np.int32)
+    base = K.encrypt(bits, 77)
+    cts = np.ascontiguousarray(np.tile(base, (count // 64 + 1, 1))[:count])
+    cts[:, :-1] = (cts[:, :-1] + np.arange(count, dtype=np.uint64)[:, None]) % np.uint64(P.big_q)  # distinct masks, any phase
+    f = fhew.gate_poly(param, [1, 1, 1, 0])
+    post = fhew.big_q_by_8(param)
+    host = fhew.Bootstrapping.bootstrap(bk, f, cts, post_add=post)
+    d_in, d_f = pkg.to_dev(cts), pkg.to_dev(f)
+    d_out = torch.empty_like(d_in)
+    fhew.Bootstrapping.bootstrap_dev(bk, d_f, d_in, d_out, post_add=post)
+    ctx.sync()
+    assert (pkg.to_host(d_out) == host).all()
+    ref = K.op([1, 1, 1, 0], cts[[0, 2250, 2251, 4500, 9000]], threads=5)
+    assert (host[[0, 2250, 2251, 4500, 9000]] == ref).all()
+    bk.free()
