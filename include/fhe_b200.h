@@ -207,6 +207,9 @@ fhe_status fhe_tfhe_pbs_batch_host(fhe_ctx* ctx, const fhe_tfhe_key* key, const 
 /* Tggsw::external_product(brk[idx[i]], glwe_i) (tggsw.rs:100-112): glwe [count][k+1][N] */
 fhe_status fhe_tfhe_external_product(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t count, const uint32_t* d_idx,
                                      const uint64_t* d_glwe_in, uint64_t* d_glwe_out);
+/* Tggsw::cmux(brk[idx[i]], ct0_i, ct1_i) = ct0 + external_product(b, ct1 - ct0) (tggsw.rs:114-121): [count][k+1][N] */
+fhe_status fhe_tfhe_cmux(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t count, const uint32_t* d_idx, const uint64_t* d_ct0,
+                         const uint64_t* d_ct1, uint64_t* d_out);
 /* blind_rotate + sample_extract(0) (tfhe/bootstrapping.rs:84-96, tglwe.rs:115-127): out [count][kN+1] */
 fhe_status fhe_tfhe_blind_rotate_extract_batch(fhe_ctx* ctx, const fhe_tfhe_key* key, const uint64_t* d_lut, size_t count,
                                                const uint64_t* d_ct_in, uint64_t* d_out);
@@ -233,6 +236,10 @@ fhe_status fhe_ckks_mul_relin_rescale_batch_host(fhe_ctx* ctx, fhe_ckks_ctx* ck,
  * ckks.rs:274-282; t == 0 means none): [count][2][l][N] -> same shape */
 fhe_status fhe_ckks_key_switch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* ksk, int64_t t, size_t level, size_t count,
                                const uint64_t* d_ct, uint64_t* d_out);
+/* Ckks::mul_constant on an already-encoded plaintext (ckks.rs:250-253): (pt * b, pt * a).rescale().
+ * d_pt [pt_count][level][N] coefficient form with pt_count == 1 (shared) or count; out [count][2][level-1][N] */
+fhe_status fhe_ckks_mul_plain_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t count, size_t pt_count,
+                                            const uint64_t* d_pt, const uint64_t* d_ct, uint64_t* d_out);
 /* CkksCiphertext::rescale (ckks.rs:123-125): [count][2][l][N] -> [count][2][l-1][N] */
 fhe_status fhe_ckks_rescale(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t count, const uint64_t* d_ct, uint64_t* d_out);
 

@@ -149,6 +149,7 @@ def lib():
         L.fhe_tfhe_pbs_batch.argtypes = [vp, vp, vp, sz, vp, vp]
         L.fhe_tfhe_pbs_batch_host.argtypes = [vp, vp, vp, sz, vp, vp]
         L.fhe_tfhe_external_product.argtypes = [vp, vp, sz, vp, vp, vp]
+        L.fhe_tfhe_cmux.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         L.fhe_tfhe_blind_rotate_extract_batch.argtypes = [vp, vp, vp, sz, vp, vp]
         L.fhe_tlwe_key_switch_batch.argtypes = [vp, vp, sz, vp, vp]
     # CKKS
@@ -163,6 +164,7 @@ def lib():
         L.fhe_ckks_mul_relin_rescale_batch_host.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
         L.fhe_ckks_key_switch.argtypes = [vp, vp, vp, i64, sz, sz, vp, vp]
         L.fhe_ckks_rescale.argtypes = [vp, vp, sz, sz, vp, vp]
+        L.fhe_ckks_mul_plain_rescale_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     _lib = L
     return L
 

@@ -122,6 +122,19 @@ class Ckks:
         return to_host(d_out)
 
     @staticmethod
+    def mul_constant(param, pt, ct):
+        """Ckks::mul_constant on an encoded plaintext (ckks.rs:250-253): pt [level][N] (shared) or [count][level][N]."""
+        import torch
+        ct, pt = _u64(ct), _u64(pt)
+        count, _, level, n = ct.shape
+        pt_count = 1 if pt.ndim == 2 else pt.shape[0]
+        d_ct, d_pt = to_dev(ct, param.ctx.device), to_dev(pt, param.ctx.device)
+        d_out = torch.empty((count, 2, level - 1, n), dtype=torch.int64, device=d_ct.device)
+        param.ctx.call("fhe_ckks_mul_plain_rescale_batch", param.h, level, count, pt_count, dptr(d_pt), dptr(d_ct), dptr(d_out))
+        param.ctx.sync()
+        return to_host(d_out)
+
+    @staticmethod
     def rescale(param, ct):
         """CkksCiphertext::rescale (ckks.rs:123-125)."""
         import torch

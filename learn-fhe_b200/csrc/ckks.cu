@@ -164,6 +164,18 @@ __global__ void __launch_bounds__(256) ckks_keymul_kernel(const Mod64* __restric
         out[o + (size_t)le * n] = m.mul(ksk[((size_t)2 * big_l + kl) * n + x], v);
     }
 }
+// plaintext x ciphertext in the evaluation domain: e [C][2][l][n] *= pe [1 or C][l][n] (limb-wise)   (ckks.rs:250-253)
+__global__ void __launch_bounds__(256) ckks_ptmul_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long count, int pt_per_ct,
+                                                         const uint64_t* __restrict__ pe, uint64_t* __restrict__ e) {
+    const size_t n = (size_t)1 << log_n, ln = (size_t)l * n;
+    const unsigned long long total = count * 2 * ln, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const unsigned long long c = idx / (2 * ln);
+        const size_t r = (size_t)(idx % ln);
+        const Mod64 m = mods[r >> log_n];
+        e[idx] = m.mul(e[idx], pe[(pt_per_ct ? c * ln : 0) + r]);
+    }
+}
 // RnsRq::automorphism (rns.rs:74-77 -> avec.rs:34-50) on [polys][n] with modulus mods[poly % l]
 __global__ void __launch_bounds__(256) rns_automorphism_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long polys, uint32_t t,
                                                                const uint64_t* __restrict__ in, uint64_t* __restrict__ out) {
@@ -490,6 +502,37 @@ fhe_status fhe_ckks_key_switch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ks
         FHE_CUDA(ctx, cudaMemcpy2DAsync(ac, l * n * 8, ct + l * n, 2 * l * n * 8, l * n * 8, c, cudaMemcpyDeviceToDevice, ctx->stream));
         FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * l, ac, ae, true));
         FHE_CHECK(key_switch_core(ctx, ck, ksk, l, c, ac, ae, xp, kk, ct, d_out + base * 2 * l * n));
+    }
+    return FHE_OK;
+}
+
+// Ckks::mul_constant after encoding (ckks.rs:250-253): (pt * ct.b, pt * ct.a).rescale(); pt [pt_count][level][N] coefficient form,
+// pt_count == 1 (shared by the batch) or == count
+fhe_status fhe_ckks_mul_plain_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t count, size_t pt_count, const uint64_t* d_pt,
+                                            const uint64_t* d_ct, uint64_t* d_out) {
+    if (!ctx || !ck) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_pt && d_ct && d_out, "null pointer");
+    FHE_REQUIRE(ctx, level >= 2 && level <= ck->big_l, "level must be in [2, L] (rescale needs a limb to drop)");
+    FHE_REQUIRE(ctx, pt_count == 1 || pt_count == count, "pt_count must be 1 or count");
+    const unsigned log_n = ck->log_n;
+    const size_t n = (size_t)1 << log_n, l = level;
+    const std::vector<uint64_t> qs = level_qs(ck, l);
+    const size_t per = 2 * l * n;
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ((size_t)4 << 30) / (per * 8)));
+    uint64_t* ws;
+    FHE_CHECK(ckks_ws(ctx, ck, (pt_count * l * n + chunk * per) * 8, &ws));
+    uint64_t* pe = ws;
+    uint64_t* e = pe + pt_count * l * n;
+    FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, pt_count * l, d_pt, pe, true));
+    for (size_t base = 0; base < count; base += chunk) {
+        const size_t c = std::min(chunk, count - base);
+        FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * 2 * l, d_ct + base * per, e, true));
+        ckks_ptmul_kernel<<<stream_grid(ctx, (unsigned long long)c * per), 256, 0, ctx->stream>>>(
+            ck->d_mods, (int)l, (int)log_n, c, pt_count == 1 ? 0 : 1, pe + (pt_count == 1 ? 0 : base * l * n), e);
+        FHE_CHECK(after_launch(ctx, "ckks_ptmul_kernel"));
+        FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, c * 2 * l, e, false));
+        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, e, nullptr, nullptr, false, d_out + base * 2 * (l - 1) * n));
     }
     return FHE_OK;
 }

@@ -163,7 +163,7 @@ HD void ff_p3(const FhewFastDev& P, const FhewFastSmem& S, const uint4* __restri
     const uint32_t P0 = swzf(t << 2);
     uint64_t sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
     const TwPair<uint32_t> t0 = S.tw[128u + t], t1 = S.tw[256u + 2u * t], t2 = S.tw[257u + 2u * t];
-#pragma unroll 2
+#pragma unroll 4
     for (uint32_t k = 0; k < rows; ++k) {
         uint32_t x[4];
         ff_ld4(S.dig + (k << FF_LOGN), P0, x);

@@ -148,9 +148,11 @@ __global__ void __launch_bounds__(TFHE_THREADS, 2) tfhe_blind_rotate_kernel(Tfhe
     }
 }
 
-// Tggsw::external_product(brk[idx[c]], glwe_c): glwe [count][k+1][N]
+// Tggsw::external_product(brk[idx[c]], glwe_c) (in1 == nullptr), or Tggsw::cmux(brk[idx[c]], ct0 = in, ct1 = in1) =
+// ct0 + external_product(b, ct1 - ct0) (tggsw.rs:100-121): glwe [count][k+1][N]
 __global__ void __launch_bounds__(TFHE_THREADS, 2) tfhe_ext_kernel(TfheDev P, const uint32_t* __restrict__ idx, const uint64_t* __restrict__ in,
-                                                                 unsigned long long count, uint64_t* __restrict__ out) {
+                                                                 const uint64_t* __restrict__ in1, unsigned long long count,
+                                                                 uint64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t n = 1u << P.log_n, k = P.k, d = P.bs_dec.d;
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);
@@ -159,13 +161,16 @@ __global__ void __launch_bounds__(TFHE_THREADS, 2) tfhe_ext_kernel(TfheDev P, co
     TFHE_RUN;
     for (unsigned long long c = blockIdx.x; c < count; c += gridDim.x) {
         const uint64_t* g = in + c * (unsigned long long)(k + 1) * n;
+        const uint64_t* g1 = in1 ? in1 + c * (unsigned long long)(k + 1) * n : nullptr;
         uint64_t* o = out + c * (unsigned long long)(k + 1) * n;
         const Cx* key = P.brk + (((size_t)idx[c] * (k + 1) * d * (k + 1)) << P.fft.lg);
         tfhe_external_product_any(
-            P, F, Pb, key, [&](uint32_t j, uint32_t x) { return g[(size_t)j * n + x]; },
+            P, F, Pb, key, [&](uint32_t j, uint32_t x) { return g1 ? g1[(size_t)j * n + x] - g[(size_t)j * n + x] : g[(size_t)j * n + x]; },
             [&](uint32_t oo, uint32_t c0, uint64_t v0, uint32_t c1, uint64_t v1, bool first) {
-                o[(size_t)oo * n + c0] = first ? v0 : o[(size_t)oo * n + c0] + v0;
-                o[(size_t)oo * n + c1] = first ? v1 : o[(size_t)oo * n + c1] + v1;
+                const uint64_t b0 = first ? (g1 ? g[(size_t)oo * n + c0] : 0) : o[(size_t)oo * n + c0];
+                const uint64_t b1 = first ? (g1 ? g[(size_t)oo * n + c1] : 0) : o[(size_t)oo * n + c1];
+                o[(size_t)oo * n + c0] = b0 + v0;
+                o[(size_t)oo * n + c1] = b1 + v1;
             },
             run);
     }
@@ -458,7 +463,19 @@ fhe_status fhe_tfhe_external_product(fhe_ctx* ctx, const fhe_tfhe_key* key, size
     const size_t smem = tfhe_smem_bytes(key->P.k, key->P.bs_dec.d, key->P.log_n);
     unsigned grid;
     FHE_CHECK(tfhe_grid(ctx, tfhe_ext_kernel, smem, count, &grid));
-    tfhe_ext_kernel<<<grid, TFHE_THREADS, smem, ctx->stream>>>(key->P, d_idx, d_glwe_in, count, d_glwe_out);
+    tfhe_ext_kernel<<<grid, TFHE_THREADS, smem, ctx->stream>>>(key->P, d_idx, d_glwe_in, nullptr, count, d_glwe_out);
+    return after_launch(ctx, "tfhe_ext_kernel");
+}
+
+fhe_status fhe_tfhe_cmux(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t count, const uint32_t* d_idx, const uint64_t* d_ct0, const uint64_t* d_ct1,
+                         uint64_t* d_out) {
+    if (!ctx || !key) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_idx && d_ct0 && d_ct1 && d_out && d_out != d_ct0 && d_out != d_ct1, "null or aliased pointer");
+    const size_t smem = tfhe_smem_bytes(key->P.k, key->P.bs_dec.d, key->P.log_n);
+    unsigned grid;
+    FHE_CHECK(tfhe_grid(ctx, tfhe_ext_kernel, smem, count, &grid));
+    tfhe_ext_kernel<<<grid, TFHE_THREADS, smem, ctx->stream>>>(key->P, d_idx, d_ct0, d_ct1, count, d_out);
     return after_launch(ctx, "tfhe_ext_kernel");
 }
 

@@ -102,6 +102,19 @@ class Tggsw:
         return to_host(d_out)
 
 
+    @staticmethod
+    def cmux(bk, idx, ct0, ct1):
+        """Tggsw::cmux(brk[idx[i]], ct0_i, ct1_i) (tggsw.rs:114-121): glwe [count, k+1, N]."""
+        import torch
+        ct0, ct1 = _u64(ct0), _u64(ct1)
+        d0, d1 = to_dev(ct0, bk.ctx.device), to_dev(ct1, bk.ctx.device)
+        d_idx = to_dev(np.ascontiguousarray(idx, dtype=np.uint32), bk.ctx.device)
+        d_out = torch.empty_like(d0)
+        bk.ctx.call("fhe_tfhe_cmux", bk.h, ct0.shape[0], dptr(d_idx), dptr(d0), dptr(d1), dptr(d_out))
+        bk.ctx.sync()
+        return to_host(d_out)
+
+
 class Tlwe:
     @staticmethod
     def key_switch(bk, ct):

@@ -122,6 +122,22 @@ def test_key_switch_rotate_conjugate_rescale(pkg, ctx, orc, ckks_setup):
         assert (got[i] == K.rescale(cts[i])).all()
 
 
+def test_mul_constant_matches_oracle(pkg, ctx, orc, ckks_setup):
+    """ckks.rs:250-253 on an encoded plaintext: limb-wise negacyclic products with the ciphertext halves, then rescale."""
+    from learn_fhe_b200 import ckks
+    K, P, rlk = ckks_setup
+    level = P.big_l
+    cts = np.stack([K.encrypt(_small_pt(60 + i, K.n), level, 500 + i) for i in range(3)])
+    for per_ct in (False, True):
+        npt = 3 if per_ct else 1
+        pts = np.stack([np.stack([np.mod(_small_pt(70 + j, K.n, 1 << 30), q).astype(np.uint64) for q in P.qs[:level]]) for j in range(npt)])
+        got = ckks.Ckks.mul_constant(P, pts if per_ct else pts[0], cts)
+        for i in range(3):
+            pt = pts[i if per_ct else 0]
+            prod = np.stack([np.stack([orc.ntt_mul(P.qs[t], cts[i, h, t], pt[t]) for t in range(level)]) for h in range(2)])
+            assert (got[i] == K.rescale(prod)).all(), (per_ct, i)
+
+
 def test_ckks_level_errors(pkg, ctx, orc, ckks_setup):
     from learn_fhe_b200 import ckks
     K, P, rlk = ckks_setup

@@ -67,6 +67,11 @@ def test_external_product_keyswitch_blind_rotate_reduced(pkg, ctx, orc, k, bs_d,
     got = tfhe.Tggsw.external_product(bk, idx, glwe)
     for c in range(count):
         assert (got[c] == K.external_product(int(idx[c]), glwe[c])).all(), c
+    # cmux = ct0 + external_product(b, ct1 - ct0) (tggsw.rs:114-121), wrapping torus arithmetic
+    other = orc.splitmix64(33, glwe.size).reshape(glwe.shape)
+    got = tfhe.Tggsw.cmux(bk, idx, glwe, other)
+    for c in range(count):
+        assert (got[c] == glwe[c] + K.external_product(int(idx[c]), other[c] - glwe[c])).all(), c
     ext = orc.splitmix64(4, count * (P.k * P.big_n + 1)).reshape(count, -1)
     got = tfhe.Tlwe.key_switch(bk, ext)
     for c in range(count):
