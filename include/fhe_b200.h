@@ -195,6 +195,11 @@ typedef struct fhe_tfhe_key fhe_tfhe_key;
 fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* param, const uint64_t* brk, const uint64_t* ksk_a,
                                const uint64_t* ksk_b, fhe_tfhe_key** out);
 void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key);
+/* Evaluation mode of every product made with this key.  0 (default): the reference's dataflow - each row * limb product is
+ * inverse-transformed and rounded on its own (misc.rs:59-61), raw torus words bit-identical to the reference.  1: products
+ * are summed in the Fourier domain and rounded once per output ((k+1) instead of (k+1)^2 d inverse FFTs per CMUX); torus
+ * words then differ from the reference's by less than its own error bound (c64.rs:186-208), decryptions are identical. */
+fhe_status fhe_tfhe_key_set_mode(fhe_ctx* ctx, fhe_tfhe_key* key, int mode);
 /* device bytes held by the key (Fourier-domain bsk + ksk) and its one-time NCCL broadcast from `root` */
 size_t fhe_tfhe_key_bytes(const fhe_tfhe_key* key);
 fhe_status fhe_tfhe_key_broadcast(fhe_ctx* ctx, fhe_tfhe_key* key, void* nccl_comm, int root);

@@ -143,6 +143,7 @@ def lib():
         L.fhe_tfhe_key_upload.argtypes = [vp, C.POINTER(TfheParam), vp, vp, vp, C.POINTER(vp)]
         L.fhe_tfhe_key_free.argtypes = [vp, vp]
         L.fhe_tfhe_key_free.restype = None
+        L.fhe_tfhe_key_set_mode.argtypes = [vp, vp, C.c_int]
         L.fhe_tfhe_key_bytes.argtypes = [vp]
         L.fhe_tfhe_key_bytes.restype = sz
         L.fhe_tfhe_key_broadcast.argtypes = [vp, vp, vp, C.c_int]

@@ -353,6 +353,7 @@ fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uin
     P.k = pp->k;
     P.n_lwe = pp->n;
     P.bs_dec = make_decomp_t64(pp->bs_log_b, pp->bs_d);
+    P.fourier_acc = 0;
     fhe_status st = get_fft_tab(ctx, pp->log_big_n, &P.fft);
     // brk: [n][(k+1)d][(k+1)][N] torus words -> Fourier domain
     const size_t polys = (size_t)pp->n * (pp->k + 1) * pp->bs_d * (pp->k + 1);
@@ -400,6 +401,13 @@ void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key) {
     if (key->d_brk) cudaFree(key->d_brk);
     if (key->d_ksk) cudaFree(key->d_ksk);
     delete key;
+}
+fhe_status fhe_tfhe_key_set_mode(fhe_ctx* ctx, fhe_tfhe_key* key, int mode) {
+    if (!ctx || !key) return FHE_EINVAL;
+    FHE_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (reference dataflow, bit-identical) or 1 (Fourier-domain accumulation)");
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    key->P.fourier_acc = (uint32_t)mode;
+    return FHE_OK;
 }
 size_t fhe_tfhe_key_bytes(const fhe_tfhe_key* key) { return key ? key->brk_bytes + key->ksk_bytes : 0; }
 fhe_status fhe_tfhe_key_broadcast(fhe_ctx* ctx, fhe_tfhe_key* key, void* nccl_comm, int root) {

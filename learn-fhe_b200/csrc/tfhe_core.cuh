@@ -275,6 +275,9 @@ struct TfheDev {
     DecompT64 bs_dec;     // TGGSW decomposor
     FftTab fft;
     const Cx* brk;        // [n_lwe][(k+1)*d rows][(k+1) outputs][N/2] Fourier-domain key polynomials
+    uint32_t fourier_acc; // 0: reference dataflow (every row*limb product rounded on its own: bit-identical torus words);
+                          // 1: sum the products in the Fourier domain, one inverse transform per output (error below the
+                          //    reference's own bound, decryptions identical; (k+1) instead of (k+1)^2 d inverse FFTs per CMUX)
 };
 // shared memory: acc[(k+1)][N] u64 | F[(k+1)*d][N/2] Cx | P[(k+1)*d][N/2] Cx
 HD size_t tfhe_smem_bytes(uint32_t k, uint32_t d, int log_n) {
@@ -411,8 +414,54 @@ HD void tfhe_external_product_c(const TfheDev& P, Cx* F, Cx* Pb, const Cx* __res
         });
     }
 }
+// Fourier-domain accumulation variant (TfheDev::fourier_acc): out_o = IFFT(sum_r FFT(limb_r) o key[r][o]).  NOT the
+// reference's rounding order: each output coefficient carries one rounding instead of (k+1)d, so it differs from the
+// reference's torus words by at most the reference's own per-product error bound 2^(64 + log_b + log_n - 53) (c64.rs:186-208)
+// times (k+1)d, far below the plaintext scale; decrypted results are identical (tests/test_gpu_tfhe.py).
+template <int LG, typename Src, typename Sink, typename Run>
+HD void tfhe_external_product_acc_c(const TfheDev& P, Cx* F, Cx* Pb, const Cx* __restrict__ key, Src src, Sink sink, Run run) {
+    constexpr uint32_t m = 1u << LG;
+    const uint32_t d = P.bs_dec.d, nl = (P.k + 1) * d, ko = P.k + 1;
+    const FftTab& T = P.fft;
+    run([&](uint32_t tid, uint32_t nthr) {
+        for (uint32_t r = 0; r < nl; ++r) {
+            const uint32_t j = r / d, i = r % d;
+            Cx* f = F + (r << LG);
+            for (uint32_t p = tid; p < m; p += nthr)
+                f[swz_cx(p)] = cx_mul(Cx{t64_to_f64(t64_digit(P.bs_dec, src(j, p), i)), t64_to_f64(t64_digit(P.bs_dec, src(j, p + m), i))}, ld_cx(T.tw + p));
+        }
+    });
+    fft_run_c<LG, true>(F, nl, T, run);
+    run([&](uint32_t tid, uint32_t nthr) {
+        for (uint32_t u = tid; u < ko * m; u += nthr) {
+            const uint32_t o = u >> LG, p = u & (m - 1);
+            Cx s = cx_mul(F[swz_cx(p)], ld_cx_stream(key + ((size_t)o << LG) + p));
+            for (uint32_t r = 1; r < nl; ++r) s = cx_add(s, cx_mul(F[(r << LG) + swz_cx(p)], ld_cx_stream(key + ((size_t)(r * ko + o) << LG) + p)));
+            Pb[(o << LG) + swz_cx(p)] = s;
+        }
+    });
+    fft_run_c<LG, false>(Pb, ko, T, run);
+    run([&](uint32_t tid, uint32_t nthr) {
+        for (uint32_t u = tid; u < ko * m; u += nthr) {
+            const uint32_t o = u >> LG, p = u & (m - 1);
+            Cx c = Pb[(o << LG) + swz_cx(p)];
+            c.re = f64_mul_rn(c.re, T.m_inv);
+            c.im = f64_mul_rn(c.im, T.m_inv);
+            const Cx x = cx_mul(c, ld_cx(T.tw_inv + p));
+            sink(o, p, f64_mod_u64_dev(x.re), p + m, f64_mod_u64_dev(x.im), true);
+        }
+    });
+}
 template <typename Src, typename Sink, typename Run>
 HD void tfhe_external_product_any(const TfheDev& P, Cx* F, Cx* Pb, const Cx* __restrict__ key, Src src, Sink sink, Run run) {
+    if (P.fourier_acc) {
+        switch (P.fft.lg) {
+            case 10: tfhe_external_product_acc_c<10>(P, F, Pb, key, src, sink, run); return;
+            case 9: tfhe_external_product_acc_c<9>(P, F, Pb, key, src, sink, run); return;
+            case 8: tfhe_external_product_acc_c<8>(P, F, Pb, key, src, sink, run); return;
+            default: break;  // other sizes: reference dataflow
+        }
+    }
     switch (P.fft.lg) {
         case 10: tfhe_external_product_c<10>(P, F, Pb, key, src, sink, run); break;
         case 9: tfhe_external_product_c<9>(P, F, Pb, key, src, sink, run); break;

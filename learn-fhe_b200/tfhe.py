@@ -52,6 +52,11 @@ class BootstrappingKey:
         except Exception:
             pass
 
+    def set_mode(self, fourier_acc):
+        """False (default): the reference's dataflow, bit-identical torus words; True: Fourier-domain accumulation (one
+        rounding per output coefficient; within the reference's error bound, decryptions identical)."""
+        self.ctx.call("fhe_tfhe_key_set_mode", self.h, 1 if fourier_acc else 0)
+
     @property
     def nbytes(self):
         return int(self.ctx.L.fhe_tfhe_key_bytes(self.h))

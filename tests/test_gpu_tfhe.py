@@ -108,6 +108,33 @@ def test_pbs_reference_parameters(pkg, ctx, orc):
     bk.free()
 
 
+def test_pbs_fourier_accumulation_mode(pkg, ctx, orc):
+    """Optional mode 1 (products summed in the Fourier domain): not the reference's rounding order, so the contract is the
+    north star's floating-point one - raw outputs within a stated bound of the reference's, decrypted results identical.
+    Bound: per CMUX and coefficient at most (k+1)d roundings of <= 2^(64 + log_b + log_n - 53) (c64.rs:186-208) are
+    replaced by one; over n CMUX steps and the key switch the phase moves by < 2^52 here (plaintext scale 2^59)."""
+    from learn_fhe_b200 import tfhe
+    P = orc.tfhe_testing_param()
+    K = orc.TfheKey(P, 0x5EED0003)
+    bk = _upload(pkg, ctx, P, K.export())
+    p = 1 << P.log_p
+    msgs = np.arange(p, dtype=np.uint64)
+    cts = K.encrypt(msgs, 21)
+    v = K.lut_poly(((3 * msgs + 1) % p).astype(np.uint64))
+    lut = tfhe.encode_lut(bk.param, v)
+    exact = tfhe.Bootstrapping.bootstrap(bk, lut, cts)
+    bk.set_mode(True)
+    fast = tfhe.Bootstrapping.bootstrap(bk, lut, cts)
+    bk.set_mode(False)
+    assert (tfhe.Bootstrapping.bootstrap(bk, lut, cts) == exact).all()  # the default mode is restored exactly
+    assert (K.decrypt(fast)[0] == (3 * msgs + 1) % p).all() and (K.decrypt(exact)[0] == (3 * msgs + 1) % p).all()
+    ph_fast, ph_exact = K.decrypt(fast)[1], K.decrypt(exact)[1]
+    diff = (ph_fast - ph_exact).astype(np.int64)
+    assert np.abs(diff).max() < 2 ** 52, np.abs(diff).max()
+    assert not (fast == exact).all()  # it really is a different rounding order
+    bk.free()
+
+
 def test_tfhe_parameter_errors(pkg, ctx, orc):
     from learn_fhe_b200 import tfhe
     P = _small_param(orc, k=1, bs_d=1, big_n=64, bs_log_b=23)
