@@ -131,7 +131,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     P = orc.fhew_testing_param()
     K = orc.FhewKey(P, 0x5EED0001)
-    sample = max(cores, 2 * cores if args.ref_sample is None else args.ref_sample)
+    sample = max(cores, 8 * cores if args.ref_sample is None else args.ref_sample)
     bits = np.random.default_rng(3).integers(0, 2, size=2 * sample).astype(np.int32)
     cts = K.encrypt(bits, 3)
     lin = (cts[:sample] + cts[sample:]) % np.uint64(P.big_q)
@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="gate bootstraps per GPU per step")
-    ap.add_argument("--ref-sample", type=int, default=None, help="gates per step of the reference arm (default 2 x cores)")
+    ap.add_argument("--ref-sample", type=int, default=None, help="gates per step of the reference arm (default 8 x cores)")
     ap.add_argument("--no-ntt", action="store_true", help="skip the NTT sweep leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ntt-reps", type=int, default=20)
@@ -467,7 +467,7 @@ def main():
         cores = os.cpu_count() or 1
         P = orc.fhew_testing_param()
         K = orc.FhewKey.from_arrays(P, *key_np) if hasattr(orc.FhewKey, "from_arrays") else None
-        sample = 2 * cores
+        sample = 40 * cores  # about 10 s of CPU work at ~4 gates/s/thread
         if K is not None:
             lin = h_in.numpy().view(np.uint64)[:sample].copy()
             t0 = time.perf_counter()
