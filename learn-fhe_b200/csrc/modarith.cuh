@@ -48,9 +48,8 @@ HD uint64_t mulhi_u64(uint64_t a, uint64_t b) {
 // hi64(a*b) from three 32x32 partial products; result in {Q-2, Q-1, Q} for Q = floor(a*b / 2^64)
 HD uint64_t mulhi_u64_approx(uint64_t a, uint64_t b) {
     uint32_t al = (uint32_t)a, ah = (uint32_t)(a >> 32), bl = (uint32_t)b, bh = (uint32_t)(b >> 32);
-    uint64_t t = (uint64_t)al * bh;
-    uint64_t u = (uint64_t)ah * bl;
-    return (uint64_t)ah * bh + (t >> 32) + (u >> 32);
+    // only the high words of the cross terms are needed: IMAD.HI (2 issue slots) instead of IMAD.WIDE (2.4)
+    return (uint64_t)ah * bh + (uint64_t)mulhi_u32(al, bh) + (uint64_t)mulhi_u32(ah, bl);
 }
 HD uint32_t umin_(uint32_t a, uint32_t b) { return a < b ? a : b; }
 // a + b for sums that cannot wrap (a + b < 2^32), forced onto the ALU pipe (VIADDMNMX).  ptxas otherwise places many
