@@ -101,3 +101,34 @@ def test_twiddle_table_matches_reference_rule(pkg, ctx, orc):
         ln = min(len(f_ref), 1 << 11)
         f, i = util.twiddles(ctx, q, ln)
         assert (f == f_ref[:ln]).all() and (i == i_ref[:ln]).all()
+
+
+def test_ntt_degree_2_17_and_rns_batches(pkg, ctx, orc):
+    """Largest supported degree (column S=4 + 2^13 tiles) and the multi-modulus entry point with ragged polynomial counts."""
+    log_n = 17
+    n = 1 << log_n
+    for bits, word in ((55, 64), (28, 32)):
+        q = orc.two_adic_primes(bits, log_n + 1, 1)[0]
+        a = orc.residues(0x5EED2000 + bits, n * 2, q).reshape(2, n)
+        ref = orc.ntt_fwd(q, a, threads=2)
+        got = _run(pkg, ctx, q, a, True, word)
+        assert (got == ref).all(), (log_n, word)
+        assert (_run(pkg, ctx, q, ref, False, word) == a).all(), (log_n, word)
+    # fhe_ntt_fwd_rns / inv_rns: [batch][limbs][n], limb = polynomial index % limbs; 3 x 5 = 15 polynomials (not a multiple of 4)
+    import torch
+    for log_n in (9, 12, 14):
+        n = 1 << log_n
+        qs = orc.two_adic_primes(55, log_n + 1, 5)
+        x = np.stack([np.stack([orc.residues(7 * b + i, n, q) for i, q in enumerate(qs)]) for b in range(3)])
+        t = pkg.to_dev(x)
+        qa = np.ascontiguousarray(qs, dtype=np.uint64)
+        ctx.call("fhe_ntt_fwd_rns", pkg.hptr(qa), len(qs), log_n, 3, pkg.dptr(t))
+        ctx.sync()
+        got = pkg.to_host(t)
+        for b in range(3):
+            for i, q in enumerate(qs):
+                assert (got[b, i] == orc.ntt_fwd(q, x[b, i])).all(), (log_n, b, i)
+        ctx.call("fhe_ntt_inv_rns", pkg.hptr(qa), len(qs), log_n, 3, pkg.dptr(t))
+        ctx.sync()
+        assert (pkg.to_host(t) == x).all()
+        ctx.call("fhe_ntt_fwd_rns", pkg.hptr(qa), len(qs), log_n, 0, pkg.dptr(t))  # empty batch is a no-op
