@@ -245,6 +245,20 @@ fhe_status fhe_ckks_key_switch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ks
  * d_pt [pt_count][level][N] coefficient form with pt_count == 1 (shared) or count; out [count][2][level-1][N] */
 fhe_status fhe_ckks_mul_plain_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t count, size_t pt_count,
                                             const uint64_t* d_pt, const uint64_t* d_ct, uint64_t* d_out);
+/* One rotation of a BSGS plan: t = 5^j mod 2N (ckks.rs:279-282; 0 = no rotation, key may then be NULL) */
+typedef struct fhe_ckks_rot {
+    int64_t t;
+    const fhe_ckks_ksk* key;
+} fhe_ckks_rot;
+/* Bootstrapping::mul_mat (scheme/ckks/src/bootstrapping.rs:92-108; the building block of coeff_to_slot / slot_to_coeff):
+ *   out = sum_i rot_{giant[i]}( sum_j mul_constant(pt_ij, rot_{baby[j]}(ct)) )
+ * with every mul_constant rescaling before the sums, exactly as the reference.  `present` [n_giant][n_baby] marks the (i, j)
+ * pairs that carry a diagonal; d_pts holds their encoded plaintexts [number present][level][N] (coefficient form) in
+ * row-major (i, j) order.  ct [count][2][level][N] -> out [count][2][level-1][N].  The BSGS plan and the diagonal encoding
+ * (misc/matrix.rs, sfft.rs, 256-bit floats) are host-side and not part of this library. */
+fhe_status fhe_ckks_mul_mat(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t count, size_t n_baby, const fhe_ckks_rot* baby,
+                            size_t n_giant, const fhe_ckks_rot* giant, const uint8_t* present, const uint64_t* d_pts,
+                            const uint64_t* d_ct, uint64_t* d_out);
 /* CkksCiphertext::rescale (ckks.rs:123-125): [count][2][l][N] -> [count][2][l-1][N] */
 fhe_status fhe_ckks_rescale(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t count, const uint64_t* d_ct, uint64_t* d_out);
 

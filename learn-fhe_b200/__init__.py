@@ -38,6 +38,11 @@ class FhewParam(C.Structure):
         return 1 << self.log_n
 
 
+class CkksRot(C.Structure):
+    """fhe_ckks_rot: one rotation of a BSGS plan (t = 5^j mod 2N, 0 = none)."""
+    _fields_ = [("t", C.c_int64), ("key", C.c_void_p)]
+
+
 class TfheParam(C.Structure):
     """fhe_tfhe_param (mirrors tfhe BootstrappingParam, scheme/tfhe/src/bootstrapping.rs:14-38)."""
     _fields_ = [("log_p", C.c_uint), ("padding", C.c_uint), ("n", C.c_uint), ("ks_log_b", C.c_uint), ("ks_d", C.c_uint),
@@ -166,6 +171,7 @@ def lib():
         L.fhe_ckks_key_switch.argtypes = [vp, vp, vp, i64, sz, sz, vp, vp]
         L.fhe_ckks_rescale.argtypes = [vp, vp, sz, sz, vp, vp]
         L.fhe_ckks_mul_plain_rescale_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
+        L.fhe_ckks_mul_mat.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

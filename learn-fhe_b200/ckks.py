@@ -135,6 +135,24 @@ class Ckks:
         return to_host(d_out)
 
     @staticmethod
+    def mul_mat(param, baby, giant, present, pts, ct):
+        """Bootstrapping::mul_mat (scheme/ckks/src/bootstrapping.rs:92-108).  baby / giant: lists of (t, CkksKeySwitchingKey or
+        None); present [n_giant][n_baby] 0/1; pts [number present][level][N] encoded diagonals in row-major (i, j) order."""
+        import torch
+        from . import CkksRot
+        ct, pts = _u64(ct), _u64(pts)
+        count, _, level, n = ct.shape
+        mk = lambda lst: (CkksRot * len(lst))(*[CkksRot(t, k.h if k is not None else None) for t, k in lst])
+        b_arr, g_arr = mk(baby), mk(giant)
+        pres = np.ascontiguousarray(present, dtype=np.uint8)
+        d_ct, d_pts = to_dev(ct, param.ctx.device), to_dev(pts, param.ctx.device)
+        d_out = torch.empty((count, 2, level - 1, n), dtype=torch.int64, device=d_ct.device)
+        param.ctx.call("fhe_ckks_mul_mat", param.h, level, count, len(baby), C.cast(b_arr, C.c_void_p), len(giant), C.cast(g_arr, C.c_void_p),
+                       hptr(pres), dptr(d_pts), dptr(d_ct), dptr(d_out))
+        param.ctx.sync()
+        return to_host(d_out)
+
+    @staticmethod
     def rescale(param, ct):
         """CkksCiphertext::rescale (ckks.rs:123-125)."""
         import torch

@@ -176,6 +176,13 @@ __global__ void __launch_bounds__(256) ckks_ptmul_kernel(const Mod64* __restrict
         e[idx] = m.mul(e[idx], pe[(pt_per_ct ? c * ln : 0) + r]);
     }
 }
+// limb-wise modular addition of RNS polynomials: out = a + b over [polys][n] with modulus mods[poly % l]   (rns.rs Add impls)
+__global__ void __launch_bounds__(256) rns_add_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long polys,
+                                                      const uint64_t* __restrict__ a, const uint64_t* __restrict__ b, uint64_t* __restrict__ out) {
+    const unsigned long long total = polys << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+        out[idx] = mods[(idx >> log_n) % l].add(a[idx], b[idx]);
+}
 // RnsRq::automorphism (rns.rs:74-77 -> avec.rs:34-50) on [polys][n] with modulus mods[poly % l]
 __global__ void __launch_bounds__(256) rns_automorphism_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long polys, uint32_t t,
                                                                const uint64_t* __restrict__ in, uint64_t* __restrict__ out) {
@@ -264,6 +271,8 @@ static fhe_status run_rescale(fhe_ctx* ctx, const std::vector<uint64_t>& all, si
 using namespace fhe;
 
 struct fhe_ckks_ctx {
+    void* ws2 = nullptr;  // second grow-only workspace (fhe_ckks_mul_mat, which calls entry points that use `ws`)
+    size_t ws2_bytes = 0;
     unsigned log_n = 0;
     size_t big_l = 0;
     std::vector<uint64_t> qs, ps;
@@ -373,6 +382,7 @@ void fhe_ckks_destroy(fhe_ctx* ctx, fhe_ckks_ctx* ck) {
     if (ctx) cudaStreamSynchronize(ctx->stream);
     if (ck->d_mods) cudaFree(ck->d_mods);
     if (ck->ws) cudaFree(ck->ws);
+    if (ck->ws2) cudaFree(ck->ws2);
     delete ck;
 }
 fhe_status fhe_ckks_ksk_upload(fhe_ctx* ctx, fhe_ckks_ctx* ck, const uint64_t* ksk, fhe_ckks_ksk** out) {
@@ -533,6 +543,76 @@ fhe_status fhe_ckks_mul_plain_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, size
         FHE_CHECK(after_launch(ctx, "ckks_ptmul_kernel"));
         FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, c * 2 * l, e, false));
         FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, e, nullptr, nullptr, false, d_out + base * 2 * (l - 1) * n));
+    }
+    return FHE_OK;
+}
+
+// Bootstrapping::mul_mat (scheme/ckks/src/bootstrapping.rs:92-108): baby-step / giant-step product of a diagonal-sparse matrix
+// with `count` ciphertexts: out = sum_i rot_{g_i}( sum_j mul_constant(pt_ij, rot_{b_j}(ct)) ), every mul_constant rescaling
+// before the sums exactly like the reference.  The BSGS plan and the encoded diagonals come from the host (misc/matrix.rs,
+// sfft.rs: out of scope); this evaluates them with the rotation / plaintext-product kernels above.
+fhe_status fhe_ckks_mul_mat(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t count, size_t n_baby, const fhe_ckks_rot* baby, size_t n_giant,
+                            const fhe_ckks_rot* giant, const uint8_t* present, const uint64_t* d_pts, const uint64_t* d_ct, uint64_t* d_out) {
+    if (!ctx || !ck) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, baby && giant && present && d_pts && d_ct && d_out && n_baby >= 1 && n_giant >= 1, "null pointer or empty plan");
+    FHE_REQUIRE(ctx, level >= 2 && level <= ck->big_l, "level must be in [2, L] (mul_constant rescales)");
+    const unsigned log_n = ck->log_n;
+    const size_t n = (size_t)1 << log_n, l = level, ct_in = count * 2 * l * n, ct_out = count * 2 * (l - 1) * n;
+    for (size_t j = 0; j < n_baby; ++j) FHE_REQUIRE(ctx, baby[j].t == 0 || baby[j].key, "baby step %zu has no rotation key", j);
+    for (size_t i = 0; i < n_giant; ++i) {
+        FHE_REQUIRE(ctx, giant[i].t == 0 || giant[i].key, "giant step %zu has no rotation key", i);
+        bool any = false;
+        for (size_t j = 0; j < n_baby; ++j) any = any || present[i * n_baby + j];
+        FHE_REQUIRE(ctx, any, "giant step %zu has no diagonal", i);
+    }
+    const size_t words = n_baby * ct_in + 3 * ct_out;
+    if (ck->ws2_bytes < words * 8) {
+        FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ck->ws2) cudaFree(ck->ws2);
+        ck->ws2 = nullptr;
+        ck->ws2_bytes = 0;
+        if (cudaMalloc(&ck->ws2, words * 8) != cudaSuccess) return fail(ctx, FHE_ENOMEM, "mul_mat workspace of %zu bytes", words * 8);
+        ck->ws2_bytes = words * 8;
+    }
+    uint64_t* rot = (uint64_t*)ck->ws2;             // [n_baby] rotated inputs
+    uint64_t* inner = rot + n_baby * ct_in;         // sum over baby steps of one giant step
+    uint64_t* tmp = inner + ct_out;
+    uint64_t* tmp2 = tmp + ct_out;
+    auto add = [&](const uint64_t* a, const uint64_t* b, uint64_t* o) -> fhe_status {
+        rns_add_kernel<<<stream_grid(ctx, (unsigned long long)ct_out), 256, 0, ctx->stream>>>(ck->d_mods, (int)(l - 1), (int)log_n,
+                                                                                               count * 2 * (l - 1), a, b, o);
+        return after_launch(ctx, "rns_add_kernel");
+    };
+    std::vector<const uint64_t*> rj(n_baby);
+    for (size_t j = 0; j < n_baby; ++j) {
+        if (baby[j].t == 0) {
+            rj[j] = d_ct;
+        } else {
+            FHE_CHECK(fhe_ckks_key_switch(ctx, ck, baby[j].key, baby[j].t, l, count, d_ct, rot + j * ct_in));
+            rj[j] = rot + j * ct_in;
+        }
+    }
+    size_t pt_idx = 0;
+    for (size_t i = 0; i < n_giant; ++i) {
+        bool first = true;
+        for (size_t j = 0; j < n_baby; ++j) {
+            if (!present[i * n_baby + j]) continue;
+            const uint64_t* pt = d_pts + pt_idx * l * n;
+            ++pt_idx;
+            FHE_CHECK(fhe_ckks_mul_plain_rescale_batch(ctx, ck, l, count, 1, pt, rj[j], first ? inner : tmp));
+            if (!first) FHE_CHECK(add(inner, tmp, inner));
+            first = false;
+        }
+        const uint64_t* term = inner;
+        if (giant[i].t != 0) {
+            FHE_CHECK(fhe_ckks_key_switch(ctx, ck, giant[i].key, giant[i].t, l - 1, count, inner, tmp2));
+            term = tmp2;
+        }
+        if (i == 0)
+            FHE_CUDA(ctx, cudaMemcpyAsync(d_out, term, ct_out * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        else
+            FHE_CHECK(add(d_out, term, d_out));
     }
     return FHE_OK;
 }

@@ -138,6 +138,39 @@ def test_mul_constant_matches_oracle(pkg, ctx, orc, ckks_setup):
             assert (got[i] == K.rescale(prod)).all(), (per_ct, i)
 
 
+def test_mul_mat_bsgs_matches_oracle(pkg, ctx, orc, ckks_setup):
+    """Bootstrapping::mul_mat (scheme/ckks/src/bootstrapping.rs:92-108) with a 2 x 2 BSGS plan (baby rotations {0, 5}, giant
+    rotations {0, -1 (conjugation key stands in for a second rotation key)}, one absent diagonal), random encoded diagonals:
+    equal, limb for limb, to the composition of the oracle's rotate / mul_constant / add in the reference's order."""
+    from learn_fhe_b200 import ckks
+    K, P, rlk = ckks_setup
+    level = P.big_l
+    q = lambda lv: [np.uint64(x) for x in P.qs[:lv]]
+    cts = np.stack([K.encrypt(_small_pt(80 + i, K.n), level, 600 + i) for i in range(2)])
+    keys = [ckks.CkksKeySwitchingKey(P, K.ksk(w)) for w in range(len(K.auto_ts))]
+    baby = [(0, None), (K.auto_ts[0], keys[0])]
+    giant = [(0, None), (K.auto_ts[1], keys[1])]
+    present = np.array([[1, 1], [0, 1]], dtype=np.uint8)
+    pts = np.stack([np.stack([np.mod(_small_pt(90 + j, K.n, 1 << 30), int(m)).astype(np.uint64) for m in P.qs[:level]]) for j in range(3)])
+    got = ckks.Ckks.mul_mat(P, baby, giant, present, pts, cts)
+
+    def rns_add(a, b, lv):
+        return np.stack([np.stack([(a[h, t] + b[h, t]) % q(lv)[t] for t in range(lv)]) for h in range(2)])
+
+    def mul_constant(pt, ct):
+        prod = np.stack([np.stack([orc.ntt_mul(P.qs[t], ct[h, t], pt[t]) for t in range(level)]) for h in range(2)])
+        return K.rescale(prod)
+
+    for c in range(2):
+        rot = [cts[c], K.key_switch(0, cts[c], apply_auto=True)]
+        inner0 = rns_add(mul_constant(pts[0], rot[0]), mul_constant(pts[1], rot[1]), level - 1)
+        inner1 = mul_constant(pts[2], rot[1])
+        ref = rns_add(inner0, K.key_switch(1, inner1, apply_auto=True), level - 1)
+        assert (got[c] == ref).all(), c
+    for k in keys:
+        k.free()
+
+
 def test_ckks_level_errors(pkg, ctx, orc, ckks_setup):
     from learn_fhe_b200 import ckks
     K, P, rlk = ckks_setup
