@@ -14,7 +14,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libfhe_b200.so")
+# FHE_B200_LIB: developer override used for A/B builds of the same library (learn-fhe_b200/csrc/Makefile, EXTRA=...)
+LIB_PATH = os.environ.get("FHE_B200_LIB") or os.path.join(_HERE, "libfhe_b200.so")
 HEADER = os.path.join(REPO, "include", "fhe_b200.h")
 
 FHE_OK, FHE_EINVAL, FHE_ECUDA, FHE_ENOMEM, FHE_EUNSUPPORTED = 0, 1, 2, 3, 4

@@ -82,7 +82,8 @@ struct Lz64 {
     static constexpr int BITS = 64;
     static constexpr int FWD_GROW = 4;
     static constexpr int FWD_LIMIT = 128;  // < 2^64 / q for q < 2^56 (only checked by the planner)
-    uint64_t q, nq, q2, q4, q16, mu;       // nq = 2^64 - q; mu = floor(2^64 / q)
+    uint64_t q, nq, q2, q4, q16;           // nq = 2^64 - q
+    uint32_t mu32, sh_e, sh_f, pad_;       // one-multiply Barrett: see barrett2
     HD uint64_t mul_lazy(uint64_t y, uint64_t w, uint64_t wp) const { return w * y + mulhi_u64_approx(wp, y) * nq; }  // [0,4q)
     HD void bf_fwd(uint64_t& x, uint64_t& y, TwPair<uint64_t> t) const {
         const uint64_t ty = mul_lazy(y, t.w, t.wp);
@@ -91,10 +92,15 @@ struct Lz64 {
         y = x0 + q4 - ty;
     }
     HD uint64_t pre_red(uint64_t x) const { return x; }
-    HD uint64_t barrett4(uint64_t x) const { return x + mulhi_u64_approx(x, mu) * nq; }  // any x -> [0,4q)
+    // x < 2^8 * 2^k (k = bit length of q; every lazy bound of this path is <= 256 q) -> [0, 2q) with ONE 32-bit high
+    // multiply: xs = x >> e < 2^32 (e = max(k - 24, 0)), mu32 = floor(2^(32+f+e) / q) < 2^32 (f = k - 1 - e), and
+    // Qh = (xs * mu32) >> (32 + f) is floor(x / q) or one less (error terms x / 2^(k+31) + 2^e / q < 1).
+    HD uint64_t barrett2(uint64_t x) const {
+        const uint32_t qh = mulhi_u32((uint32_t)(x >> sh_e), mu32) >> sh_f;
+        return x + (uint64_t)qh * nq;
+    }
     HD uint64_t canon(uint64_t x) const {
-        uint64_t r = barrett4(x);
-        r = umin_(r, r - q2);
+        const uint64_t r = barrett2(x);
         return umin_(r, r - q);
     }
     // stage = 0 for the first stage executed inside the pass (operands < 16q), 1 for the next (sum chain < 32q), ...
@@ -108,12 +114,37 @@ struct Lz64 {
         x = mul_lazy(s, ninv.w, ninv.wp);
         y = mul_lazy(d, wninv.w, wninv.wp);
     }
-    HD uint64_t inv_pass_fix(uint64_t x) const { return barrett4(x); }
+    HD uint64_t inv_pass_fix(uint64_t x) const { return barrett2(x); }
     HD uint64_t inv_canon(uint64_t x) const {  // [0,4q) -> [0,q)
         uint64_t r = umin_(x, x - q2);
         return umin_(r, r - q);
     }
 };
+
+// host-side constructors (setup only; shared by the launcher and tests/hostsim)
+inline Lz32 make_lz32(uint64_t q) {
+    Lz32 m;
+    m.q = (uint32_t)q;
+    m.q2 = (uint32_t)(2 * q);
+    m.q8 = (uint32_t)(8 * q);
+    m.mu = (uint32_t)((1ull << 32) / q);
+    return m;
+}
+inline Lz64 make_lz64(uint64_t q) {
+    Lz64 m;
+    m.q = q;
+    m.nq = 0 - q;
+    m.q2 = 2 * q;
+    m.q4 = 4 * q;
+    m.q16 = 16 * q;
+    int k = 0;
+    while ((q >> k) != 0) ++k;  // q < 2^k
+    m.sh_e = (uint32_t)(k > 24 ? k - 24 : 0);
+    m.sh_f = (uint32_t)(k - 1) - m.sh_e;
+    m.mu32 = (uint32_t)((((unsigned __int128)1) << (32 + m.sh_f + m.sh_e)) / q);
+    m.pad_ = 0;
+    return m;
+}
 
 // per-limb descriptor (device array; limb = polynomial index % limbs)
 template <typename L>

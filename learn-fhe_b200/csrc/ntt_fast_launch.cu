@@ -6,6 +6,7 @@
 //                            inverse stages), coalesced along the row direction.
 // Replaces util/src/ring/fft/zq.rs:27-36 (+ ring/fft.rs:40-77) for every caller: fhe_ntt_*, CKKS limb batches, key
 // upload.  Moduli outside the lazy-reduction preconditions fall back to the generic kernels (ntt_launch.cu).
+#include <cstdlib>
 #include <algorithm>
 
 #include "ctx.cuh"
@@ -36,8 +37,17 @@ struct FastGeom {
     static constexpr int NP3 = (LOGT - R1) / 3;
 };
 
+// resident threads per SM the tile kernels are compiled for (register cap = 65536 / this): u64 1024 (64 registers),
+// u32 1536 (40 registers; 2048 forces 32 and spills in the 2^12 / 2^13 tiles)
+#ifndef FAST_OCC32
+#define FAST_OCC32 1536
+#endif
+#ifndef FAST_OCC64
+#define FAST_OCC64 1024
+#endif
 template <typename L, int LOGT, bool FWD, bool FINAL>
-__global__ void __launch_bounds__(FastGeom<LOGT>::NTHR) ntt_fast_tile_kernel(FastArgs<L> a) {
+__global__ void __launch_bounds__(FastGeom<LOGT>::NTHR, (L::BITS == 32 ? FAST_OCC32 : FAST_OCC64) / FastGeom<LOGT>::NTHR)
+ntt_fast_tile_kernel(FastArgs<L> a) {
     typedef typename L::W W;
     typedef FastGeom<LOGT> G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -105,23 +115,11 @@ template <typename L>
 L make_lazy(uint64_t q);
 template <>
 Lz32 make_lazy<Lz32>(uint64_t q) {
-    Lz32 m;
-    m.q = (uint32_t)q;
-    m.q2 = (uint32_t)(2 * q);
-    m.q8 = (uint32_t)(8 * q);
-    m.mu = (uint32_t)((1ull << 32) / q);
-    return m;
+    return make_lz32(q);
 }
 template <>
 Lz64 make_lazy<Lz64>(uint64_t q) {
-    Lz64 m;
-    m.q = q;
-    m.nq = 0 - q;
-    m.q2 = 2 * q;
-    m.q4 = 4 * q;
-    m.q16 = 16 * q;
-    m.mu = (uint64_t)((((u128_t)1) << 64) / q);
-    return m;
+    return make_lz64(q);
 }
 
 template <typename L>
@@ -215,7 +213,12 @@ static fhe_status launch_ntt_fast(fhe_ctx* ctx, const uint64_t* qs, size_t nl, u
         if (!fast_modulus_ok<L>(qs[i])) return FHE_EUNSUPPORTED;
     if (n_polys == 0) return FHE_OK;
     if (n_polys > 0x7FFFFFFFull) return fail(ctx, FHE_EINVAL, "batch too large");
-    const int logt = log_n <= 13 ? (int)log_n : (log_n == 17 ? 13 : 12);
+    // rings larger than one tile: column kernel (S <= 4 stages, HBM-bound) + tiles; measured best tile 2^11 for N = 2^14, 2^15
+    int logt = log_n <= 13 ? (int)log_n : (log_n <= 15 ? 11 : (int)log_n - 4);
+    if (const char* e = getenv("FHE_B200_NTT_LOGT")) {  // tuning knob: tile size for rings larger than one tile
+        const int v = atoi(e);
+        if (log_n > 13 && v >= 9 && v <= 13 && (int)log_n - v <= 4) logt = v;
+    }
     const int S = (int)log_n - logt;
     FastArgs<L> a;
     a.data = d_a;

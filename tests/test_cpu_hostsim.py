@@ -149,6 +149,21 @@ def test_kernel_logic_ntt_fast(H, orc, log_n):
             assert fn(q, log_n, logt, x, 0) == 0 and (x.astype(np.uint64) == a).all(), (log_n, bits, logt, "inv")
 
 
+def test_lz64_one_multiply_barrett(H):
+    """Lz64::barrett2 (one 32-bit high multiply): for moduli of every bit length 3..56 and lazy values up to the
+    path's largest bound 256 q (edges included) the result is congruent and below 2q, and canon() is exact."""
+    rng = np.random.default_rng(11)
+    H.sim_lz64_barrett2.argtypes = [C.c_uint64, C.c_void_p, C.c_size_t]
+    for k in range(3, 57):
+        for q in {(1 << k) - 1, (1 << (k - 1)) + 1, int(rng.integers((1 << (k - 1)) + 1, 1 << k)) | 1}:
+            edge = [0, 1, q - 1, q, q + 1, 2 * q - 1, 2 * q, 255 * q, 256 * q - 1, 128 * q, 128 * q - 1]
+            mult = rng.integers(0, 256, size=2000, dtype=np.uint64) * np.uint64(q)
+            xs = np.concatenate([np.array(edge, dtype=np.uint64), mult + rng.integers(0, q, size=2000, dtype=np.uint64),
+                                 mult[:50], mult[:50] + np.uint64(q - 1)])
+            assert int(xs.max()) < 256 * q
+            assert H.sim_lz64_barrett2(q, xs.ctypes.data, xs.size) == 0, (k, q)
+
+
 def test_fast_swizzle(H):
     H.sim_swz2_32.restype = C.c_uint
     H.sim_swz2_64.restype = C.c_uint
