@@ -153,6 +153,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def ncu_traffic(kernel, units):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py) when that capture processed the same number of units."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        rec = json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+    return rec["dram_bytes"] if rec and rec.get("units") == units else None
+
+
 def ntt_sweep(pkg, ctx, torch, hbm_peak, reps, log_ns, batch):
     """BASELINE configs[1]: forward + inverse, in place, device resident; buffers rotate through a pool larger than L2."""
     from learn_fhe_b200 import util
@@ -254,7 +267,10 @@ def tfhe_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps, synthetic_
     m, lg, nl = N // 2, (N // 2).bit_length() - 1, (k + 1) * P.bs_d
     ffts = n * (nl + (k + 1) * nl)
     flops = ffts * (m // 2) * lg * 10 + n * (nl * m * 6 + (k + 1) * nl * m * (6 + 8))
-    fp64_peak = 148 * 64 * 2 * 1.965e9  # nominal: 64 FP64 FMA lanes per SM per clock (no measured f64 peak in MEASURED_PEAKS.json)
+    # The reference rounds every product and every sum separately (c64.rs / fft.rs use plain f64 * and +), so a bit-identical
+    # kernel cannot contract them into FMAs: the binding rate is one f64 operation per lane per clock.  Nominal B200 figure
+    # (64 FP64 lanes per SM per clock at the maximum SM clock; MEASURED_PEAKS.json has no f64 entry).
+    fp64_ops_peak = 148 * 64 * 1.965e9
     res = {"metric": "tfhe_pbs_per_sec", "value": batch * world * steps / (ms * 1e-3), "unit": "PBS/s", "batch_per_gpu": batch,
            "steps": steps, "ms_per_step": ms / steps,
            "config": ("synthetic, not from the reference: n=630 N=1024 k=1 B=2^7 d=3, ks B=2^2 d=8; bit-exact f64 FFT dataflow" if synthetic_n1024 else
@@ -262,9 +278,12 @@ def tfhe_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps, synthetic_
            "key_bytes": bk.nbytes,
            "kernels": {kk: {"ms_per_launch": v["ms"] / v["launches"], "launches": v["launches"]} for kk, v in prof.items()},
            "roofline": {"bound": "fp64", "kernel": "tfhe_blind_rotate_kernel", "achieved": flops * batch / (br_ms * 1e-3) / 1e12 if br_ms else None,
-                        "peak": fp64_peak / 1e12, "unit": "TFLOP/s f64 (algorithmic, unfused mul/add; peak nominal 64 FMA lanes/SM/clk)",
-                        "frac": flops * batch / (br_ms * 1e-3) / fp64_peak if br_ms else None, "traffic": None,
-                        "flops_per_pbs": flops}}
+                        "peak": fp64_ops_peak / 1e12,
+                        "unit": "Tflop/s f64 (algorithmic unfused multiplies and adds of the reference dataflow; peak = nominal "
+                                "non-FMA issue rate, 64 lanes/SM/clk x 148 SMs x 1.965 GHz)",
+                        "frac": flops * batch / (br_ms * 1e-3) / fp64_ops_peak if br_ms else None,
+                        "frac_vs_fma_peak": flops * batch / (br_ms * 1e-3) / (2 * fp64_ops_peak) if br_ms else None,
+                        "traffic": ncu_traffic("tfhe_blind_rotate_kernel", batch), "flops_per_pbs": flops}}
     # optional evaluation mode: products summed in the Fourier domain (within the reference's error bound, decryptions
     # identical; NOT bit-identical, so it is reported beside the headline, never as it)
     bk.set_mode(True)
@@ -312,6 +331,21 @@ def ckks_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps):
            "config": "CKKS-T: N=2^16, log_qi=55, L=8 (+8 special primes), level 8 -> 7, rlk resident",
            "compulsory_hbm_gbs": io_bytes * steps / (ms * 1e-3) / 1e9, "ntt_per_mult": 9 * L + 3 * L,
            "kernels": {kk: {"ms_per_step": v["ms"] / steps, "launches": v["launches"]} for kk, v in prof.items()}}
+    # INT32-pipe roofline of the whole operation (same instruction-mix rule as the NTT lines: 9 32-bit products per 64-bit
+    # Shoup butterfly or modular multiply).  Work per Ckks::mul (ckks.rs:255-293, rns.rs:99-158), l = L:
+    #   (9l + 3L) NTTs of N/2 log N butterflies; tensor 4 l N; key products 2 (l + L) N; base conversion l -> L of d2:
+    #   (l + l L) N; rescale_k by the L special primes of 2 polynomials: 2 (L + L l + l) N; final rescale: 2 (1 + 2 (l - 1)) N
+    pk = ctx.int32_peak()
+    if pk.get("imad"):
+        l = L
+        n_bf = (9 * l + 3 * L) * (P.n // 2) * log_n
+        n_mm = (4 * l + 2 * (l + L) + (l + l * L) + 2 * (L + L * l + l) + 2 * (1 + 2 * (l - 1))) * P.n
+        per = (4 / pk["imad"] + 2 / pk["imad_hi"] + 3 / pk["imad_wide"]) / 1e12
+        t_min = (n_bf + n_mm) * per * batch
+        res["roofline"] = {"bound": "int32", "kernel": "whole Ckks::mul (ntt_fast_* 60 %, rns_rescale 20 %)", "achieved": 9 * (n_bf + n_mm) * batch / (ms / steps * 1e-3) / 1e12,
+                           "peak": 9 / per / 1e12, "unit": "Tmul/s (algorithmic 32-bit products; peak = measured INT32 multiply-pipe rate for 3 IMAD.WIDE + 2 IMAD.HI + 4 IMAD)",
+                           "frac": t_min / (ms / steps * 1e-3), "traffic": None,
+                           "butterflies_per_mult": n_bf, "pointwise_modmuls_per_mult": n_mm}
     rlk.free()
     P.free()
     del ct0, ct1, out
@@ -502,7 +536,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ct_words * 8 + param.n * 8),
                         "d2h_bytes_per_step": int(ct_words * 8)},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": kt["roofline"], "kernels": kt["kernels"], "cpu_baseline": cpu, "peak_source": peak_src}
+                "roofline": dict(kt["roofline"], traffic=ncu_traffic("fhew_blind_rotate_fast_kernel", B)), "kernels": kt["kernels"], "cpu_baseline": cpu, "peak_source": peak_src}
         if tfhe_res is not None:
             line["tfhe_pbs"] = tfhe_res
             line["tfhe_pbs_n1024_synthetic"] = tfhe_res_1024
@@ -514,6 +548,16 @@ def main():
             line["roofline_ntt"] = {"bound": "hbm", "achieved": best["fwd_gbs"], "peak": hbm_peak, "unit": "GB/s",
                                     "frac": best["fwd_frac_hbm"], "traffic": None,
                                     "kernel": "ntt fwd u64 N=2^%d batch 4096" % best["log_n"]}
+            # the transforms are bound by the INT32 multiply pipe, not by HBM: a 64-bit Shoup butterfly is 9 32-bit products
+            # (3 IMAD.WIDE + 2 IMAD.HI + 4 IMAD), a 32-bit one 3 (2 IMAD + 1 IMAD.HI); same measured rates as `roofline`
+            pk = kt["roofline"]["int32_peaks_tops"]
+            if pk.get("imad"):
+                for r in ntt:
+                    bf = r["batch"] * (1 << r["log_n"]) // 2 * r["log_n"]
+                    per = (4 / pk["imad"] + 2 / pk["imad_hi"] + 3 / pk["imad_wide"]) if r["word_bits"] == 64 else (2 / pk["imad"] + 1 / pk["imad_hi"])
+                    r["fwd_frac_int32"] = round(bf * per / 1e12 / (r["fwd_ms"] * 1e-3), 4)
+                    r["inv_frac_int32"] = round(bf * per / 1e12 / (r["inv_ms"] * 1e-3), 4)
+                line["roofline_ntt"]["frac_int32_pipe"] = best["fwd_frac_int32"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -230,9 +230,11 @@ class Context:
 
     def int32_peak(self):
         """Measured IMAD / IMAD.HI / IMAD.WIDE peaks of this device, 10^12 thread-ops per second."""
-        a, b, c = C.c_double(), C.c_double(), C.c_double()
-        self.ck(self.L.fhe_diag_int32_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"imad": a.value, "imad_hi": b.value, "imad_wide": c.value}
+        if getattr(self, "_int32_peak", None) is None:
+            a, b, c = C.c_double(), C.c_double(), C.c_double()
+            self.ck(self.L.fhe_diag_int32_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
+            self._int32_peak = {"imad": a.value, "imad_hi": b.value, "imad_wide": c.value}
+        return dict(self._int32_peak)
 
     @property
     def launches(self):

@@ -164,8 +164,11 @@ __global__ void fhew_pack4_kernel(const uint2* __restrict__ ab, uint4* __restric
 }
 
 // Fast path (fhew_fast.cuh).  mode 0: out = LWE ciphertext [N+1] (sample_extract + post_add); mode 1: accumulator [2][N]
+#ifndef FF_MINB
+#define FF_MINB 7
+#endif
 template <typename FT, typename OT>
-__global__ void __launch_bounds__(FF_THREADS) fhew_blind_rotate_fast_kernel(FhewFastDev P, const FT* __restrict__ f,
+__global__ void __launch_bounds__(FF_THREADS, FF_MINB) fhew_blind_rotate_fast_kernel(FhewFastDev P, const FT* __restrict__ f,
                                                                              const uint32_t* __restrict__ ct2n, uint32_t post_add,
                                                                              unsigned long long count, OT* __restrict__ out, int mode,
                                                                              int* __restrict__ err) {
@@ -174,8 +177,14 @@ __global__ void __launch_bounds__(FF_THREADS) fhew_blind_rotate_fast_kernel(Fhew
     FhewFastSmem S;
     S.acc = words;
     S.dig = words + 2 * FF_N;
-    S.tw = reinterpret_cast<TwPair<uint32_t>*>(words + 10 * FF_N);
-    S.itw = S.tw + FF_N;
+#if FF_TW_NC
+    S.tw = P.tw;
+    S.itw = P.itw;
+#else
+    TwPair<uint32_t>* stw = reinterpret_cast<TwPair<uint32_t>*>(words + 10 * FF_N);
+    S.tw = stw;
+    S.itw = stw + FF_N;
+#endif
     uint16_t* steps = reinterpret_cast<uint16_t*>(words + ff_fixed_words());
     const uint32_t max_steps = P.n_s + FF_N + 2;
     uint32_t* a2n = reinterpret_cast<uint32_t*>(steps + ((max_steps + 1) & ~1u));
@@ -183,10 +192,12 @@ __global__ void __launch_bounds__(FF_THREADS) fhew_blind_rotate_fast_kernel(Fhew
     uint16_t* cnt = reinterpret_cast<uint16_t*>(S.dig);  // schedule scratch aliases the digit region
     uint16_t* sorted = cnt + FF_N;
     const uint32_t tid = threadIdx.x;
+#if !FF_TW_NC
     for (uint32_t i = tid; i < (uint32_t)FF_N; i += FF_THREADS) {
-        S.tw[i] = P.tw[i];
-        S.itw[i] = P.itw[i];
+        stw[i] = P.tw[i];
+        stw[FF_N + i] = P.itw[i];
     }
+#endif
     auto run = [&](auto phase) {
         phase(tid);
         __syncthreads();

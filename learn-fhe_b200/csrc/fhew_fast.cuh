@@ -45,10 +45,16 @@ struct FhewFastDev {
 struct FhewFastSmem {
     uint32_t* acc;
     uint32_t* dig;
-    TwPair<uint32_t>* tw;
-    TwPair<uint32_t>* itw;
+    const TwPair<uint32_t>* tw;
+    const TwPair<uint32_t>* itw;
 };
-HD constexpr size_t ff_fixed_words() { return (size_t)2 * FF_N + 8 * FF_N + 4 * FF_N; }
+// FF_TW_NC = 1: twiddle tables stay in global memory and are read through the read-only L1 path (8 KB less shared memory
+// per CTA); 0: copied into shared memory by every CTA
+#ifndef FF_TW_NC
+#define FF_TW_NC 0
+#endif
+HD constexpr size_t ff_fixed_words() { return (size_t)2 * FF_N + 8 * FF_N + (FF_TW_NC ? 0 : 4 * FF_N); }
+HD TwPair<uint32_t> ff_tw(const TwPair<uint32_t>* p) { return FF_TW_NC ? ld_tw(p) : *p; }
 
 // swizzle of the digit polynomials: bits 5,6,7 -> 2,3,4 and bit 8 -> 2 (the radix-16 pass at stride 4 needs bit 8)
 HD uint32_t swzf(uint32_t p) { return p ^ ((p >> 3) & 0x1Cu) ^ ((p >> 6) & 4u); }
@@ -117,7 +123,7 @@ HD void ff_p1(const FhewFastDev& P, const FhewFastSmem& S, const DecompParam& dp
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = ff_dec_step(P, dp, st[j]);
         if (k >= lo && k < hi) {
-            fast_fwd_regs<Lz32, 3, false>(P.m, x, S.tw, 1u);
+            fast_fwd_regs<Lz32, 3, FF_TW_NC != 0>(P.m, x, S.tw, 1u);
             uint32_t* d = S.dig + ((pbase + k) << FF_LOGN);
 #pragma unroll
             for (int j = 0; j < 8; ++j) d[P0 ^ swzf((uint32_t)j << 6)] = x[j];
@@ -132,7 +138,7 @@ HD void ff_p2(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32
     uint32_t x[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) x[j] = d[P0 ^ swzf((uint32_t)j << 2)];
-    fast_fwd_regs<Lz32, 4, false>(P.m, x, S.tw, 8u + hi);
+    fast_fwd_regs<Lz32, 4, FF_TW_NC != 0>(P.m, x, S.tw, 8u + hi);
 #pragma unroll
     for (int j = 0; j < 16; ++j) d[P0 ^ swzf((uint32_t)j << 2)] = x[j];
 }
@@ -162,7 +168,7 @@ HD uint4 ff_ldg4(const uint4* p) {
 HD void ff_p3(const FhewFastDev& P, const FhewFastSmem& S, const uint4* __restrict__ key /* [rows][128][2] */, uint32_t rows, uint32_t t) {
     const uint32_t P0 = swzf(t << 2);
     uint64_t sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-    const TwPair<uint32_t> t0 = S.tw[128u + t], t1 = S.tw[256u + 2u * t], t2 = S.tw[257u + 2u * t];
+    const TwPair<uint32_t> t0 = ff_tw(S.tw + 128u + t), t1 = ff_tw(S.tw + 256u + 2u * t), t2 = ff_tw(S.tw + 257u + 2u * t);
 #pragma unroll 4
     for (uint32_t k = 0; k < rows; ++k) {
         uint32_t x[4];
@@ -183,7 +189,7 @@ HD void ff_p3(const FhewFastDev& P, const FhewFastSmem& S, const uint4* __restri
         y[i] = ff_reduce64(P, sa[i]);
         y[4 + i] = ff_reduce64(P, sb[i]);
     }
-    const TwPair<uint32_t> i0 = S.itw[128u + t], i1 = S.itw[256u + 2u * t], i2 = S.itw[257u + 2u * t];
+    const TwPair<uint32_t> i0 = ff_tw(S.itw + 128u + t), i1 = ff_tw(S.itw + 256u + 2u * t), i2 = ff_tw(S.itw + 257u + 2u * t);
 #pragma unroll
     for (int o = 0; o < 8; o += 4) {  // first inverse radix-4 pass (stages 8, 7) of a then b
         P.m.bf_inv(y[o + 0], y[o + 1], i1, 0);
@@ -202,7 +208,7 @@ HD void ff_p4(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32
     uint32_t x[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) x[j] = d[P0 ^ swzf((uint32_t)j << 2)];
-    fast_inv_regs<Lz32, 4, false, false>(P.m, x, S.itw, 8u + hi, P.ninv, P.wninv);
+    fast_inv_regs<Lz32, 4, false, FF_TW_NC != 0>(P.m, x, S.itw, 8u + hi, P.ninv, P.wninv);
 #pragma unroll
     for (int j = 0; j < 16; ++j) d[P0 ^ swzf((uint32_t)j << 2)] = x[j];
 }
@@ -214,7 +220,7 @@ HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, ui
     uint32_t x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = d[P0 ^ swzf((uint32_t)j << 6)];
-    fast_inv_regs<Lz32, 3, true, false>(P.m, x, S.itw, 1u, P.ninv, P.wninv);
+    fast_inv_regs<Lz32, 3, true, FF_TW_NC != 0>(P.m, x, S.itw, 1u, P.ninv, P.wninv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         uint32_t v = P.m.inv_canon(x[j]);

@@ -1,8 +1,12 @@
 #!/usr/bin/env python
 """Condense an .ncu-rep (ncu --set full) into the per-launch CSV kept under profiles/: duration, DRAM traffic, pipe and
 issue utilisation, occupancy limiters, shared-memory conflicts, top stall reasons.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_ncu_<what>.csv"""
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--traffic KERNEL_SUBSTRING=UNITS] > profiles/rNN_ncu_<what>.csv
+--traffic also records dram read + write bytes of the first matching launch (which processed UNITS work items) in
+profiles/ncu_traffic.json, where bench.py picks up `roofline.traffic`."""
 import csv
+import json
+import os
 import subprocess
 import sys
 
@@ -29,6 +33,19 @@ def main():
     col = {h: i for i, h in enumerate(hdr)}
     w = csv.writer(sys.stdout)
     w.writerow(["kernel", "block", "grid"] + ["%s [%s]" % (k, units[col[m]]) if m in col else k for k, m in KEYS] + ["top_stalls"])
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for a in [x.split("=") for i, x in enumerate(sys.argv) if i > 0 and sys.argv[i - 1] == "--traffic"]:
+        for r in rows[2:]:
+            if a[0] in r[col["Kernel Name"]]:
+                b = sum(float(r[col[m]]) * scale[units[col[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+                if "--traffic-out" in sys.argv:
+                    path = sys.argv[sys.argv.index("--traffic-out") + 1]
+                d = json.load(open(path)) if os.path.exists(path) else {}
+                d[a[0]] = {"units": int(a[1]), "dram_bytes": int(b), "duration_ms_under_ncu": float(r[col["gpu__time_duration.sum"]]) * {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}[units[col["gpu__time_duration.sum"]]],
+                           "source": os.path.basename(rep)}
+                json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+                break
     for r in rows[2:]:
         st = [(h.replace("smsp__pcsamp_warps_issue_stalled_", ""), float(r[i])) for i, h in enumerate(hdr)
               if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued") and r[i] not in ("", "0")]

@@ -1,0 +1,34 @@
+#!/bin/bash
+# One-GPU profiling pass (run under gpurun): each command first runs plain (must exit 0), then under ncu.
+#   gpurun_out/prof_<what>_full.ncu-rep : ncu --set full captures of full-size launches (read with tools/ncu_summary.py)
+#   gpurun_out/launches_bench.csv       : launch list of the bench command (gpu__time_duration only)
+# usage: bash tools/profile_all.sh <tag> [what...]   what in {fhew, ntt, tfhe, ckks, launches}; default all
+set -u
+TAG=${1:-rXX}; shift || true
+WHAT=${*:-fhew ntt tfhe ckks launches}
+OUT=gpurun_out
+mkdir -p $OUT
+NCU="ncu --set full --clock-control none --import-source on -f"
+run() { # name, kernel regex, launch count, command...
+    local name=$1 re=$2 cnt=$3; shift 3
+    "$@" > $OUT/plain_${name}.log 2>&1 || { echo "plain run of $name failed"; tail -5 $OUT/plain_${name}.log; return 1; }
+    $NCU -k regex:$re -c $cnt -o $OUT/prof_${name}_${TAG} "$@" > $OUT/ncu_${name}.log 2>&1 || { echo "ncu run of $name failed"; tail -5 $OUT/ncu_${name}.log; return 1; }
+    python tools/ncu_summary.py $OUT/prof_${name}_${TAG}.ncu-rep ${TRAFFIC:+--traffic $TRAFFIC --traffic-out $OUT/ncu_traffic.json} > $OUT/sum_${name}_${TAG}.csv
+    # per-source-line attribution of the first captured launch (needs -lineinfo + --import-source)
+    ncu -i $OUT/prof_${name}_${TAG}.ncu-rep --page source --csv --print-source cuda,sass --launch-count 1 > $OUT/src_${name}_${TAG}.csv 2>/dev/null
+    gzip -f $OUT/src_${name}_${TAG}.csv
+    [ "${KEEP:-0}" = 1 ] || rm -f $OUT/prof_${name}_${TAG}.ncu-rep   # gpurun copies back at most 64 MiB
+    echo "$name: ok"
+}
+for w in $WHAT; do
+    case $w in
+        fhew) TRAFFIC=fhew_blind_rotate_fast_kernel=16384 KEEP=1 run fhew fhew_blind_rotate_fast 1 python tools/prof_cmd.py fhew --batch 16384 ;;
+        ntt) TRAFFIC= run ntt ntt_fast 12 python tools/prof_cmd.py ntt ;;
+        tfhe) TRAFFIC=tfhe_blind_rotate_kernel=16384 KEEP=1 run tfhe tfhe_blind_rotate 1 python tools/tfhe_bench.py tfhe --batch 16384 ;;
+        ckks) TRAFFIC= run ckks 'rns_|ckks_' 8 python tools/tfhe_bench.py ckks --count 128 ;;
+        launches)
+            python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/plain_bench.log 2>&1 || { echo "plain bench failed"; continue; }
+            ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_bench_${TAG}.csv \
+                python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_bench.log 2>&1 && echo "launches: ok" ;;
+    esac
+done
