@@ -198,9 +198,16 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINB) fhew_blind_rotate_fast_ke
         stw[FF_N + i] = P.itw[i];
     }
 #endif
-    auto run = [&](auto phase) {
+    // 64-thread barriers (ids 1, 2) where only the threads of one half exchange data (fhew_fast.cuh, ff_step)
+    auto run = [&](auto phase, int scope) {
         phase(tid);
-        __syncthreads();
+        if (scope == FF_SYNC_FULL)
+            __syncthreads();
+        else
+            if (tid < 64u)
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+            else
+                asm volatile("bar.sync 2, 64;" ::: "memory");
     };
     for (unsigned long long ct = blockIdx.x; ct < count; ct += gridDim.x) {
         const uint32_t* src = ct2n + ct * (P.n_s + 1);
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINB) fhew_blind_rotate_fast_ke
             if (tid == 0) atomicExch(err, 1);
             ns = 0;
         }
-        for (uint32_t s = 0; s < ns; ++s) ff_step(P, S, steps[s], run);
+        for (uint32_t s = 0; s < ns; ++s) ff_step(P, S, steps[s], s + 1 == ns || ff_step_is_auto(steps[s + 1]), run);
         const uint32_t* acc = S.acc;
         if (mode == 0) {
             ff_extract(P, acc, post_add, out + ct * (FF_N + 1), tid);

@@ -53,6 +53,8 @@ struct FhewFastSmem {
 #ifndef FF_TW_NC
 #define FF_TW_NC 0
 #endif
+// digit slot that receives the b half of a step's result (the a half goes to slot 0); see ff_step
+static constexpr uint32_t FF_RB = 4;
 HD constexpr size_t ff_fixed_words() { return (size_t)2 * FF_N + 8 * FF_N + (FF_TW_NC ? 0 : 4 * FF_N); }
 HD TwPair<uint32_t> ff_tw(const TwPair<uint32_t>* p) { return FF_TW_NC ? ld_tw(p) : *p; }
 
@@ -198,9 +200,9 @@ HD void ff_p3(const FhewFastDev& P, const FhewFastSmem& S, const uint4* __restri
         P.m.bf_inv(y[o + 1], y[o + 3], i0, 1);
     }
     ff_st4(S.dig, P0, y);
-    ff_st4(S.dig + FF_N, P0, y + 4);
+    ff_st4(S.dig + FF_RB * FF_N, P0, y + 4);
 }
-// ---- P4: inverse radix-16 pass (stages 6..3) on result polynomial `poly` (0 = a, 1 = b) ---------------------------------------------
+// ---- P4: inverse radix-16 pass (stages 6..3) on the result polynomial in digit slot `poly` (0: a, FF_RB: b) -----------------------
 HD void ff_p4(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32_t grp) {
     const uint32_t lo = grp & 3u, hi = grp >> 2;
     const uint32_t P0 = swzf((hi << 6) | lo);
@@ -216,7 +218,7 @@ HD void ff_p4(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32
 template <typename Add>
 HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, uint32_t g, uint32_t h, bool do_add, Add add) {
     const uint32_t P0 = swzf(g);
-    const uint32_t* d = S.dig + (h << FF_LOGN);
+    const uint32_t* d = S.dig + ((h * FF_RB) << FF_LOGN);
     uint32_t x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = d[P0 ^ swzf((uint32_t)j << 6)];
@@ -232,40 +234,84 @@ HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, ui
     }
 }
 
-// One full step on the accumulator S.acc (updated in place).
-// run(phase): phase(tid) for every thread of the CTA followed by a barrier.
-template <typename Run>
-HD void ff_step(const FhewFastDev& P, const FhewFastSmem& S, uint32_t step, Run run) {
-    const bool is_auto = (step & FHEW_STEP_AUTO) != 0;
+// One step on the accumulator S.acc (updated in place) as five phases.  Threads 0..63 form half 0, threads 64..127 half 1.
+// Data flow between the halves (what lets most barriers be 64-thread barriers, so the halves can drift apart):
+//   P1 (ext)  half h decomposes acc[h] into digit slots [h d, (h+1) d)            reads acc[h]            (own half)
+//   P1 (auto) half h transforms its share [lo_h, hi_h) of the digits of a(X^t)    reads acc[0], acc[1]    (BOTH halves: full barrier before)
+//   P2        half h runs the radix-16 pass on the slots it wrote in P1                                   (own half)
+//   P3        every thread needs every slot at its four evaluation points; results a -> slot 0, b -> slot FF_RB   (full barrier before and after)
+//   P4, P5    half h finishes result slot h FF_RB and writes acc[h]                                        (own half)
+// Slot 0 lies in half 0's P1/P2 range and slot FF_RB = 4 in half 1's for an external product with d = 4; for the narrower
+// cases (d < 4, automorphisms) half 1's slots start below 4 and slot 4 is free, so a half never touches a slot the other
+// half may still be reading.  dig[7] (the parked b(X^t)) is written and read by half 1 only.
+enum : int { FF_SYNC_HALF = 0, FF_SYNC_FULL = 1 };
+struct FfStep {
+    bool is_auto;
+    uint32_t d, rows, tinv;
+    const uint4* key;
+};
+HD FfStep ff_decode(const FhewFastDev& P, uint32_t step) {
+    FfStep s;
+    s.is_auto = (step & FHEW_STEP_AUTO) != 0;
     const uint32_t idx = step & 0x7FFFu;
-    const uint32_t* acc_in = S.acc;
-    uint32_t* acc_out = S.acc;
-    const DecompParam& dp = is_auto ? P.r_dec : P.g_dec;
-    const uint32_t d = dp.d, rows = is_auto ? d : 2 * d;
-    const uint4* key = is_auto ? P.ak4 + (size_t)idx * d * FF_THREADS * 2 : P.brk4 + (size_t)idx * (2 * d) * FF_THREADS * 2;
-    const uint32_t tinv = is_auto ? P.ak_tinv[idx] : 0;
-    // external product: digits of acc.a -> polynomials [0, d), digits of acc.b -> [d, 2d)   (rgsw.rs:122-124)
-    // automorphism:     digits of a(X^t) -> polynomials [0, d); half h transforms digits [h * ceil(d/2), ...)   (rlwe.rs:182)
-    run([&](uint32_t tid) {
-        const uint32_t g = tid & 63u, h = tid >> 6;
-        const uint32_t half = (d + 1) / 2;
-        const uint32_t lo = is_auto ? h * half : 0u, hi = is_auto ? (h == 0 ? half : d) : d;
-        ff_p1(P, S, dp, acc_in, is_auto, tinv, g, h, lo, hi, is_auto ? 0u : h * d);
-    });
-    run([&](uint32_t tid) {
-#pragma unroll 1
-        for (uint32_t u = tid; u < rows * 32u; u += FF_THREADS) ff_p2(P, S, u >> 5, u & 31u);
-    });
-    run([&](uint32_t tid) { ff_p3(P, S, key, rows, tid); });
-    run([&](uint32_t tid) {
-        if (tid < 64u) ff_p4(P, S, tid >> 5, tid & 31u);
-    });
-    run([&](uint32_t tid) {
-        const uint32_t g = tid & 63u, h = tid >> 6;
-        // key switch adds the (permuted) body: b' = sum ksk.b_k * limb_k + b(X^t)   (rlwe.rs:184)
-        ff_p5(P, S, acc_out, g, h, is_auto && h == 1, [&](int j) { return S.dig[7 * FF_N + g + 64u * j]; });
-    });
+    s.d = s.is_auto ? P.r_dec.d : P.g_dec.d;
+    s.rows = s.is_auto ? s.d : 2 * s.d;
+    s.key = s.is_auto ? P.ak4 + (size_t)idx * s.d * FF_THREADS * 2 : P.brk4 + (size_t)idx * (2 * s.d) * FF_THREADS * 2;
+    s.tinv = s.is_auto ? P.ak_tinv[idx] : 0;
+    return s;
 }
+// digit slots half h owns in P1 / P2
+HD void ff_half_slots(const FfStep& s, uint32_t h, uint32_t& lo, uint32_t& hi) {
+    if (s.is_auto) {
+        const uint32_t half = (s.d + 1) / 2;
+        lo = h * half;
+        hi = h == 0 ? half : s.d;
+    } else {
+        lo = h * s.d;
+        hi = lo + s.d;
+    }
+}
+// external product: digits of acc.a -> slots [0, d), digits of acc.b -> [d, 2d)   (rgsw.rs:122-124)
+// automorphism:     digits of a(X^t) -> slots [0, d), split between the halves    (rlwe.rs:182)
+HD void ff_phase1(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) {
+    const uint32_t g = tid & 63u, h = tid >> 6;
+    uint32_t lo, hi;
+    ff_half_slots(s, h, lo, hi);
+    const DecompParam& dp = s.is_auto ? P.r_dec : P.g_dec;
+    if (s.is_auto)
+        ff_p1(P, S, dp, S.acc, true, s.tinv, g, h, lo, hi, 0u);
+    else
+        ff_p1(P, S, dp, S.acc, false, 0u, g, h, 0u, s.d, lo);
+}
+HD void ff_phase2(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) {
+    const uint32_t l = tid & 63u, h = tid >> 6;
+    uint32_t lo, hi;
+    ff_half_slots(s, h, lo, hi);
+#pragma unroll 1
+    for (uint32_t u = l; u < (hi - lo) * 32u; u += 64u) ff_p2(P, S, lo + (u >> 5), u & 31u);
+}
+HD void ff_phase3(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) { ff_p3(P, S, s.key, s.rows, tid); }
+HD void ff_phase4(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) {
+    if ((tid & 32u) == 0) ff_p4(P, S, (tid >> 6) * FF_RB, tid & 31u);  // first warp of each half
+}
+HD void ff_phase5(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) {
+    const uint32_t g = tid & 63u, h = tid >> 6;
+    // key switch adds the (permuted) body: b' = sum ksk.b_k * limb_k + b(X^t)   (rlwe.rs:184)
+    ff_p5(P, S, S.acc, g, h, s.is_auto && h == 1, [&](int j) { return S.dig[7 * FF_N + g + 64u * j]; });
+}
+// run(phase, scope): phase(tid) for every thread of the CTA, then a barrier of the given scope.  `first` = no earlier step
+// of this blind rotation (the caller has just executed a full barrier); `next_full` = the barrier after P5 must be a full
+// one (the next step is an automorphism, or there is no next step).
+template <typename Run>
+HD void ff_step(const FhewFastDev& P, const FhewFastSmem& S, uint32_t step, bool next_full, Run run) {
+    const FfStep s = ff_decode(P, step);
+    run([&](uint32_t tid) { ff_phase1(P, S, s, tid); }, FF_SYNC_HALF);
+    run([&](uint32_t tid) { ff_phase2(P, S, s, tid); }, FF_SYNC_FULL);
+    run([&](uint32_t tid) { ff_phase3(P, S, s, tid); }, FF_SYNC_FULL);
+    run([&](uint32_t tid) { ff_phase4(P, S, s, tid); }, FF_SYNC_HALF);
+    run([&](uint32_t tid) { ff_phase5(P, S, s, tid); }, next_full ? FF_SYNC_FULL : FF_SYNC_HALF);
+}
+HD bool ff_step_is_auto(uint32_t step) { return (step & FHEW_STEP_AUTO) != 0; }
 
 // acc init (bootstrapping.rs:158-169): acc = (0, f(X^-g) * X^(b*g))
 template <typename FT>

@@ -300,4 +300,10 @@ def test_kernel_logic_fhew_fast(H, orc, fhew_setup):
         assert H.sim_fhew_fast_blind_rotate_extract(h, f, pro[i], q8, o, a) == 0
         assert (a.reshape(2, -1) == K.blind_rotate(f, pro[i])).all()
         assert (o == ref[i]).all()
+        # the kernel's 64-thread barriers: either half may run ahead of the other between two full barriers
+        H.sim_fhew_fast_blind_rotate_extract_drift.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u64p, C.c_int]
+        for drift in (1, 2):
+            o2 = np.zeros(P.n + 1, dtype=np.uint64)
+            assert H.sim_fhew_fast_blind_rotate_extract_drift(h, f, pro[i], q8, o2, drift) == 0
+            assert (o2 == ref[i]).all(), drift
     H.sim_fhew_key_free(h)
