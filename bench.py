@@ -49,12 +49,19 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []  # (host monotonic time, csv line)
+        self.t0 = self.t1 = None
+
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -62,7 +69,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.monotonic(), ln.strip()))
 
     def stop(self):
         if not self.proc:
@@ -72,8 +79,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        # the sampler runs from before the warm-up (nvidia-smi needs ~0.1 s to start); only samples taken between begin()
+        # and end() - the timed region - are used, unless the region was too short to catch any
+        inside = [ln for t, ln in self.lines if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1]
+        note = None
+        if not inside:
+            inside = [ln for _, ln in self.lines]
+            note = "timed region shorter than the sampling period: samples include the warm-up steps of the same workload"
         sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -88,8 +102,11 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(pw) if pw else None,
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def synth_fhew_key(param, seed):
@@ -424,12 +441,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler.begin()
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ker_evs = []
@@ -438,6 +456,7 @@ def main():
         step(i)
     e1.record(stream)
     barrier()
+    sampler.end()
     launches = ctx.launches - l0
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
