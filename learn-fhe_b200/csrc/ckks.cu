@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) rns_copy_limbs_kernel(int log_n, unsigned
     }
 }
 // rescale_k: in [B][l+k][n] (+ pre [B][l+k][n]) -> out [B][l][n] (+ post [B][l][n]; if post_even_only only for even b)
-__global__ void __launch_bounds__(256) rns_rescale_kernel(const __grid_constant__ RescaleTabV R, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
+__global__ void __launch_bounds__(256, 3) rns_rescale_kernel(const __grid_constant__ RescaleTabV R, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
                                                           const uint64_t* __restrict__ pre, const uint64_t* __restrict__ post, int post_even_only,
                                                           uint64_t* __restrict__ out) {
     const unsigned long long total = batch << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;

@@ -17,7 +17,11 @@ static constexpr int RNS_MAXL = 16;  // max source limbs of one base conversion 
 // strides RNS_MAXL / RNS_MAXL + 1.
 struct RnsExtTab {
     int nq, np;
-    int lazy;                  // 1: every p_k < 2^58, so nq <= 16 lazy Shoup products ([0, 4 p_k) each) sum below 2^64
+    int lazy;                  // 2: every p_k in [2^33, 2^59): exact 128-bit sum of the nq <= 16 products, reduced once (c64, m32)
+                               // 1: every p_k < 2^58, so nq <= 16 lazy Shoup products ([0, 4 p_k) each) sum below 2^64
+    const uint64_t* c64;       // [np] 2^64 mod p_k, Shoup companion in c64_sh; m32 = floor(2^64 / p_k) (< 2^31)
+    const uint64_t* c64_sh;
+    const uint64_t* m32;
     const Mod64* mq;           // [nq]
     const uint64_t* qhat_inv;  // [nq]  (Q/q_i)^-1 mod q_i, with Shoup companion in qhat_inv_sh
     const uint64_t* qhat_inv_sh;
@@ -36,6 +40,7 @@ struct RnsExtTabV {
     Mod64 mp[RNS_MAXL];
     uint64_t qhat_ps[RNS_MAXL * RNS_MAXL], qhat_ps_sh[RNS_MAXL * RNS_MAXL];
     uint64_t uq_ps[RNS_MAXL * (RNS_MAXL + 1)];
+    uint64_t c64[RNS_MAXL], c64_sh[RNS_MAXL], m32[RNS_MAXL];
 };
 
 // rescale_k (rns.rs:99-132) over moduli kept (l) ++ dropped (k)
@@ -103,7 +108,26 @@ HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq
         const Mod64 m = T.mp[k];
         const uint64_t* qh = T.qhat_ps + (size_t)k * RNS_MAXL;
         uint64_t s = 0;
-        if (T.lazy) {
+        if (T.lazy == 2) {
+            // sum_i qhat_i * v_i < 16 * 2^59 * 2^64 < 2^128 accumulated exactly (4 wide products per term instead of the 9
+            // of a Shoup product), then hi * 2^64 + lo reduced once: hi by a lazy Shoup product with c64 = 2^64 mod p
+            // ([0, 4p)), lo by a one-multiply Barrett on its top 32 bits ([0, 3p) for p >= 2^33: the quotient estimate
+            // floor(floor(lo / 2^32) * m32 / 2^32) is floor(lo / p) - {0, 1, 2}).  Same canonical value as the reference's
+            // per-term canonical Zq arithmetic.
+            unsigned __int128 acc = 0;
+#pragma unroll
+            for (int i = 0; i < RNS_MAXL; ++i) {
+                if (i >= T.nq) break;
+                acc += (unsigned __int128)qh[i] * v[i];
+            }
+            const uint64_t hi = (uint64_t)(acc >> 64), lo = (uint64_t)acc;
+            const uint64_t r1 = T.c64[k] * hi - mulhi_u64_approx(T.c64_sh[k], hi) * m.q;
+            const uint64_t r0 = lo - (uint64_t)mulhi_u32((uint32_t)(lo >> 32), (uint32_t)T.m32[k]) * m.q;
+            s = r1 + r0;  // < 7p < 2^62
+            s = umin_(s, s - 4 * m.q);
+            s = umin_(s, s - m.q2);
+            s = umin_(s, s - m.q);
+        } else if (T.lazy) {
             // constant * variable products by Shoup (valid for ANY 64-bit v, so v_i needs no reduction mod p_k first); the
             // canonical value of the sum is what the reference's per-term canonical Zq arithmetic yields
             const uint64_t* qs = T.qhat_ps_sh + (size_t)k * RNS_MAXL;
@@ -143,6 +167,7 @@ HD void rns_rescale_coeff(const Tab& R, Load x, Emit emit) {
         uint64_t xs[RNS_MAXL];
 #pragma unroll
         for (int j = 0; j < RNS_MAXL; ++j) xs[j] = j < k ? rounded(l + j) : 0;
+        // (loading the kept limbs up front and unrolling the target loop was measured: more registers, lower occupancy, slower)
         rns_extend_coeff(R.ext, xs, [&](int i, uint64_t y) { finish(i, y); });
     }
 }

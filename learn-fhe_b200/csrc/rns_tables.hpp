@@ -2,6 +2,7 @@
 // constants of rescale_k, rns.rs:120-132).  The reference computes them with BigUint; they are mathematically determined
 // residues, computed here with 128-bit modular arithmetic only.  Shared by ckks.cu and tests/hostsim.
 #pragma once
+#include <cstdlib>
 #include <cstdint>
 #include <vector>
 
@@ -45,7 +46,7 @@ inline uint64_t host_inv_any(uint64_t a, uint64_t q) {  // extended Euclid: q ne
 
 struct RnsExtHost {
     std::vector<Mod64> mq, mp;
-    std::vector<uint64_t> qhat_inv, qhat_inv_sh, qhat_ps, qhat_ps_sh, uq_ps;
+    std::vector<uint64_t> qhat_inv, qhat_inv_sh, qhat_ps, qhat_ps_sh, uq_ps, c64, c64_sh, m32;
     int lazy = 1;
     std::vector<double> frac;
     void build(const std::vector<uint64_t>& qs, const std::vector<uint64_t>& ps) {
@@ -58,6 +59,10 @@ struct RnsExtHost {
         qhat_ps.assign(np * RNS_MAXL, 0);
         qhat_ps_sh.assign(np * RNS_MAXL, 0);
         lazy = nq <= 16 ? 1 : 0;
+        bool wide = nq <= 16;
+        c64.assign(np, 0);
+        c64_sh.assign(np, 0);
+        m32.assign(np, 0);
         uq_ps.assign(np * (RNS_MAXL + 1), 0);
         for (size_t i = 0; i < nq; ++i) {
             mq[i] = host_make_mod64(qs[i]);
@@ -68,6 +73,10 @@ struct RnsExtHost {
         for (size_t k = 0; k < np; ++k) {
             mp[k] = host_make_mod64(ps[k]);
             if (ps[k] >= (1ull << 58)) lazy = 0;
+            if (ps[k] < (1ull << 33) || ps[k] >= (1ull << 59)) wide = false;
+            c64[k] = (uint64_t)((((u128_t)1) << 64) % ps[k]);
+            c64_sh[k] = host_shoup64(c64[k], ps[k]);
+            m32[k] = (uint64_t)((((u128_t)1) << 64) / ps[k]);
             for (size_t i = 0; i < nq; ++i) {
                 qhat_ps[k * RNS_MAXL + i] = host_prod_mod(qs, ps[k], i);
                 qhat_ps_sh[k * RNS_MAXL + i] = host_shoup64(qhat_ps[k * RNS_MAXL + i], ps[k]);
@@ -75,6 +84,7 @@ struct RnsExtHost {
             const uint64_t qmod = host_prod_mod(qs, ps[k]);
             for (size_t u = 0; u <= nq; ++u) uq_ps[k * (RNS_MAXL + 1) + u] = host_mulmod(u % ps[k], qmod, ps[k]);
         }
+        if (wide && getenv("FHE_B200_RNS_NO_WIDE") == nullptr) lazy = 2;
     }
     // by-value form (kernel parameter); requires nq, np <= RNS_MAXL
     void fill(RnsExtTabV& t) const {
@@ -88,7 +98,12 @@ struct RnsExtHost {
             t.qhat_inv_sh[i] = qhat_inv_sh[i];
             t.frac[i] = frac[i];
         }
-        for (size_t k = 0; k < mp.size(); ++k) t.mp[k] = mp[k];
+        for (size_t k = 0; k < mp.size(); ++k) {
+            t.mp[k] = mp[k];
+            t.c64[k] = c64[k];
+            t.c64_sh[k] = c64_sh[k];
+            t.m32[k] = m32[k];
+        }
         for (size_t i = 0; i < qhat_ps.size(); ++i) {
             t.qhat_ps[i] = qhat_ps[i];
             t.qhat_ps_sh[i] = qhat_ps_sh[i];
@@ -107,6 +122,9 @@ struct RnsExtHost {
         t.qhat_ps = qhat_ps.data();
         t.qhat_ps_sh = qhat_ps_sh.data();
         t.lazy = lazy;
+        t.c64 = c64.data();
+        t.c64_sh = c64_sh.data();
+        t.m32 = m32.data();
         t.uq_ps = uq_ps.data();
         return t;
     }

@@ -205,6 +205,20 @@ def test_kernel_logic_rns(H, orc):
         out = np.zeros((nq - k, n), dtype=np.uint64)
         assert H.sim_rns_rescale(U(qs), nq, k, x.reshape(-1), out.reshape(-1), n) == 0
         assert (out == orc.rns_rescale_k(qs, k, x)).all(), (nq, k)
+    # the three accumulation modes of rns_extend_coeff at the largest fan-in (16 source limbs, all residues q_i - 1):
+    # exact 128-bit sum (targets in [2^33, 2^59), incl. primes just below 2^59), lazy Shoup sum (forced), canonical (61-bit)
+    big = orc.two_adic_primes(59, 8, 16)
+    for targets, env in ((orc.two_adic_primes(59, 8, 18)[16:], None), (primes[:2], "1"), (orc.two_adic_primes(61, 8, 2), None)):
+        x = np.stack([orc.residues(500 + i, n, q) for i, q in enumerate(big)])
+        x[:, :8] = np.array([[q - 1] * 8 for q in big], dtype=np.uint64)
+        out = np.zeros((2, n), dtype=np.uint64)
+        if env:
+            os.environ["FHE_B200_RNS_NO_WIDE"] = env
+        try:
+            assert H.sim_rns_extend(U(big), 16, U(targets), 2, x.reshape(-1), out.reshape(-1), n) == 0
+        finally:
+            os.environ.pop("FHE_B200_RNS_NO_WIDE", None)
+        assert (out == orc.rns_extend_bases(big, targets, x)[16:]).all(), targets
     # mixed-width moduli (source residues larger than the target modulus)
     qs, ps = orc.two_adic_primes(55, 8, 3), orc.two_adic_primes(30, 8, 2) + orc.two_adic_primes(40, 8, 1)
     x = np.stack([orc.residues(99 + i, n, q) for i, q in enumerate(qs)])
