@@ -134,7 +134,8 @@ fhe_status fhe_rns_rescale_k(fhe_ctx* ctx, const uint64_t* qs, size_t nq, size_t
 /* ---- FHEW / LMKCDEY (scheme/fhew/src/{lwe,rlwe,rgsw,bootstrapping,fhew}.rs) ------------------------------------- */
 typedef struct fhe_fhew_param {
     unsigned log_n;      /* ring degree N = 2^log_n                                   (rlwe.rs:13-20)       */
-    uint64_t big_q;      /* RLWE/RGSW modulus Q, prime < 2^30, Q = 1 mod 2N           (boolean.rs:225-239)  */
+    uint64_t big_q;      /* RLWE/RGSW modulus Q, prime, Q = 1 mod 2N: < 2^30 (boolean.rs:225-239; 32-bit kernels, fused fast path at
+                          * N = 512) or < 2^62 (examples/multi_key_uint8.rs:15-29: 55 bits, N = 2048, d = 5; 64-bit generic kernels) */
     uint64_t p;          /* plaintext modulus                                                             */
     unsigned rlwe_log_b, rlwe_d;   /* RLWE key-switch decomposor (automorphism keys)  (rlwe.rs:17-19)       */
     unsigned rgsw_log_b, rgsw_d;   /* RGSW decomposor                                 (rgsw.rs:18-27)       */

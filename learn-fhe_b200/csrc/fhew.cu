@@ -18,7 +18,9 @@
 
 struct fhe_fhew_key {
     fhe_fhew_param param;
-    fhe::FhewDev P;
+    fhe::FhewDev P;                      // Q < 2^30; its scalar fields (log_n, n_s, w, decomposors, ak_t) are always filled
+    fhe::FhewDevT<fhe::Mod64> P64;       // wide: 2^30 <= Q < 2^62 (examples/multi_key_uint8.rs: 55-bit Q, N = 2048, d = 5)
+    bool wide = false;
     fhe::LweKsDev K;
     uint32_t kmax = 0;
     void* d_brk = nullptr;
@@ -37,17 +39,19 @@ struct fhe_fhew_key {
 namespace fhe {
 
 static constexpr int BR_THREADS = 128;
+static constexpr int BR_THREADS_WIDE = 512;
 static constexpr int PRO_G = 4;
 static constexpr int PRO_THREADS = 128;
 
-__global__ void fhew_pack_rows_kernel(const uint32_t* __restrict__ ab /* [rows][2][N] eval form */, uint2* __restrict__ out, uint32_t n,
+template <typename W>
+__global__ void fhew_pack_rows_kernel(const W* __restrict__ ab /* [rows][2][N] eval form */, KeyPair<W>* __restrict__ out, uint32_t n,
                                       unsigned long long rows) {
     unsigned long long total = rows * n;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long r = i / n;
         uint32_t c = (uint32_t)(i - r * n);
-        out[i] = make_uint2(ab[(r * 2) * n + c], ab[(r * 2 + 1) * n + c]);
+        out[i] = KeyPair<W>{ab[(r * 2) * n + c], ab[(r * 2 + 1) * n + c]};
     }
 }
 
@@ -78,13 +82,16 @@ __global__ void __launch_bounds__(PRO_THREADS) fhew_prologue_kernel(LweKsDev K, 
 }
 
 // mode 0: out = LWE ciphertext [N+1] (sample_extract + post_add); mode 1: out = accumulator [2][N]
-template <typename FT, typename OT>
-__global__ void __launch_bounds__(BR_THREADS) fhew_blind_rotate_kernel(FhewDev P, uint32_t kmax, const FT* __restrict__ f,
-                                                                          const uint32_t* __restrict__ ct2n, uint32_t post_add,
+// NT = threads per CTA the kernel is compiled for: 128 for 32-bit moduli (several CTAs per SM), BR_THREADS_WIDE for 64-bit
+// moduli at N = 2048, where the working set (196 KB) admits one CTA per SM and the CTA itself has to fill it
+template <typename M, typename FT, typename OT, int NT>
+__global__ void __launch_bounds__(NT) fhew_blind_rotate_kernel(FhewDevT<M> P, uint32_t kmax, const FT* __restrict__ f,
+                                                                          const uint32_t* __restrict__ ct2n, typename M::W post_add,
                                                                           unsigned long long count, OT* __restrict__ out, int mode,
                                                                           int* __restrict__ err) {
+    typedef typename M::W W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
+    W* smem = reinterpret_cast<W*>(smem_raw);
     const uint32_t n = 1u << P.log_n;
     uint16_t* steps = reinterpret_cast<uint16_t*>(smem + (size_t)(2 + kmax) * n);
     const uint32_t max_steps = P.n_s + n + 2;
@@ -116,19 +123,20 @@ __global__ void __launch_bounds__(BR_THREADS) fhew_blind_rotate_kernel(FhewDev P
         } else {
             OT* o = out + ct * 2ull * n;
             for (uint32_t i = tid; i < n; i += nthr) {
-                o[i] = (OT)smem[swz<uint32_t>(i)];
-                o[n + i] = (OT)smem[n + swz<uint32_t>(i)];
+                o[i] = (OT)smem[swz<W>(i)];
+                o[n + i] = (OT)smem[n + swz<W>(i)];
             }
         }
         __syncthreads();
     }
 }
 
-template <typename IT, typename OT>
-__global__ void __launch_bounds__(BR_THREADS) fhew_step_kernel(FhewDev P, uint32_t kmax, uint32_t kind_flag, const uint32_t* __restrict__ idx,
+template <typename M, typename IT, typename OT>
+__global__ void __launch_bounds__(BR_THREADS) fhew_step_kernel(FhewDevT<M> P, uint32_t kmax, uint32_t kind_flag, const uint32_t* __restrict__ idx,
                                                                  const IT* __restrict__ acc_in, OT* __restrict__ acc_out, unsigned long long count) {
+    typedef typename M::W W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* smem = reinterpret_cast<uint32_t*>(smem_raw);
+    W* smem = reinterpret_cast<W*>(smem_raw);
     const uint32_t n = 1u << P.log_n;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     auto run = [&](auto phase) {
@@ -138,15 +146,15 @@ __global__ void __launch_bounds__(BR_THREADS) fhew_step_kernel(FhewDev P, uint32
     for (unsigned long long c = blockIdx.x; c < count; c += gridDim.x) {
         const IT* in = acc_in + c * 2ull * n;
         for (uint32_t i = tid; i < n; i += nthr) {
-            smem[swz<uint32_t>(i)] = (uint32_t)in[i];
-            smem[n + swz<uint32_t>(i)] = (uint32_t)in[n + i];
+            smem[swz<W>(i)] = (W)in[i];
+            smem[n + swz<W>(i)] = (W)in[n + i];
         }
         __syncthreads();
         fhew_step(P, smem, kind_flag | idx[c], run);
         OT* o = acc_out + c * 2ull * n;
         for (uint32_t i = tid; i < n; i += nthr) {
-            o[i] = (OT)smem[swz<uint32_t>(i)];
-            o[n + i] = (OT)smem[n + swz<uint32_t>(i)];
+            o[i] = (OT)smem[swz<W>(i)];
+            o[n + i] = (OT)smem[n + swz<W>(i)];
         }
         __syncthreads();
     }
@@ -241,7 +249,7 @@ static size_t br_fast_smem_bytes(const fhe_fhew_key* key) {
 static size_t br_smem_bytes(const fhe_fhew_key* key) {
     const uint32_t n = 1u << key->P.log_n;
     const uint32_t max_steps = key->P.n_s + n + 2;
-    return (size_t)(2 + key->kmax) * n * 4 + (size_t)((max_steps + 1) & ~1u) * 2 + (size_t)(key->P.n_s + 1) * 4 + 16;
+    return (size_t)(2 + key->kmax) * n * (key->wide ? 8 : 4) + (size_t)((max_steps + 1) & ~1u) * 2 + (size_t)(key->P.n_s + 1) * 4 + 16;
 }
 
 template <typename K>
@@ -254,34 +262,44 @@ static fhe_status persistent_grid(fhe_ctx* ctx, K kern, int threads, size_t smem
     return FHE_OK;
 }
 
-static fhe_status upload_rows_eval(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* rows_ab, size_t rows, void** d_out, size_t* bytes) {
+template <typename W>
+static fhe_status upload_rows_eval_t(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* rows_ab, size_t rows, void** d_out, size_t* bytes) {
     const uint32_t n = 1u << key->P.log_n;
     const size_t words = rows * 2 * n;
-    std::vector<uint32_t> h(words);
+    std::vector<W> h(words);
     const uint64_t q = key->param.big_q;
     for (size_t i = 0; i < words; ++i) {
         FHE_REQUIRE(ctx, rows_ab[i] < q, "key coefficient out of range");
-        h[i] = (uint32_t)rows_ab[i];
+        h[i] = (W)rows_ab[i];
     }
-    uint32_t* d_tmp = nullptr;
-    FHE_CUDA(ctx, cudaMalloc(&d_tmp, words * 4));
-    cudaError_t e = cudaMemcpyAsync(d_tmp, h.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream);
+    W* d_tmp = nullptr;
+    FHE_CUDA(ctx, cudaMalloc(&d_tmp, words * sizeof(W)));
+    cudaError_t e = cudaMemcpyAsync(d_tmp, h.data(), words * sizeof(W), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     fhe_status st = e == cudaSuccess ? FHE_OK : fail(ctx, FHE_ECUDA, "key upload: %s", cudaGetErrorString(e));
-    if (st == FHE_OK) st = launch_ntt_u32(ctx, (uint32_t)q, (unsigned)key->P.log_n, rows * 2, d_tmp, true);
     if (st == FHE_OK) {
-        *bytes = rows * n * sizeof(uint2);
+        if (sizeof(W) == 4)
+            st = launch_ntt_u32(ctx, (uint32_t)q, (unsigned)key->P.log_n, rows * 2, (uint32_t*)d_tmp, true);
+        else
+            st = launch_ntt_u64(ctx, q, (unsigned)key->P.log_n, rows * 2, (uint64_t*)d_tmp, true);
+    }
+    if (st == FHE_OK) {
+        *bytes = rows * n * sizeof(KeyPair<W>);
         if (cudaMalloc(d_out, *bytes) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "key alloc");
     }
     if (st == FHE_OK) {
         unsigned long long total = (unsigned long long)rows * n;
         unsigned grid = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)ctx->sm_count * 8);
-        fhew_pack_rows_kernel<<<grid, 256, 0, ctx->stream>>>(d_tmp, (uint2*)*d_out, n, rows);
+        fhew_pack_rows_kernel<W><<<grid, 256, 0, ctx->stream>>>(d_tmp, (KeyPair<W>*)*d_out, n, rows);
         st = after_launch(ctx, "fhew_pack_rows_kernel");
     }
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d_tmp);
     return st;
+}
+static fhe_status upload_rows_eval(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* rows_ab, size_t rows, void** d_out, size_t* bytes) {
+    return key->wide ? upload_rows_eval_t<uint64_t>(ctx, key, rows_ab, rows, d_out, bytes)
+                     : upload_rows_eval_t<uint32_t>(ctx, key, rows_ab, rows, d_out, bytes);
 }
 
 static fhe_status run_prologue(fhe_ctx* ctx, const fhe_fhew_key* key, size_t count, const uint64_t* d_ct_in, bool sw_in, bool sw_out,
@@ -314,29 +332,38 @@ static bool fhew_force_generic() {
 }
 template <typename OT>
 static fhe_status run_blind_rotate_fast(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n,
-                                        uint32_t post_add, size_t count, OT* d_out, int mode, bool reset_err) {
+                                        uint64_t post_add, size_t count, OT* d_out, int mode, bool reset_err) {
     const size_t smem = br_fast_smem_bytes(key);
     auto kern = fhew_blind_rotate_fast_kernel<uint64_t, OT>;
     unsigned grid;
     FHE_CHECK(persistent_grid(ctx, kern, FF_THREADS, smem, count, &grid));
     if (reset_err) FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
-    kern<<<grid, FF_THREADS, smem, ctx->stream>>>(key->F, d_f, d_ct2n, post_add, count, d_out, mode, key->d_err);
+    kern<<<grid, FF_THREADS, smem, ctx->stream>>>(key->F, d_f, d_ct2n, (uint32_t)post_add, count, d_out, mode, key->d_err);
     return after_launch(ctx, "fhew_blind_rotate_kernel");
 }
 static bool fhew_fast_instantiated(unsigned dg, unsigned dr) { return dg >= 1 && dg <= 4 && dr >= 1 && dr <= 4; }
 
 template <typename OT>
-static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n, uint32_t post_add,
+static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* d_f, const uint32_t* d_ct2n, uint64_t post_add,
                                    size_t count, OT* d_out, int mode, bool reset_err = true) {
     if (key->fast && !fhew_force_generic()) {
         return run_blind_rotate_fast<OT>(ctx, key, d_f, d_ct2n, post_add, count, d_out, mode, reset_err);
     }
     const size_t smem = br_smem_bytes(key);
-    auto kern = fhew_blind_rotate_kernel<uint64_t, OT>;
     unsigned grid;
+    if (key->wide) {
+        auto kern = fhew_blind_rotate_kernel<Mod64, uint64_t, OT, BR_THREADS_WIDE>;
+        // small rings leave room for several CTAs per SM: keep 128 threads there
+        const int nt = smem > 64 * 1024 ? BR_THREADS_WIDE : BR_THREADS;
+        FHE_CHECK(persistent_grid(ctx, kern, nt, smem, count, &grid));
+        if (reset_err) FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
+        kern<<<grid, nt, smem, ctx->stream>>>(key->P64, key->kmax, d_f, d_ct2n, post_add, count, d_out, mode, key->d_err);
+        return after_launch(ctx, "fhew_blind_rotate_kernel");
+    }
+    auto kern = fhew_blind_rotate_kernel<Mod32, uint64_t, OT, BR_THREADS>;
     FHE_CHECK(persistent_grid(ctx, kern, BR_THREADS, smem, count, &grid));
     if (reset_err) FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
-    kern<<<grid, BR_THREADS, smem, ctx->stream>>>(key->P, key->kmax, d_f, d_ct2n, post_add, count, d_out, mode, key->d_err);
+    kern<<<grid, BR_THREADS, smem, ctx->stream>>>(key->P, key->kmax, d_f, d_ct2n, (uint32_t)post_add, count, d_out, mode, key->d_err);
     return after_launch(ctx, "fhew_blind_rotate_kernel");
 }
 
@@ -359,8 +386,9 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     if (!ctx || !pp || !out) return FHE_EINVAL;
     *out = nullptr;
     FHE_REQUIRE(ctx, ksk_a && ksk_b && brk && ak && ak_t, "null key pointer");
-    FHE_REQUIRE(ctx, pp->log_n >= 2 && pp->log_n <= 11, "FHEW u32 path supports 4 <= N <= 2048 (got log_n = %u)", pp->log_n);
-    FHE_REQUIRE(ctx, pp->big_q < (1ull << 30), "FHEW u32 path needs Q < 2^30 (54/55-bit multi-key parameters are a later row)");
+    FHE_REQUIRE(ctx, pp->log_n >= 2 && pp->log_n <= 11, "FHEW path supports 4 <= N <= 2048 (got log_n = %u)", pp->log_n);
+    FHE_REQUIRE(ctx, pp->big_q < (1ull << 62), "FHEW path needs Q < 2^62");
+    const bool wide = pp->big_q >= (1ull << 30);  // 64-bit residues (generic kernels only)
     FHE_REQUIRE(ctx, pp->q_ks >= 2 && pp->q_ks <= (1ull << 32) && (pp->q_ks & (pp->q_ks - 1)) == 0, "q_ks must be a power of two <= 2^32");
     FHE_REQUIRE(ctx, pp->w >= 1 && pp->w < 40, "window w must be in [1, 39]");
     FHE_REQUIRE(ctx, pp->rgsw_d >= 1 && pp->rlwe_d >= 1 && pp->ks_d >= 1 && pp->rgsw_log_b >= 1 && pp->rlwe_log_b >= 1 && pp->ks_log_b >= 1,
@@ -371,24 +399,42 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     FHE_REQUIRE(ctx, pp->n_s >= 1 && pp->n_s < 32768, "n_s out of range");
     const uint32_t n = 1u << pp->log_n;
     const NttTable* t;
-    FHE_CHECK(get_ntt_table(ctx, pp->big_q, 32, n, &t));
+    FHE_CHECK(get_ntt_table(ctx, pp->big_q, wide ? 64 : 32, n, &t));
     fhe_fhew_key* key = new fhe_fhew_key();
     key->param = *pp;
+    key->wide = wide;
     const uint64_t q = pp->big_q;
     FhewDev& P = key->P;
-    P.m = make_mod<Mod32>(q);
+    if (!wide) P.m = make_mod<Mod32>(q);
     P.log_n = (int)pp->log_n;
     P.n_s = pp->n_s;
     P.w = pp->w;
     P.g_dec = make_decomp(q, pp->rgsw_log_b, pp->rgsw_d);
     P.r_dec = make_decomp(q, pp->rlwe_log_b, pp->rlwe_d);
     P.small_digits = (pp->rgsw_log_b * pp->rgsw_d <= 32 && pp->rlwe_log_b * pp->rlwe_d <= 32) ? 1 : 0;
-    P.tw = (const TwPair<uint32_t>*)t->d_fwd;
-    P.itw = (const TwPair<uint32_t>*)t->d_inv;
     const uint64_t ninv = host_invmod(n % q, q);
-    P.ninv = make_twpair<uint32_t>(ninv, q);
-    P.wninv = make_twpair<uint32_t>(host_mulmod(t->h_inv[1], ninv, q), q);
+    if (!wide) {
+        P.tw = (const TwPair<uint32_t>*)t->d_fwd;
+        P.itw = (const TwPair<uint32_t>*)t->d_inv;
+        P.ninv = make_twpair<uint32_t>(ninv, q);
+        P.wninv = make_twpair<uint32_t>(host_mulmod(t->h_inv[1], ninv, q), q);
+    }
     for (unsigned v = 0; v <= pp->w; ++v) P.ak_t[v] = (uint32_t)(((ak_t[v] % (int64_t)(2 * n)) + 2 * n) % (2 * n));
+    if (wide) {
+        FhewDevT<Mod64>& W = key->P64;
+        W.m = make_mod<Mod64>(q);
+        W.log_n = P.log_n;
+        W.n_s = P.n_s;
+        W.w = P.w;
+        W.g_dec = P.g_dec;
+        W.r_dec = P.r_dec;
+        W.small_digits = P.small_digits;
+        W.tw = (const TwPair<uint64_t>*)t->d_fwd;
+        W.itw = (const TwPair<uint64_t>*)t->d_inv;
+        W.ninv = make_twpair<uint64_t>(ninv, q);
+        W.wninv = make_twpair<uint64_t>(host_mulmod(t->h_inv[1], ninv, q), q);
+        for (unsigned v = 0; v <= pp->w; ++v) W.ak_t[v] = P.ak_t[v];
+    }
     key->kmax = std::max(2 * pp->rgsw_d, pp->rlwe_d);
     fhe_status st = upload_rows_eval(ctx, key, brk, (size_t)pp->n_s * 2 * pp->rgsw_d, &key->d_brk, &key->brk_bytes);
     if (st == FHE_OK) st = upload_rows_eval(ctx, key, ak, (size_t)(pp->w + 1) * pp->rlwe_d, &key->d_ak, &key->ak_bytes);
@@ -424,11 +470,14 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
         fhe_fhew_key_free(ctx, key);
         return st;
     }
-    P.brk = (const uint2*)key->d_brk;
-    P.ak = (const uint2*)key->d_ak;
+    P.brk = (const KeyPair<uint32_t>*)key->d_brk;
+    P.ak = (const KeyPair<uint32_t>*)key->d_ak;
     P.dlog = (const uint16_t*)key->d_dlog;
+    key->P64.brk = (const KeyPair<uint64_t>*)key->d_brk;
+    key->P64.ak = (const KeyPair<uint64_t>*)key->d_ak;
+    key->P64.dlog = P.dlog;
     // fast path structures
-    if (pp->log_n == FF_LOGN && q < (1ull << 28) && P.small_digits && pp->rgsw_log_b >= 2 && pp->rlwe_log_b >= 2 && pp->rgsw_log_b * pp->rgsw_d <= 30 &&
+    if (!wide && pp->log_n == FF_LOGN && q < (1ull << 28) && P.small_digits && pp->rgsw_log_b >= 2 && pp->rlwe_log_b >= 2 && pp->rgsw_log_b * pp->rgsw_d <= 30 &&
         pp->rlwe_log_b * pp->rlwe_d <= 30 &&
         fhew_fast_instantiated(pp->rgsw_d, pp->rlwe_d)) {
         FhewFastDev& F = key->F;
@@ -507,9 +556,15 @@ static fhe_status fhew_step_api(fhe_ctx* ctx, const fhe_fhew_key* key, uint32_t 
     if (!ctx || !key) return FHE_EINVAL;
     if (count == 0) return FHE_OK;
     const uint32_t n = 1u << key->P.log_n;
-    const size_t smem = (size_t)(2 + key->kmax) * n * 4;
-    auto kern = fhew_step_kernel<uint64_t, uint64_t>;
+    const size_t smem = (size_t)(2 + key->kmax) * n * (key->wide ? 8 : 4);
     unsigned grid;
+    if (key->wide) {
+        auto kern = fhew_step_kernel<Mod64, uint64_t, uint64_t>;
+        FHE_CHECK(persistent_grid(ctx, kern, BR_THREADS, smem, count, &grid));
+        kern<<<grid, BR_THREADS, smem, ctx->stream>>>(key->P64, key->kmax, flag, d_idx, d_acc_in, d_acc_out, count);
+        return after_launch(ctx, "fhew_step_kernel");
+    }
+    auto kern = fhew_step_kernel<Mod32, uint64_t, uint64_t>;
     FHE_CHECK(persistent_grid(ctx, kern, BR_THREADS, smem, count, &grid));
     kern<<<grid, BR_THREADS, smem, ctx->stream>>>(key->P, key->kmax, flag, d_idx, d_acc_in, d_acc_out, count);
     return after_launch(ctx, "fhew_step_kernel");
@@ -551,7 +606,7 @@ fhe_status fhe_fhew_bootstrap_batch(fhe_ctx* ctx, const fhe_fhew_key* key, const
     void* scratch;
     FHE_CHECK(ensure_scratch(ctx, count * (key->P.n_s + 1) * 4, &scratch));
     FHE_CHECK(run_prologue(ctx, key, count, d_ct_in, true, true, (uint32_t*)scratch, nullptr));
-    return run_blind_rotate<uint64_t>(ctx, key, d_f, (const uint32_t*)scratch, (uint32_t)post_add, count, d_ct_out, 0);
+    return run_blind_rotate<uint64_t>(ctx, key, d_f, (const uint32_t*)scratch, post_add, count, d_ct_out, 0);
 }
 
 fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* f, uint64_t post_add, size_t count,
@@ -594,7 +649,7 @@ fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, 
         cu(cudaEventRecord(ev[2 * c], ctx->copy_in), "event");
         cu(cudaStreamWaitEvent(ctx->stream, ev[2 * c], 0), "wait");
         if (st == FHE_OK) st = run_prologue(ctx, key, cnt, dd_in, true, true, sc, nullptr);
-        if (st == FHE_OK) st = run_blind_rotate<uint64_t>(ctx, key, (const uint64_t*)d_f, sc, (uint32_t)post_add, cnt, dd_out, 0, false);
+        if (st == FHE_OK) st = run_blind_rotate<uint64_t>(ctx, key, (const uint64_t*)d_f, sc, post_add, cnt, dd_out, 0, false);
         cu(cudaEventRecord(ev[2 * c + 1], ctx->stream), "event");
         cu(cudaStreamWaitEvent(ctx->copy_out, ev[2 * c + 1], 0), "wait");
         cu(cudaMemcpyAsync(ct_out + off * row, dd_out, cnt * row * 8, cudaMemcpyDeviceToHost, ctx->copy_out), "D2H");

@@ -1,4 +1,4 @@
-// FHEW / LMKCDEY blind-rotation building blocks (u32 path, Q < 2^30), __host__ __device__ so that
+// FHEW / LMKCDEY blind-rotation building blocks (generic path: Mod32 for Q < 2^30, Mod64 above), __host__ __device__ so that
 // tests/hostsim can replay the kernel logic on the CPU.
 //
 // Reference call sites replaced (all under scheme/fhew/src unless noted):
@@ -139,88 +139,105 @@ HD uint32_t build_schedule(uint32_t n, uint32_t n_s, uint32_t w, const AT* a, co
 inline uint32_t max_schedule_steps(uint32_t n, uint32_t n_s) { return n_s + n + 2; }
 
 // ---- per-CTA accumulator steps ---------------------------------------------------------------------------
-struct FhewDev {
-    Mod32 m;
+// M = Mod32 (Q < 2^30, the single-key parameter sets) or Mod64 (Q < 2^62: the 54/55-bit multi-key set of
+// examples/multi_key_uint8.rs:15-29); W = M::W is the word every residue, twiddle and key entry is stored in.
+template <typename W>
+struct alignas(2 * sizeof(W)) KeyPair {
+    W x, y;  // {a, b} of one key row at one evaluation point
+};
+template <typename M>
+struct FhewDevT {
+    typedef typename M::W W;
+    M m;
     int log_n;
     uint32_t n_s, w;
     DecompParam g_dec;  // RGSW decomposor
     DecompParam r_dec;  // RLWE key-switch decomposor
     uint32_t small_digits;  // 1 if both decomposors satisfy log_b * d <= 32 (u32 digit extraction)
-    const TwPair<uint32_t>* tw;
-    const TwPair<uint32_t>* itw;
-    TwPair<uint32_t> ninv, wninv;
-    const uint2* brk;  // [n_s][2*g_d][N] of {a, b} in evaluation form
-    const uint2* ak;   // [w+1][r_d][N] of {a, b} in evaluation form
+    const TwPair<W>* tw;
+    const TwPair<W>* itw;
+    TwPair<W> ninv, wninv;
+    const KeyPair<W>* brk;  // [n_s][2*g_d][N] of {a, b} in evaluation form
+    const KeyPair<W>* ak;   // [w+1][r_d][N] of {a, b} in evaluation form
     const uint16_t* dlog;
     uint32_t ak_t[40];  // automorphism exponents t mod 2N for ak[0..w]
 };
+typedef FhewDevT<Mod32> FhewDev;
 
-// Shared-memory working set of one accumulator (all polynomials swizzled with swz<uint32_t>):
+// Shared-memory working set of one accumulator (all polynomials swizzled with swz<W>):
 //   acc_a[N], acc_b[N]   coefficient form, canonical
 //   dig[kmax][N]         digit polynomials / evaluation-domain products
-HD uint32_t* fhew_dig(uint32_t* smem, uint32_t n, uint32_t k) { return smem + (size_t)(2 + k) * n; }
+template <typename W>
+HD W* fhew_dig(W* smem, uint32_t n, uint32_t k) { return smem + (size_t)(2 + k) * n; }
 
 // Phase D (external product): digits of acc.a -> dig[0..d), digits of acc.b -> dig[d..2d)   (rgsw.rs:122-124)
-HD void fhew_phase_decomp_ext(const FhewDev& P, uint32_t* smem, uint32_t tid, uint32_t nthr) {
+template <typename M>
+HD void fhew_phase_decomp_ext(const FhewDevT<M>& P, typename M::W* smem, uint32_t tid, uint32_t nthr) {
+    typedef typename M::W W;
     const uint32_t n = 1u << P.log_n, d = P.g_dec.d;
     for (uint32_t i = tid; i < n; i += nthr) {
-        const uint32_t si = swz<uint32_t>(i);
+        const uint32_t si = swz<W>(i);
         for (uint32_t h = 0; h < 2; ++h) {
-            const uint32_t v = smem[h * n + si];
-            uint32_t* base = fhew_dig(smem, n, h * d) + si;
+            const W v = smem[h * n + si];
+            W* base = fhew_dig(smem, n, h * d) + si;
             if (P.small_digits)
-                decompose_zq<uint32_t>(P.m.q, P.g_dec, v, [&](uint32_t k, uint64_t dg) { base[(size_t)k * n] = (uint32_t)dg; });
+                decompose_zq<uint32_t>(P.m.q, P.g_dec, v, [&](uint32_t k, uint64_t dg) { base[(size_t)k * n] = (W)dg; });
             else
-                decompose_zq<uint64_t>(P.m.q, P.g_dec, v, [&](uint32_t k, uint64_t dg) { base[(size_t)k * n] = (uint32_t)dg; });
+                decompose_zq<uint64_t>(P.m.q, P.g_dec, v, [&](uint32_t k, uint64_t dg) { base[(size_t)k * n] = (W)dg; });
         }
     }
 }
 // Phase D (automorphism + key switch), step 1: digits of a(X^t) -> dig[0..d)   (rlwe.rs:80-82,182; avec.rs:34-50)
-HD void fhew_phase_decomp_auto_a(const FhewDev& P, uint32_t* smem, uint32_t t, uint32_t tid, uint32_t nthr) {
+template <typename M>
+HD void fhew_phase_decomp_auto_a(const FhewDevT<M>& P, typename M::W* smem, uint32_t t, uint32_t tid, uint32_t nthr) {
+    typedef typename M::W W;
     const uint32_t n = 1u << P.log_n;
     for (uint32_t i = tid; i < n; i += nthr) {
         const uint32_t it = (i * t) & (2 * n - 1);
-        uint32_t v = smem[swz<uint32_t>(i)];
+        W v = smem[swz<W>(i)];
         if (it >= n) v = P.m.neg(v);
-        uint32_t* base = fhew_dig(smem, n, 0) + swz<uint32_t>(it & (n - 1));
+        W* base = fhew_dig(smem, n, 0) + swz<W>(it & (n - 1));
         if (P.small_digits)
-            decompose_zq<uint32_t>(P.m.q, P.r_dec, v, [&](uint32_t k, uint64_t dg) { base[(size_t)k * n] = (uint32_t)dg; });
+            decompose_zq<uint32_t>(P.m.q, P.r_dec, v, [&](uint32_t k, uint64_t dg) { base[(size_t)k * n] = (W)dg; });
         else
-            decompose_zq<uint64_t>(P.m.q, P.r_dec, v, [&](uint32_t k, uint64_t dg) { base[(size_t)k * n] = (uint32_t)dg; });
+            decompose_zq<uint64_t>(P.m.q, P.r_dec, v, [&](uint32_t k, uint64_t dg) { base[(size_t)k * n] = (W)dg; });
     }
 }
 // step 2 (after a barrier; acc_a is dead): b(X^t) -> acc_a region
-HD void fhew_phase_auto_b(const FhewDev& P, uint32_t* smem, uint32_t t, uint32_t tid, uint32_t nthr) {
+template <typename M>
+HD void fhew_phase_auto_b(const FhewDevT<M>& P, typename M::W* smem, uint32_t t, uint32_t tid, uint32_t nthr) {
+    typedef typename M::W W;
     const uint32_t n = 1u << P.log_n;
     for (uint32_t i = tid; i < n; i += nthr) {
         const uint32_t it = (i * t) & (2 * n - 1);
-        uint32_t v = smem[n + swz<uint32_t>(i)];
+        W v = smem[n + swz<W>(i)];
         if (it >= n) v = P.m.neg(v);
-        smem[swz<uint32_t>(it & (n - 1))] = v;
+        smem[swz<W>(it & (n - 1))] = v;
     }
 }
 // forward / inverse NTT passes over `npoly` consecutive digit polynomials
-template <int R>
-HD void fhew_fwd_pass(const FhewDev& P, uint32_t* polys, uint32_t npoly, int t0, uint32_t tid, uint32_t nthr) {
+template <int R, typename M>
+HD void fhew_fwd_pass(const FhewDevT<M>& P, typename M::W* polys, uint32_t npoly, int t0, uint32_t tid, uint32_t nthr) {
     const int c = P.log_n;
     const uint32_t lg_groups = (uint32_t)(c - R);
     const uint32_t total = npoly << lg_groups;
     for (uint32_t u = tid; u < total; u += nthr) {
         const uint32_t poly = u >> lg_groups, g = u & ((1u << lg_groups) - 1u);
-        fwd_tile_group<Mod32, R>(P.m, polys + ((size_t)poly << c), c, t0, 0, 0, g, P.tw);
+        fwd_tile_group<M, R>(P.m, polys + ((size_t)poly << c), c, t0, 0, 0, g, P.tw);
     }
 }
-template <int R, bool LAST>
-HD void fhew_inv_pass(const FhewDev& P, uint32_t* polys, uint32_t npoly, int t0, uint32_t tid, uint32_t nthr) {
+template <int R, bool LAST, typename M>
+HD void fhew_inv_pass(const FhewDevT<M>& P, typename M::W* polys, uint32_t npoly, int t0, uint32_t tid, uint32_t nthr) {
     const int c = P.log_n;
     const uint32_t lg_groups = (uint32_t)(c - R);
     const uint32_t total = npoly << lg_groups;
     for (uint32_t u = tid; u < total; u += nthr) {
         const uint32_t poly = u >> lg_groups, g = u & ((1u << lg_groups) - 1u);
-        inv_tile_group<Mod32, R, LAST>(P.m, polys + ((size_t)poly << c), c, t0, 0, 0, g, P.itw, P.ninv, P.wninv);
+        inv_tile_group<M, R, LAST>(P.m, polys + ((size_t)poly << c), c, t0, 0, 0, g, P.itw, P.ninv, P.wninv);
     }
 }
-HD void fhew_fwd_pass_dyn(const FhewDev& P, uint32_t* polys, uint32_t npoly, int t0, int r, uint32_t tid, uint32_t nthr) {
+template <typename M>
+HD void fhew_fwd_pass_dyn(const FhewDevT<M>& P, typename M::W* polys, uint32_t npoly, int t0, int r, uint32_t tid, uint32_t nthr) {
     if (r == 3)
         fhew_fwd_pass<3>(P, polys, npoly, t0, tid, nthr);
     else if (r == 2)
@@ -228,7 +245,8 @@ HD void fhew_fwd_pass_dyn(const FhewDev& P, uint32_t* polys, uint32_t npoly, int
     else
         fhew_fwd_pass<1>(P, polys, npoly, t0, tid, nthr);
 }
-HD void fhew_inv_pass_dyn(const FhewDev& P, uint32_t* polys, uint32_t npoly, int t0, int r, uint32_t tid, uint32_t nthr) {
+template <typename M>
+HD void fhew_inv_pass_dyn(const FhewDevT<M>& P, typename M::W* polys, uint32_t npoly, int t0, int r, uint32_t tid, uint32_t nthr) {
     if (t0 == 0) {
         if (r == 3)
             fhew_inv_pass<3, true>(P, polys, npoly, t0, tid, nthr);
@@ -248,63 +266,82 @@ HD void fhew_inv_pass_dyn(const FhewDev& P, uint32_t* polys, uint32_t npoly, int
 // Phase M: evaluation-domain multiply-accumulate against `rows` pre-transformed key rows {a,b}[rows][N];
 // results overwrite dig[0] (a) and dig[1] (b) at the same index (each index is owned by one thread).
 // Digits come out of the forward transform in [0,4q) and are canonicalised here so that rows * q^2 < 2^64.
-HD void fhew_phase_mac(const FhewDev& P, uint32_t* smem, const uint2* __restrict__ key, uint32_t rows, uint32_t tid, uint32_t nthr) {
+template <typename M>
+HD void fhew_phase_mac(const FhewDevT<M>& P, typename M::W* smem, const KeyPair<typename M::W>* __restrict__ key, uint32_t rows, uint32_t tid,
+                       uint32_t nthr) {
+    typedef typename M::W W;
     const uint32_t n = 1u << P.log_n;
-    uint32_t* dig = fhew_dig(smem, n, 0);
+    W* dig = fhew_dig(smem, n, 0);
     for (uint32_t i = tid; i < n; i += nthr) {
-        const uint32_t si = swz<uint32_t>(i);
-        uint64_t sa = 0, sb = 0;
-        for (uint32_t k = 0; k < rows; ++k) {
-            const uint2 kv = key[(size_t)k * n + i];
-            const uint32_t dg = P.m.canon4(dig[(size_t)k * n + si]);
-            sa += (uint64_t)kv.x * dg;
-            sb += (uint64_t)kv.y * dg;
+        const uint32_t si = swz<W>(i);
+        if constexpr (sizeof(W) == 4) {
+            uint64_t sa = 0, sb = 0;
+            for (uint32_t k = 0; k < rows; ++k) {
+                const KeyPair<W> kv = key[(size_t)k * n + i];
+                const uint32_t dg = P.m.canon4(dig[(size_t)k * n + si]);
+                sa += (uint64_t)kv.x * dg;
+                sb += (uint64_t)kv.y * dg;
+            }
+            dig[si] = P.m.reduce64(sa);
+            dig[n + si] = P.m.reduce64(sb);
+        } else {  // 64-bit modulus: every product is reduced (rows * q^2 does not fit the 128-bit Barrett's input range)
+            W sa = 0, sb = 0;
+            for (uint32_t k = 0; k < rows; ++k) {
+                const KeyPair<W> kv = key[(size_t)k * n + i];
+                const W dg = P.m.canon4(dig[(size_t)k * n + si]);
+                sa = P.m.add(sa, P.m.mul(kv.x, dg));
+                sb = P.m.add(sb, P.m.mul(kv.y, dg));
+            }
+            dig[si] = sa;
+            dig[n + si] = sb;
         }
-        dig[si] = P.m.reduce64(sa);
-        dig[n + si] = P.m.reduce64(sb);
     }
 }
 // Phase F: acc <- (dig[0], dig[1] (+ b(X^t) parked in the acc_a region when add_b))
-HD void fhew_phase_finish(const FhewDev& P, uint32_t* smem, bool add_b, uint32_t tid, uint32_t nthr) {
+template <typename M>
+HD void fhew_phase_finish(const FhewDevT<M>& P, typename M::W* smem, bool add_b, uint32_t tid, uint32_t nthr) {
+    typedef typename M::W W;
     const uint32_t n = 1u << P.log_n;
-    const uint32_t* dig = fhew_dig(smem, n, 0);
+    const W* dig = fhew_dig(smem, n, 0);
     for (uint32_t i = tid; i < n; i += nthr) {
-        const uint32_t si = swz<uint32_t>(i);
-        uint32_t a = P.m.redq(dig[si]);
-        uint32_t b = P.m.redq(dig[n + si]);
+        const uint32_t si = swz<W>(i);
+        W a = P.m.redq(dig[si]);
+        W b = P.m.redq(dig[n + si]);
         if (add_b) b = P.m.add(b, smem[si]);
         smem[si] = a;
         smem[n + si] = b;
     }
 }
 // acc init (bootstrapping.rs:158-169): acc = (0, f(X^-g) * X^(b*g)); both maps are signed permutations, composed here.
-template <typename FT>
-HD void fhew_phase_init(const FhewDev& P, uint32_t* smem, const FT* __restrict__ f, uint32_t b2n, uint32_t tid, uint32_t nthr) {
+template <typename M, typename FT>
+HD void fhew_phase_init(const FhewDevT<M>& P, typename M::W* smem, const FT* __restrict__ f, uint32_t b2n, uint32_t tid, uint32_t nthr) {
+    typedef typename M::W W;
     const uint32_t n = 1u << P.log_n, m2 = 2 * n - 1;
     const uint32_t t = (2 * n - 5) & m2;   // -g mod 2N
     const uint32_t e = (b2n * 5) & m2;     // b*g mod 2N (the centred value and its residue give the same monomial)
     for (uint32_t i = tid; i < n; i += nthr) {
         const uint32_t pos = (i * t + e) & m2;
-        uint32_t v = (uint32_t)f[i];
+        W v = (W)f[i];
         if (pos >= n) v = P.m.neg(v);
-        smem[swz<uint32_t>(i)] = 0;
-        smem[n + swz<uint32_t>(pos & (n - 1))] = v;
+        smem[swz<W>(i)] = 0;
+        smem[n + swz<W>(pos & (n - 1))] = v;
     }
 }
 
 // One full step (external product or automorphism).  `run(phase)` executes phase(tid, nthr) for every thread of
 // the CTA followed by a barrier: on the device run = { phase(threadIdx.x, blockDim.x); __syncthreads(); },
 // in tests/hostsim it loops tid sequentially.
-template <typename Run>
-HD void fhew_step(const FhewDev& P, uint32_t* smem, uint32_t step, Run run) {
+template <typename M, typename Run>
+HD void fhew_step(const FhewDevT<M>& P, typename M::W* smem, uint32_t step, Run run) {
+    typedef typename M::W W;
     const uint32_t n = 1u << P.log_n;
     const PassPlan plan = make_plan(P.log_n);
     const bool is_auto = (step & FHEW_STEP_AUTO) != 0;
     const uint32_t idx = step & 0x7FFFu;
     const uint32_t rows = is_auto ? P.r_dec.d : 2 * P.g_dec.d;
-    const uint2* key = is_auto ? P.ak + (size_t)idx * rows * n : P.brk + (size_t)idx * rows * n;
+    const KeyPair<W>* key = is_auto ? P.ak + (size_t)idx * rows * n : P.brk + (size_t)idx * rows * n;
     const uint32_t t = is_auto ? P.ak_t[idx] : 0;
-    uint32_t* dig = fhew_dig(smem, n, 0);
+    W* dig = fhew_dig(smem, n, 0);
     if (!is_auto)
         run([&](uint32_t tid, uint32_t nthr) { fhew_phase_decomp_ext(P, smem, tid, nthr); });
     else
@@ -406,14 +443,15 @@ HD uint64_t lwe_phase_out(const LweKsDev& P, uint32_t acc, uint32_t j, uint32_t 
 }
 
 // Rlwe::sample_extract(ct, 0) (rlwe.rs:193-202) from the swizzled accumulator: out = [a_0, -a_{N-1}, .., -a_1, b_0 + post_add]
-template <typename OT>
-HD void fhew_phase_extract(const FhewDev& P, const uint32_t* smem, uint32_t post_add, OT* out, uint32_t tid, uint32_t nthr) {
+template <typename M, typename OT>
+HD void fhew_phase_extract(const FhewDevT<M>& P, const typename M::W* smem, typename M::W post_add, OT* out, uint32_t tid, uint32_t nthr) {
+    typedef typename M::W W;
     const uint32_t n = 1u << P.log_n;
     for (uint32_t k = tid; k < n; k += nthr) {
-        uint32_t v = k == 0 ? smem[swz<uint32_t>(0)] : P.m.neg(smem[swz<uint32_t>(n - k)]);
+        W v = k == 0 ? smem[swz<W>(0)] : P.m.neg(smem[swz<W>(n - k)]);
         out[k] = (OT)v;
     }
-    if (tid == 0) out[n] = (OT)P.m.add(smem[n + swz<uint32_t>(0)], post_add);
+    if (tid == 0) out[n] = (OT)P.m.add(smem[n + swz<W>(0)], post_add);
 }
 
 }  // namespace fhe

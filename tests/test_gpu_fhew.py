@@ -171,3 +171,72 @@ def test_host_path_pipelining_matches_device_path(pkg, ctx, orc, fhew_setup):
     ref = K.op([1, 1, 1, 0], cts[[0, 2250, 2251, 4500, 9000]], threads=5)
     assert (host[[0, 2250, 2251, 4500, 9000]] == ref).all()
     bk.free()
+
+
+# ---- 64-bit modulus path (the parameter shape of examples/multi_key_uint8.rs:15-29) -------------------
+def _wide_setup(pkg, ctx, orc, log_n, n_s, seed):
+    """55-bit Q = two_adic_primes(55, log_n + 1).next(), RLWE / RGSW decomposor (11, 5), LWE q = 2^20 with (4, 5), w = 10."""
+    from learn_fhe_b200 import fhew
+    P = orc.fhew_testing_param()
+    P.log_n, P.big_q = log_n, orc.two_adic_primes(55, log_n + 1, 1)[0]
+    P.rlwe_log_b = P.rgsw_log_b = 11
+    P.rlwe_d = P.rgsw_d = 5
+    P.n_s, P.q_ks, P.ks_log_b, P.ks_d, P.w = n_s, 1 << 20, 4, 5, 10
+    K = orc.FhewKey(P, seed)
+    ex = K.export()
+    param = pkg.FhewParam(log_n=log_n, big_q=P.big_q, p=4, rlwe_log_b=11, rlwe_d=5, rgsw_log_b=11, rgsw_d=5, n_s=n_s, q_ks=1 << 20,
+                          ks_log_b=4, ks_d=5, w=10)
+    key = fhew.BootstrappingKey(ctx, param, ex["ksk_a"], ex["ksk_b"], ex["brk"], ex["ak"], ex["ak_t"])
+    return P, K, param, key
+
+
+@pytest.mark.parametrize("log_n", [5, 8])
+def test_wide_modulus_steps_and_gates_reduced(pkg, ctx, orc, log_n):
+    from learn_fhe_b200 import fhew
+    P, K, param, key = _wide_setup(pkg, ctx, orc, log_n, 24, 0x5EED0009)
+    count = 6
+    acc = orc.residues(19, count * 2 * P.n, P.big_q).reshape(count, 2, P.n)
+    acc[0, 0, :3] = [0, P.big_q - 1, P.big_q // 2]
+    d_acc = pkg.to_dev(acc)
+    out = torch.empty_like(d_acc)
+    idx = np.array([0, 1, 7, 23, 12, 3], dtype=np.uint32)
+    d_idx = pkg.to_dev(idx)
+    ctx.call("fhe_fhew_external_product", key.h, count, pkg.dptr(d_idx), pkg.dptr(d_acc), pkg.dptr(out))
+    ctx.sync()
+    got = pkg.to_host(out)
+    for i in range(count):
+        assert (got[i] == K.external_product(int(idx[i]), acc[i])).all(), i
+    vidx = np.array([0, 1, 2, 10, 5, 9], dtype=np.uint32)
+    d_vidx = pkg.to_dev(vidx)
+    ctx.call("fhe_fhew_automorphism", key.h, count, pkg.dptr(d_vidx), pkg.dptr(d_acc), pkg.dptr(out))
+    ctx.sync()
+    got = pkg.to_host(out)
+    for i in range(count):
+        assert (got[i] == K.automorphism(int(vidx[i]), acc[i])).all(), i
+    bits = np.array([0, 0, 1, 1, 0, 1, 0, 1] * 3, dtype=np.int32)
+    cts = K.encrypt(bits, 17)
+    half = len(bits) // 2
+    lin = (cts[:half] + cts[half:]) % np.uint64(P.big_q)
+    for name in ("nand", "xor"):
+        table, pre = fhew.GATES[name]
+        x = fhew.Fhew.linear(param, pre, (cts[:half], cts[half:]))
+        got = fhew.Fhew.op(key, table, x)
+        assert (got == K.op(table, x, threads=4)).all(), name
+    nand = fhew.Fhew.op(key, [1, 1, 1, 0], lin)
+    assert (K.decrypt(nand) == 1 - (bits[:half] & bits[half:])).all()
+    key.free()
+
+
+def test_wide_modulus_at_the_multi_key_parameter_size(pkg, ctx, orc):
+    """N = 2048, Q 55 bits, d = 5, LWE n = 600 (examples/multi_key_uint8.rs:15-29): decryptions of a batch of gates and one
+    ciphertext compared word for word with the oracle."""
+    from learn_fhe_b200 import fhew
+    P, K, param, key = _wide_setup(pkg, ctx, orc, 11, 600, 0x5EED000A)
+    bits = np.array([0, 0, 1, 1, 0, 1, 0, 1] * 2, dtype=np.int32)
+    cts = K.encrypt(bits, 23)
+    half = len(bits) // 2
+    lin = (cts[:half] + cts[half:]) % np.uint64(P.big_q)
+    got = fhew.Fhew.op(key, [1, 1, 1, 0], lin)
+    assert (K.decrypt(got) == 1 - (bits[:half] & bits[half:])).all()
+    assert (got[:1] == K.op([1, 1, 1, 0], lin[:1], threads=1)).all()
+    key.free()
