@@ -110,6 +110,56 @@ def test_kernel_logic_fhew(H, orc, fhew_setup):
     H.sim_fhew_key_free(h)
 
 
+def test_kernel_logic_fhew_64bit_modulus(H, orc):
+    """The generic FHEW kernels instantiated for a 64-bit modulus (fhew.cu `wide`: the parameter shape of
+    examples/multi_key_uint8.rs:15-29 - 55-bit Q, decomposors (11, 5), LWE q = 2^20 - at N = 64): single steps, the LWE
+    prologue and whole gate bootstraps against the oracle, bit-exact."""
+    P = orc.fhew_testing_param()
+    P.log_n, P.big_q = 6, orc.two_adic_primes(55, 7, 1)[0]
+    P.rlwe_log_b = P.rgsw_log_b = 11
+    P.rlwe_d = P.rgsw_d = 5
+    P.n_s, P.q_ks, P.ks_log_b, P.ks_d, P.w = 12, 1 << 20, 4, 5, 10
+    K = orc.FhewKey(P, 0x5EED000B)
+    ex = K.export()
+    sp = SimParam(*[getattr(P, f[0]) for f in SimParam._fields_])
+    H.sim_fhew64_key_upload.restype = C.c_void_p
+    H.sim_fhew64_key_upload.argtypes = [C.POINTER(SimParam), u64p, u64p, u64p, u64p, i64p]
+    H.sim_fhew64_key_free.argtypes = [C.c_void_p]
+    H.sim_fhew64_step.argtypes = [C.c_void_p, C.c_uint, u64p, u64p, C.c_uint]
+    H.sim_fhew64_prologue.argtypes = [C.c_void_p, u64p, u64p, C.c_int, C.c_int, C.c_uint]
+    H.sim_fhew64_blind_rotate_extract.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint]
+    U = lambda v: np.ascontiguousarray(v, dtype=np.uint64).reshape(-1)
+    ak_t = np.ascontiguousarray(ex["ak_t"], dtype=np.int64)
+    h = H.sim_fhew64_key_upload(C.byref(sp), U(ex["ksk_a"]), U(ex["ksk_b"]), U(ex["brk"]), U(ex["ak"]), ak_t)
+    assert h
+    acc = orc.residues(29, 2 * P.n, P.big_q).reshape(2, P.n)
+    acc[0, :3] = [0, P.big_q - 1, P.big_q // 2]
+    out = np.zeros_like(acc)
+    for j in (0, 5, 11):
+        assert H.sim_fhew64_step(h, j, acc.reshape(-1), out.reshape(-1), 48) == 0
+        assert (out == K.external_product(j, acc)).all(), j
+    for v in (0, 1, 10):
+        assert H.sim_fhew64_step(h, 0x8000 | v, acc.reshape(-1), out.reshape(-1), 48) == 0
+        assert (out == K.automorphism(v, acc)).all(), v
+    bits = np.array([0, 0, 1, 1, 0, 1, 0, 1], dtype=np.int32)
+    cts = K.encrypt(bits, 7)
+    lin = (cts[:4] + cts[4:]) % np.uint64(P.big_q)
+    pro = K.prologue(lin)
+    f = orc.fhew_gate_poly(P, [1, 1, 1, 0])
+    q8 = int(round(P.big_q / 8.0))
+    ref = K.op([1, 1, 1, 0], lin, threads=2)
+    for i in range(4):
+        o = np.zeros(P.n_s + 1, dtype=np.uint64)
+        assert H.sim_fhew64_prologue(h, lin[i], o, 1, 1, 32) == 0
+        assert (o == pro[i]).all()
+        o = np.zeros(P.n + 1, dtype=np.uint64)
+        a = np.zeros(2 * P.n, dtype=np.uint64)
+        assert H.sim_fhew64_blind_rotate_extract(h, f, pro[i], q8, o, a, 40) == 0
+        assert (o == ref[i]).all()
+    assert (K.decrypt(ref) == 1 - (bits[:4] & bits[4:])).all()
+    H.sim_fhew64_key_free(h)
+
+
 def test_kernel_logic_fhew_golden_tiny(H, orc):
     """The kernel logic on the committed tiny-parameter fixture (produced by pyref in the reference dataflow)."""
     from test_cpu_oracle import golden_fhew_tiny
