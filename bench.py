@@ -370,6 +370,78 @@ def ckks_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps):
     return res
 
 
+def next_rows_leg(pkg, ctx, torch, bk, param, local):
+    """Throughput of the SURVEY.md §8(f) rows built so far, one GPU (rank 0), small fixed sizes; parity of each is in tests/."""
+    from learn_fhe_b200 import ckks, circuits, fhew
+    dev = "cuda:%d" % local
+    stream = torch.cuda.current_stream(local)
+    res = {}
+    # rank 1: FhewU8::wrapping_mul (uint8.rs:123-135) on a vector of 512 encrypted bytes, level-batched gate DAG
+    B = 512
+
+    def u8_mul():
+        eng = circuits.GateEngine(bk)
+        a = circuits.FhewU8.from_ciphertexts(eng, xa)
+        b = circuits.FhewU8.from_ciphertexts(eng, xb)
+        prod = a * b
+        eng.evaluate([bit.node for bit in prod.bits])
+        return eng
+
+    xa = [pkg.to_dev(synth_cts(param, B, 900 + i), local) for i in range(8)]
+    xb = [pkg.to_dev(synth_cts(param, B, 950 + i), local) for i in range(8)]
+    eng = u8_mul()
+    ms = device_ms(torch, stream, u8_mul, 0, 2) / 2
+    res["fhew_u8_wrapping_mul"] = {"bytes_per_call": B, "gate_bootstraps_per_call": eng.gates, "bootstrap_batches_per_call": eng.launches,
+                                   "ms_per_call": ms, "u8_mul_per_sec": B / (ms * 1e-3), "gate_bootstraps_per_sec": eng.gates / (ms * 1e-3)}
+    del xa, xb, eng
+    # rank 4: the 64-bit-modulus FHEW path at the multi-key parameter size (examples/multi_key_uint8.rs:15-29), synthetic key
+    q = pkg.first_two_adic_prime(55, 12)
+    wp = pkg.FhewParam(log_n=11, big_q=q, p=4, rlwe_log_b=11, rlwe_d=5, rgsw_log_b=11, rgsw_d=5, n_s=600, q_ks=1 << 20, ks_log_b=4, ks_d=5, w=10)
+    wk = fhew.BootstrappingKey(ctx, wp, *synth_fhew_key(wp, 5))
+    wf = pkg.to_dev(fhew.gate_poly(wp, [1, 1, 1, 0]), local)
+    wb = 2 * ctx.sm_count
+    win = pkg.to_dev(synth_cts(wp, wb, 6), local)
+    wout = torch.empty_like(win)
+    step = lambda: fhew.Bootstrapping.bootstrap_dev(wk, wf, win, wout, post_add=fhew.big_q_by_8(wp))
+    step()
+    ms = device_ms(torch, stream, step, 0, 1)
+    res["fhew_64bit_modulus"] = {"config": "N=2048, 55-bit Q, decomposors (11,5), LWE n=600 q=2^20; synthetic key; generic kernels", "batch": wb,
+                                 "ms_per_step": ms, "gates_per_sec": wb / (ms * 1e-3), "key_bytes": wk.nbytes}
+    wk.free()
+    del win, wout
+    # rank 2: Bootstrapping::mul_mat (ckks/bootstrapping.rs:92-108) at N = 2^16, level 8: 8 baby x 4 giant steps, dense
+    log_n, L, count, nb, ng = 16, 8, 16, 8, 4
+    P = ckks.CkksParam.new(ctx, log_n, 55, L)
+    rng = np.random.default_rng(0x5EED0005)
+    mk = lambda: ckks.CkksKeySwitchingKey(P, np.stack([np.stack([rng.integers(0, m, size=P.n, dtype=np.uint64) for m in P.qs + P.ps]) for _ in range(2)]))
+    keys = [mk() for _ in range(nb - 1 + ng - 1)]
+    baby = [(0, None)] + [(pow(5, j, 2 * P.n), keys[j - 1]) for j in range(1, nb)]
+    giant = [(0, None)] + [(pow(5, nb * i, 2 * P.n), keys[nb - 1 + i - 1]) for i in range(1, ng)]
+    rot = lambda lst: (pkg.CkksRot * len(lst))(*[pkg.CkksRot(t, k.h if k is not None else None) for t, k in lst])
+    b_arr, g_arr = rot(baby), rot(giant)
+    present = np.ones((ng, nb), dtype=np.uint8)
+    pts = torch.empty((ng * nb, L, P.n), dtype=torch.int64, device=dev)
+    ct = torch.empty((count, 2, L, P.n), dtype=torch.int64, device=dev)
+    for i, m in enumerate(P.qs):
+        pts[:, i, :].random_(0, m)
+        ct[:, :, i, :].random_(0, m)
+    out = torch.empty((count, 2, L - 1, P.n), dtype=torch.int64, device=dev)
+    import ctypes as C
+    step = lambda: ctx.call("fhe_ckks_mul_mat", P.h, L, count, nb, C.cast(b_arr, C.c_void_p), ng, C.cast(g_arr, C.c_void_p), pkg.hptr(present),
+                            pkg.dptr(pts), pkg.dptr(ct), pkg.dptr(out))
+    step()
+    ms = device_ms(torch, stream, step, 0, 2) / 2
+    res["ckks_mul_mat"] = {"config": "N=2^16, level 8 -> 7, dense 32-diagonal BSGS (8 baby x 4 giant), 10 rotation keys resident, synthetic", "ciphertexts": count,
+                           "ms_per_call": ms, "matrix_vector_products_per_sec": count / (ms * 1e-3),
+                           "rotations_per_call": count * (nb - 1 + ng - 1), "plain_mults_per_call": count * nb * ng}
+    for k in keys:
+        k.free()
+    P.free()
+    del pts, ct, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -383,6 +455,7 @@ def main():
     ap.add_argument("--ntt-reps", type=int, default=20)
     ap.add_argument("--no-tfhe", action="store_true", help="skip the TFHE PBS leg (BASELINE configs[2])")
     ap.add_argument("--no-ckks", action="store_true", help="skip the CKKS hom-mult leg (BASELINE configs[3])")
+    ap.add_argument("--no-next", action="store_true", help="skip the SURVEY 8(f) legs (u8 circuits, 64-bit FHEW, CKKS mul_mat)")
     ap.add_argument("--tfhe-batch", type=int, default=16384, help="PBS per GPU per step")
     ap.add_argument("--ckks-batch", type=int, default=512, help="ciphertext pairs per GPU per step")
     args = ap.parse_args()
@@ -517,6 +590,10 @@ def main():
     tfhe_res_1024 = None if args.no_tfhe else tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, max(1, min(args.steps, 2)), True)
     ckks_res = None if args.no_ckks else ckks_leg(pkg, ctx, torch, dist, world, rank, local, args.ckks_batch, max(1, min(args.steps, 3)))
 
+    next_res = None
+    if rank == 0 and not args.no_next:
+        next_res = next_rows_leg(pkg, ctx, torch, bk, param, local)
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         from oracle import orc  # cpu_baseline leg: the oracle as the timed CPU port + bit-exact checker of a GPU sample
@@ -561,6 +638,8 @@ def main():
             line["tfhe_pbs_n1024_synthetic"] = tfhe_res_1024
         if ckks_res is not None:
             line["ckks_mul"] = ckks_res
+        if next_res is not None:
+            line["next_rows"] = next_res
         if ntt is not None:
             line["ntt"] = ntt
             best = max(ntt, key=lambda r: (r["log_n"], r["word_bits"]))
