@@ -389,13 +389,15 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     FHE_REQUIRE(ctx, pp->log_n >= 2 && pp->log_n <= 11, "FHEW path supports 4 <= N <= 2048 (got log_n = %u)", pp->log_n);
     FHE_REQUIRE(ctx, pp->big_q < (1ull << 62), "FHEW path needs Q < 2^62");
     const bool wide = pp->big_q >= (1ull << 30);  // 64-bit residues (generic kernels only)
+    FHE_REQUIRE(ctx, wide ? (2 * pp->rgsw_d <= 32 && pp->rlwe_d <= 32) : 2 * pp->rgsw_d <= 16,
+                "too many digits: 2 * rgsw_d <= 16 for Q < 2^30 (64-bit MAC accumulator bound), <= 32 above");
     FHE_REQUIRE(ctx, pp->q_ks >= 2 && pp->q_ks <= (1ull << 32) && (pp->q_ks & (pp->q_ks - 1)) == 0, "q_ks must be a power of two <= 2^32");
     FHE_REQUIRE(ctx, pp->w >= 1 && pp->w < 40, "window w must be in [1, 39]");
     FHE_REQUIRE(ctx, pp->rgsw_d >= 1 && pp->rlwe_d >= 1 && pp->ks_d >= 1 && pp->rgsw_log_b >= 1 && pp->rlwe_log_b >= 1 && pp->ks_log_b >= 1,
                 "decomposor parameters must be positive");
     FHE_REQUIRE(ctx, pp->rgsw_log_b * pp->rgsw_d <= 64 && pp->rlwe_log_b * pp->rlwe_d <= 64 && pp->ks_log_b * pp->ks_d <= 32,
                 "decomposor log_b * d too large");
-    FHE_REQUIRE(ctx, 2 * pp->rgsw_d <= 16, "2 * rgsw_d must be <= 16 (64-bit MAC accumulator bound)");
+    // (the check against `wide` follows below, once it is known)
     FHE_REQUIRE(ctx, pp->n_s >= 1 && pp->n_s < 32768, "n_s out of range");
     const uint32_t n = 1u << pp->log_n;
     const NttTable* t;

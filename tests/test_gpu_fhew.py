@@ -240,3 +240,46 @@ def test_wide_modulus_at_the_multi_key_parameter_size(pkg, ctx, orc):
     assert (K.decrypt(got) == 1 - (bits[:half] & bits[half:])).all()
     assert (got[:1] == K.op([1, 1, 1, 0], lin[:1], threads=1)).all()
     key.free()
+
+
+@pytest.mark.parametrize("log_n", list(range(2, 10)))
+def test_reference_ring_sweep_45bit_primes_nine_digits(pkg, ctx, orc, log_n):
+    """The shapes of the reference's own RLWE / RGSW tests (testing_n_q, rlwe.rs:337-342: log_n x 45-bit primes of
+    two_adic_primes(45, log_n + 1); decomposor log_b = 5, d = 9, rgsw.rs:163-227, rlwe.rs:344-459): external product,
+    automorphism + key switch and gate bootstraps through the 64-bit kernels, every word equal to the oracle's."""
+    from learn_fhe_b200 import fhew
+    for pi, q in enumerate(orc.two_adic_primes(45, log_n + 1, 3)):
+        P = orc.fhew_testing_param()
+        P.log_n, P.big_q = log_n, q
+        P.rlwe_log_b = P.rgsw_log_b = 5
+        P.rlwe_d = P.rgsw_d = 9
+        P.n_s, P.q_ks, P.ks_log_b, P.ks_d, P.w = 6, 1 << 16, 4, 4, 3
+        K = orc.FhewKey(P, 0x5EED0100 + 16 * log_n + pi)
+        ex = K.export()
+        param = pkg.FhewParam(log_n=log_n, big_q=q, p=4, rlwe_log_b=5, rlwe_d=9, rgsw_log_b=5, rgsw_d=9, n_s=P.n_s, q_ks=P.q_ks,
+                              ks_log_b=4, ks_d=4, w=P.w)
+        key = fhew.BootstrappingKey(ctx, param, ex["ksk_a"], ex["ksk_b"], ex["brk"], ex["ak"], ex["ak_t"])
+        count = P.n_s
+        acc = orc.residues(31 + pi, count * 2 * P.n, q).reshape(count, 2, P.n)
+        acc[0, 0, :2] = [0, q - 1]
+        d_acc = pkg.to_dev(acc)
+        out = torch.empty_like(d_acc)
+        d_idx = pkg.to_dev(np.arange(count, dtype=np.uint32))
+        ctx.call("fhe_fhew_external_product", key.h, count, pkg.dptr(d_idx), pkg.dptr(d_acc), pkg.dptr(out))
+        ctx.sync()
+        got = pkg.to_host(out)
+        for i in range(count):
+            assert (got[i] == K.external_product(i, acc[i])).all(), (log_n, q, i)
+        nv = P.w + 1
+        d_vidx = pkg.to_dev(np.arange(nv, dtype=np.uint32))
+        ctx.call("fhe_fhew_automorphism", key.h, nv, pkg.dptr(d_vidx), pkg.dptr(d_acc), pkg.dptr(out))
+        ctx.sync()
+        got = pkg.to_host(out)
+        for v in range(nv):
+            assert (got[v] == K.automorphism(v, acc[v])).all(), (log_n, q, v)
+        if log_n >= 4:  # a gate needs N >= 16 for the four plateaus of the test polynomial to be distinguishable
+            bits = np.array([0, 0, 1, 1, 0, 1, 0, 1], dtype=np.int32)
+            cts = K.encrypt(bits, 5)
+            lin = (cts[:4] + cts[4:]) % np.uint64(q)
+            assert (fhew.Fhew.op(key, [1, 1, 1, 0], lin) == K.op([1, 1, 1, 0], lin, threads=2)).all(), (log_n, q)
+        key.free()
