@@ -55,7 +55,7 @@ def test_rns_argument_errors(pkg, ctx, orc):
         ckks.rescale_k(ctx, p[:2], 2, x)
 
 
-@pytest.fixture(scope="module", params=[(4, 3), (9, 4), (12, 3)])
+@pytest.fixture(scope="module", params=[(1, 8), (4, 3), (6, 8), (9, 4), (12, 3)])
 def ckks_setup(request, pkg, ctx, orc):
     from learn_fhe_b200 import ckks
     log_n, big_l = request.param

@@ -54,7 +54,7 @@ def _upload(pkg, ctx, P, ex):
     return tfhe.BootstrappingKey(ctx, param, ex["brk"], ex["ksk_a"], ex["ksk_b"])
 
 
-@pytest.mark.parametrize("k,bs_d,big_n", [(2, 4, 256), (1, 1, 512), (1, 3, 1024)])
+@pytest.mark.parametrize("k,bs_d,big_n", [(2, 4, 256), (2, 8, 256), (1, 1, 512), (1, 3, 1024)])
 def test_external_product_keyswitch_blind_rotate_reduced(pkg, ctx, orc, k, bs_d, big_n):
     """tggsw.rs:134-181 / tlwe.rs:162-192 shapes (N=256, k=2, d=8-style) at reduced n."""
     from learn_fhe_b200 import tfhe
