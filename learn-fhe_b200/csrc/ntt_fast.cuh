@@ -16,6 +16,9 @@
 // ntt_kernels.cuh): u32: q < 2^28; u64: q < 2^56; 9 <= log_n <= 17.
 // Everything is __host__ __device__ so tests/hostsim can replay the passes thread by thread on the CPU.
 #pragma once
+#ifndef FAST_PAIR32
+#define FAST_PAIR32 1
+#endif
 #include "modarith.cuh"
 #include "ntt_core.cuh"
 
@@ -218,6 +221,71 @@ HD void fast_inv_regs(const L& m, typename L::W* x, const TwPair<typename L::W>*
     }
 }
 
+// Two groups that share every twiddle (adjacent positions lo, lo + 1 of the same pass): each twiddle is fetched once.
+template <typename L, int R, bool NC = true>
+HD void fast_fwd_regs2(const L& m, typename L::W* x, typename L::W* y, const TwPair<typename L::W>* __restrict__ tw, uint32_t tb) {
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+        const int h = 1 << (R - 1 - u);
+#pragma unroll
+        for (int top = 0; top < (1 << u); ++top) {
+            const TwPair<typename L::W> t = NC ? ld_tw(tw + ((tb << u) + top)) : tw[(tb << u) + top];
+#pragma unroll
+            for (int low = 0; low < h; ++low) {
+                const int j = (top << (R - u)) | low;
+                m.bf_fwd(x[j], x[j + h], t);
+                m.bf_fwd(y[j], y[j + h], t);
+            }
+        }
+    }
+}
+template <typename L, int R, bool LAST, bool NC = true>
+HD void fast_inv_regs2(const L& m, typename L::W* x, typename L::W* y, const TwPair<typename L::W>* __restrict__ itw, uint32_t tb,
+                       TwPair<typename L::W> ninv, TwPair<typename L::W> wninv) {
+#pragma unroll
+    for (int u = R - 1; u >= 0; --u) {
+        const int h = 1 << (R - 1 - u);
+        const int stage = R - 1 - u;
+#pragma unroll
+        for (int top = 0; top < (1 << u); ++top) {
+            if (LAST && u == 0) {
+#pragma unroll
+                for (int low = 0; low < h; ++low) {
+                    m.bf_inv_last(x[low], x[low + h], ninv, wninv, stage);
+                    m.bf_inv_last(y[low], y[low + h], ninv, wninv, stage);
+                }
+            } else {
+                const TwPair<typename L::W> t = NC ? ld_tw(itw + ((tb << u) + top)) : itw[(tb << u) + top];
+#pragma unroll
+                for (int low = 0; low < h; ++low) {
+                    const int j = (top << (R - u)) | low;
+                    m.bf_inv(x[j], x[j + h], t, stage);
+                    m.bf_inv(y[j], y[j + h], t, stage);
+                }
+            }
+        }
+    }
+}
+// 8-byte access to two adjacent 32-bit words (even word address)
+HD void ld_pair(const uint32_t* p, uint32_t& a, uint32_t& b) {
+#if defined(__CUDA_ARCH__)
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    a = v.x;
+    b = v.y;
+#else
+    a = p[0];
+    b = p[1];
+#endif
+}
+HD void st_pair(uint32_t* p, uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint2*>(p) = make_uint2(a, b);
+#else
+    p[0] = a;
+    p[1] = b;
+#endif
+}
+
 // ---- 16-byte vector helpers (8 logically contiguous words at swizzled word address P0, P0 = swz(8g)) ----------------
 #if defined(__CUDA_ARCH__)
 DEV void ld_vec8(const uint32_t* s, uint32_t P0, uint32_t* x) {
@@ -308,6 +376,30 @@ HD void fast_fwd_first(const FastLimb<L>& d, const typename L::W* g, typename L:
         for (int j = 0; j < (1 << R1); ++j) s[P0 ^ swz2<W>((uint32_t)j << LL)] = x[j];
     }
 }
+// paired first pass (32-bit words, R1 <= 3): groups grp, grp + 1 -> 8-byte global loads and shared stores, shared twiddles
+template <typename L, int LOGT, int R1, int TPP>
+HD void fast_fwd_first2(const FastLimb<L>& d, const uint32_t* g, uint32_t* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {
+    typedef uint32_t W;
+    constexpr int LL = LOGT - R1;
+    const uint32_t tb = (1u << s0) + k;
+#pragma unroll 1
+    for (uint32_t grp = tid << 1; grp < (1u << LL); grp += 2 * TPP) {
+        W x[1 << R1], y[1 << R1];
+#pragma unroll
+        for (int j = 0; j < (1 << R1); ++j) ld_pair(g + grp + ((uint32_t)j << LL), x[j], y[j]);
+        if (pre_red) {
+#pragma unroll
+            for (int j = 0; j < (1 << R1); ++j) {
+                x[j] = d.m.pre_red(x[j]);
+                y[j] = d.m.pre_red(y[j]);
+            }
+        }
+        fast_fwd_regs2<L, R1>(d.m, x, y, d.tw, tb);
+        const uint32_t P0 = swz2<W>(grp);
+#pragma unroll
+        for (int j = 0; j < (1 << R1); ++j) st_pair(s + (P0 ^ swz2<W>((uint32_t)j << LL)), x[j], y[j]);
+    }
+}
 // forward middle pass (radix-8, shared -> shared); local stages t0 .. t0+2, LL = LOGT - t0 - 3 >= 3
 template <typename L, int LOGT, int TPP, int t0>
 HD void fast_fwd_mid(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {
@@ -328,6 +420,34 @@ HD void fast_fwd_mid(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k,
         fast_fwd_regs<L, 3>(d.m, x, d.tw, tb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[P0 ^ swz2<W>((uint32_t)j << LL)] = x[j];
+    }
+}
+// forward middle pass for 32-bit words, two adjacent groups (lo even, lo + 1) per iteration: the XOR swizzle leaves word-address
+// bits 0..1 alone, so the pair is one aligned 8-byte shared access, and both groups use the same twiddles.  Half as many
+// shared-memory wavefronts, twiddle fetches and address computations per butterfly as fast_fwd_mid.
+template <typename L, int LOGT, int TPP, int t0>
+HD void fast_fwd_mid2(const FastLimb<L>& d, uint32_t* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {
+    typedef uint32_t W;
+    constexpr int LL = LOGT - t0 - 3;
+    static_assert(LL >= 1, "paired groups need a stride of at least two words");
+#pragma unroll 1
+    for (uint32_t gp = tid; gp < (1u << (LOGT - 4)); gp += TPP) {
+        const uint32_t lo = (gp & ((1u << (LL - 1)) - 1u)) << 1, hi = gp >> (LL - 1);
+        const uint32_t P0 = swz2<W>((hi << (LL + 3)) | lo);
+        W x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ld_pair(s + (P0 ^ swz2<W>((uint32_t)j << LL)), x[j], y[j]);
+        if (pre_red) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                x[j] = d.m.pre_red(x[j]);
+                y[j] = d.m.pre_red(y[j]);
+            }
+        }
+        const uint32_t tb = (1u << (s0 + t0)) + (k << t0) + hi;
+        fast_fwd_regs2<L, 3>(d.m, x, y, d.tw, tb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_pair(s + (P0 ^ swz2<W>((uint32_t)j << LL)), x[j], y[j]);
     }
 }
 // forward last pass (radix-8, LL = 0): shared -> registers -> global, canonical output
@@ -384,6 +504,26 @@ HD void fast_inv_mid(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k,
         for (int j = 0; j < 8; ++j) s[P0 ^ swz2<W>((uint32_t)j << LL)] = x[j];
     }
 }
+template <typename L, int LOGT, int TPP, int t0>
+HD void fast_inv_mid2(const FastLimb<L>& d, uint32_t* s, int s0, uint32_t k, uint32_t tid) {  // see fast_fwd_mid2
+    typedef uint32_t W;
+    constexpr int LL = LOGT - t0 - 3;
+    static_assert(LL >= 1, "paired groups need a stride of at least two words");
+#pragma unroll 1
+    for (uint32_t gp = tid; gp < (1u << (LOGT - 4)); gp += TPP) {
+        const uint32_t lo = (gp & ((1u << (LL - 1)) - 1u)) << 1, hi = gp >> (LL - 1);
+        const uint32_t P0 = swz2<W>((hi << (LL + 3)) | lo);
+        W x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ld_pair(s + (P0 ^ swz2<W>((uint32_t)j << LL)), x[j], y[j]);
+        const uint32_t tb = (1u << (s0 + t0)) + (k << t0) + hi;
+        fast_inv_regs2<L, 3, false>(d.m, x, y, d.itw, tb, d.ninv, d.wninv);
+        x[0] = d.m.inv_pass_fix(x[0]);
+        y[0] = d.m.inv_pass_fix(y[0]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_pair(s + (P0 ^ swz2<W>((uint32_t)j << LL)), x[j], y[j]);
+    }
+}
 // inverse last pass (R1 stages at local stages 0..R1-1): shared -> registers -> global.
 // FINAL: s0 == 0, this is the end of the transform: fold n^-1 and write canonical residues; otherwise the column
 // kernel follows and the pass invariant (u32 [0,2q), u64 < 16q) is restored instead.
@@ -411,6 +551,83 @@ HD void fast_inv_last(const FastLimb<L>& d, const typename L::W* s, typename L::
     }
 }
 
+template <typename L, int LOGT, int R1, int TPP, bool FINAL>
+HD void fast_inv_last2(const FastLimb<L>& d, const uint32_t* s, uint32_t* __restrict__ g, int s0, uint32_t k, uint32_t tid) {  // see fast_fwd_first2
+    typedef uint32_t W;
+    constexpr int LL = LOGT - R1;
+    const uint32_t tb = (1u << s0) + k;
+#pragma unroll 1
+    for (uint32_t grp = tid << 1; grp < (1u << LL); grp += 2 * TPP) {
+        const uint32_t P0 = swz2<W>(grp);
+        W x[1 << R1], y[1 << R1];
+#pragma unroll
+        for (int j = 0; j < (1 << R1); ++j) ld_pair(s + (P0 ^ swz2<W>((uint32_t)j << LL)), x[j], y[j]);
+        fast_inv_regs2<L, R1, FINAL>(d.m, x, y, d.itw, tb, d.ninv, d.wninv);
+        if (FINAL) {
+#pragma unroll
+            for (int j = 0; j < (1 << R1); ++j) {
+                x[j] = d.m.inv_canon(x[j]);
+                y[j] = d.m.inv_canon(y[j]);
+            }
+        } else {
+            x[0] = d.m.inv_pass_fix(x[0]);
+            y[0] = d.m.inv_pass_fix(y[0]);
+        }
+#pragma unroll
+        for (int j = 0; j < (1 << R1); ++j) st_pair(g + grp + ((uint32_t)j << LL), x[j], y[j]);
+    }
+}
+
+// first-pass radix of a 2^logt tile (the remaining stages are radix-8 passes)
+HD constexpr int fast_r1(int logt) { return logt % 3 == 0 ? 3 : (logt % 3 == 1 ? 4 : 2); }
+// ---- tile geometry and pass sequence (shared by the kernel and tests/hostsim) -----------------------------------------------
+// PAIR (32-bit words only): middle passes process two adjacent groups per thread, so half as many threads cover a tile.
+template <typename L, int LOGT>
+struct FastGeom {
+    static constexpr int R1 = fast_r1(LOGT);
+    static constexpr int RMAX = R1 > 3 ? R1 : 3;
+    static constexpr int PAIR = (L::BITS == 32 && FAST_PAIR32) ? 1 : 0;
+    static constexpr int TPP = 1 << (LOGT - RMAX - PAIR);
+    static constexpr int PB = TPP >= 256 ? 1 : 256 / TPP;
+    static constexpr int NTHR = TPP * PB;
+    static constexpr int NP3 = (LOGT - R1) / 3;
+};
+template <typename L, int LOGT, int t0>
+HD void fast_fwd_mid_any(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {
+    typedef FastGeom<L, LOGT> G;
+    if constexpr (G::PAIR != 0)
+        fast_fwd_mid2<L, LOGT, G::TPP, t0>(d, s, s0, k, pre_red, tid);
+    else
+        fast_fwd_mid<L, LOGT, G::TPP, t0>(d, s, s0, k, pre_red, tid);
+}
+template <typename L, int LOGT, int t0>
+HD void fast_inv_mid_any(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, uint32_t tid) {
+    typedef FastGeom<L, LOGT> G;
+    if constexpr (G::PAIR != 0)
+        fast_inv_mid2<L, LOGT, G::TPP, t0>(d, s, s0, k, tid);
+    else
+        fast_inv_mid<L, LOGT, G::TPP, t0>(d, s, s0, k, tid);
+}
+template <typename L, int LOGT>
+HD void fast_fwd_first_any(const FastLimb<L>& d, const typename L::W* g, typename L::W* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {
+    typedef FastGeom<L, LOGT> G;
+    if constexpr (G::PAIR != 0 && G::R1 <= 3)
+        fast_fwd_first2<L, LOGT, G::R1, G::TPP>(d, g, s, s0, k, pre_red, tid);
+    else
+        fast_fwd_first<L, LOGT, G::R1, G::TPP>(d, g, s, s0, k, pre_red, tid);
+}
+template <typename L, int LOGT, bool FINAL>
+HD void fast_inv_last_any(const FastLimb<L>& d, const typename L::W* s, typename L::W* __restrict__ g, int s0, uint32_t k, uint32_t tid) {
+    typedef FastGeom<L, LOGT> G;
+    if constexpr (G::PAIR != 0 && G::R1 <= 3)
+        fast_inv_last2<L, LOGT, G::R1, G::TPP, FINAL>(d, s, g, s0, k, tid);
+    else
+        fast_inv_last<L, LOGT, G::R1, G::TPP, FINAL>(d, s, g, s0, k, tid);
+}
+// tile size used for a ring of degree 2^log_n: rings larger than one tile take a column kernel (S <= 4 stages, HBM-bound)
+// first; measured best tile 2^11 for N = 2^14, 2^15
+HD constexpr int fast_tile_logt(int log_n) { return log_n <= 13 ? log_n : (log_n <= 15 ? 11 : log_n - 4); }
+
 // ---- column passes (first S forward stages / last S inverse stages of a polynomial too large for one tile) ------------
 // the polynomial is viewed as a [2^S][2^lc] row-major matrix; one thread transforms one column in registers.
 template <typename L, int S>
@@ -435,7 +652,6 @@ HD void fast_inv_column(const FastLimb<L>& d, const typename L::W* gin, typename
 }
 
 // tile plan: first-pass radix for a tile of LOGT stages
-HD constexpr int fast_r1(int logt) { return logt % 3 == 0 ? 3 : (logt % 3 == 1 ? 4 : 2); }
 
 // Bounds bookkeeping for the u32 forward path (host side, planner): returns the pre_red bit mask for the passes of the
 // tile (bit 0 = first pass, bit i = i-th radix-8 pass after it) given the bound (in units of q) of the values entering

@@ -27,29 +27,20 @@ struct FastArgs {
     unsigned long long n_items;  // n_polys << s0
 };
 
-template <int LOGT>
-struct FastGeom {
-    static constexpr int R1 = fast_r1(LOGT);
-    static constexpr int RMAX = R1 > 3 ? R1 : 3;
-    static constexpr int TPP = 1 << (LOGT - RMAX);
-    static constexpr int PB = TPP >= 256 ? 1 : 256 / TPP;
-    static constexpr int NTHR = TPP * PB;
-    static constexpr int NP3 = (LOGT - R1) / 3;
-};
 
 // resident threads per SM the tile kernels are compiled for (register cap = 65536 / this): u64 1024 (64 registers),
-// u32 1536 (40 registers; 2048 forces 32 and spills in the 2^12 / 2^13 tiles)
+// u32 1280 (48 registers; measured best for the paired-group passes: 1024 and 1536 are 3-8 % slower on some sizes)
 #ifndef FAST_OCC32
-#define FAST_OCC32 1536
+#define FAST_OCC32 1280
 #endif
 #ifndef FAST_OCC64
 #define FAST_OCC64 1024
 #endif
 template <typename L, int LOGT, bool FWD, bool FINAL>
-__global__ void __launch_bounds__(FastGeom<LOGT>::NTHR, (L::BITS == 32 ? FAST_OCC32 : FAST_OCC64) / FastGeom<LOGT>::NTHR)
+__global__ void __launch_bounds__(FastGeom<L, LOGT>::NTHR, (L::BITS == 32 ? FAST_OCC32 : FAST_OCC64) / FastGeom<L, LOGT>::NTHR)
 ntt_fast_tile_kernel(FastArgs<L> a) {
     typedef typename L::W W;
-    typedef FastGeom<LOGT> G;
+    typedef FastGeom<L, LOGT> G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t pslot = threadIdx.x / G::TPP, tid = threadIdx.x % G::TPP;
     W* s = reinterpret_cast<W*>(smem_raw) + ((size_t)pslot << LOGT);
@@ -65,14 +56,14 @@ ntt_fast_tile_kernel(FastArgs<L> a) {
     W* g = a.data + off;
     const W* gin = a.in + off;
     if (FWD) {
-        if (active) fast_fwd_first<L, LOGT, G::R1, G::TPP>(d, gin, s, a.s0, k, (a.pre_red & 1u) != 0, tid);
+        if (active) fast_fwd_first_any<L, LOGT>(d, gin, s, a.s0, k, (a.pre_red & 1u) != 0, tid);
         __syncthreads();
         if (G::NP3 > 1) {
-            if (active) fast_fwd_mid<L, LOGT, G::TPP, G::R1>(d, s, a.s0, k, ((a.pre_red >> 1) & 1u) != 0, tid);
+            if (active) fast_fwd_mid_any<L, LOGT, G::R1>(d, s, a.s0, k, ((a.pre_red >> 1) & 1u) != 0, tid);
             __syncthreads();
         }
         if (G::NP3 > 2) {
-            if (active) fast_fwd_mid<L, LOGT, G::TPP, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, s, a.s0, k, ((a.pre_red >> 2) & 1u) != 0, tid);
+            if (active) fast_fwd_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, s, a.s0, k, ((a.pre_red >> 2) & 1u) != 0, tid);
             __syncthreads();
         }
         static_assert(G::NP3 <= 3, "at most two middle passes");
@@ -81,14 +72,14 @@ ntt_fast_tile_kernel(FastArgs<L> a) {
         if (active) fast_inv_first<L, LOGT, G::TPP>(d, gin, s, a.s0, k, tid);
         __syncthreads();
         if (G::NP3 > 2) {
-            if (active) fast_inv_mid<L, LOGT, G::TPP, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, s, a.s0, k, tid);
+            if (active) fast_inv_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, s, a.s0, k, tid);
             __syncthreads();
         }
         if (G::NP3 > 1) {
-            if (active) fast_inv_mid<L, LOGT, G::TPP, G::R1>(d, s, a.s0, k, tid);
+            if (active) fast_inv_mid_any<L, LOGT, G::R1>(d, s, a.s0, k, tid);
             __syncthreads();
         }
-        if (active) fast_inv_last<L, LOGT, G::R1, G::TPP, FINAL>(d, s, g, a.s0, k, tid);
+        if (active) fast_inv_last_any<L, LOGT, FINAL>(d, s, g, a.s0, k, tid);
     }
 }
 
@@ -160,7 +151,7 @@ static fhe_status get_fast_limbs(fhe_ctx* ctx, const uint64_t* qs, size_t nl, un
 
 template <typename L, int LOGT, bool FWD, bool FINAL>
 static fhe_status launch_fast_tile(fhe_ctx* ctx, FastArgs<L>& a) {
-    typedef FastGeom<LOGT> G;
+    typedef FastGeom<L, LOGT> G;
     auto kern = ntt_fast_tile_kernel<L, LOGT, FWD, FINAL>;
     const size_t smem = (size_t)G::PB * sizeof(typename L::W) << LOGT;
     static bool attr_set = false;
@@ -213,8 +204,7 @@ static fhe_status launch_ntt_fast(fhe_ctx* ctx, const uint64_t* qs, size_t nl, u
         if (!fast_modulus_ok<L>(qs[i])) return FHE_EUNSUPPORTED;
     if (n_polys == 0) return FHE_OK;
     if (n_polys > 0x7FFFFFFFull) return fail(ctx, FHE_EINVAL, "batch too large");
-    // rings larger than one tile: column kernel (S <= 4 stages, HBM-bound) + tiles; measured best tile 2^11 for N = 2^14, 2^15
-    int logt = log_n <= 13 ? (int)log_n : (log_n <= 15 ? 11 : (int)log_n - 4);
+    int logt = fast_tile_logt((int)log_n);
     if (const char* e = getenv("FHE_B200_NTT_LOGT")) {  // tuning knob: tile size for rings larger than one tile
         const int v = atoi(e);
         if (log_n > 13 && v >= 9 && v <= 13 && (int)log_n - v <= 4) logt = v;
