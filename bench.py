@@ -346,17 +346,18 @@ def ckks_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps):
     res = {"metric": "ckks_mul_relin_rescale_per_sec", "value": batch * world * steps / (ms * 1e-3), "unit": "mult/s",
            "batch_per_gpu": batch, "steps": steps, "ms_per_step": ms / steps,
            "config": "CKKS-T: N=2^16, log_qi=55, L=8 (+8 special primes), level 8 -> 7, rlk resident",
-           "compulsory_hbm_gbs": io_bytes * steps / (ms * 1e-3) / 1e9, "ntt_per_mult": 9 * L + 3 * L,
+           "compulsory_hbm_gbs": io_bytes * steps / (ms * 1e-3) / 1e9, "ntt_per_mult": 7 * L + 3 * L,
            "kernels": {kk: {"ms_per_step": v["ms"] / steps, "launches": v["launches"]} for kk, v in prof.items()}}
     # INT32-pipe roofline of the whole operation (same instruction-mix rule as the NTT lines: 9 32-bit products per 64-bit
     # Shoup butterfly or modular multiply).  Work per Ckks::mul (ckks.rs:255-293, rns.rs:99-158), l = L:
-    #   (9l + 3L) NTTs of N/2 log N butterflies; tensor 4 l N; key products 2 (l + L) N; base conversion l -> L of d2:
+    #   (7l + 3L) NTTs of N/2 log N butterflies (4l forward of the inputs, l inverse + L forward around the base conversion of d2,
+    #   2(l + L) inverse of the key products with P (d0, d1) folded in); tensor 4 l N; key products 2 (l + L) N + fold 2 l N; base conversion l -> L of d2:
     #   (l + l L) N; rescale_k by the L special primes of 2 polynomials: 2 (L + L l + l) N; final rescale: 2 (1 + 2 (l - 1)) N
     pk = ctx.int32_peak()
     if pk.get("imad"):
         l = L
-        n_bf = (9 * l + 3 * L) * (P.n // 2) * log_n
-        n_mm = (4 * l + 2 * (l + L) + (l + l * L) + 2 * (L + L * l + l) + 2 * (1 + 2 * (l - 1))) * P.n
+        n_bf = (7 * l + 3 * L) * (P.n // 2) * log_n
+        n_mm = (4 * l + 2 * (l + L) + 2 * l + (l + l * L) + 2 * (L + L * l + l) + 2 * (1 + 2 * (l - 1))) * P.n
         per = (4 / pk["imad"] + 2 / pk["imad_hi"] + 3 / pk["imad_wide"]) / 1e12
         t_min = (n_bf + n_mm) * per * batch
         res["roofline"] = {"bound": "int32", "kernel": "whole Ckks::mul (ntt_fast_* 60 %, rns_rescale 20 %)", "achieved": 9 * (n_bf + n_mm) * batch / (ms / steps * 1e-3) / 1e12,

@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(256) ckks_tensor_kernel(const Mod64* __restric
 // key products: x = [xq (l limbs, eval) ; xp (L limbs, eval)] against ksk [2 (b,a)][2L][n] eval -> out [C][2][l+L][n]  (ckks.rs:289-291)
 __global__ void __launch_bounds__(256) ckks_keymul_kernel(const Mod64* __restrict__ mods /* [2L]: qs then ps */, int l, int big_l, int log_n,
                                                           unsigned long long count, const uint64_t* __restrict__ xq, const uint64_t* __restrict__ xp,
-                                                          const uint64_t* __restrict__ ksk, uint64_t* __restrict__ out) {
+                                                          const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ addend /* [C][2][l][n] or null */,
+                                                          const uint64_t* __restrict__ pmod /* [L]: P mod q_j */, uint64_t* __restrict__ out) {
     const size_t n = (size_t)1 << log_n;
     const int le = l + big_l;
     const unsigned long long total = count * le * n, stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -160,8 +161,18 @@ __global__ void __launch_bounds__(256) ckks_keymul_kernel(const Mod64* __restric
         const Mod64 m = mods[kl];
         const uint64_t v = j < l ? xq[(c * l + j) * n + x] : xp[(c * big_l + (j - l)) * n + x];
         const size_t o = c * 2 * le * n + r;
-        out[o] = m.mul(ksk[(size_t)kl * n + x], v);
-        out[o + (size_t)le * n] = m.mul(ksk[((size_t)2 * big_l + kl) * n + x], v);
+        uint64_t kb = m.mul(ksk[(size_t)kl * n + x], v);
+        uint64_t ka = m.mul(ksk[((size_t)2 * big_l + kl) * n + x], v);
+        if (addend && j < l) {
+            // Ckks::mul adds (d0, d1) to the relinearised pair after the division by P (ckks.rs:266, rns.rs:127-132).  On the
+            // kept limbs rescale_k is (x_i + P/2 - ext_i) * P^-1, so adding P * d_i to x_i here - in the evaluation domain, before
+            // the inverse transform - yields exactly d_i + rescale_k(x)_i and saves the inverse transforms of d0 and d1.
+            const size_t a0 = (c * 2 * l + j) * n + x;
+            kb = m.add(kb, m.mul(pmod[j], addend[a0]));
+            ka = m.add(ka, m.mul(pmod[j], addend[a0 + (size_t)l * n]));
+        }
+        out[o] = kb;
+        out[o + (size_t)le * n] = ka;
     }
 }
 // plaintext x ciphertext in the evaluation domain: e [C][2][l][n] *= pe [1 or C][l][n] (limb-wise)   (ckks.rs:250-253)
@@ -277,6 +288,7 @@ struct fhe_ckks_ctx {
     size_t big_l = 0;
     std::vector<uint64_t> qs, ps;
     Mod64* d_mods = nullptr;  // [2L]: qs then ps
+    uint64_t* d_pmod = nullptr;  // [L]: (product of the special primes) mod q_j
     // grow-only workspace
     void* ws = nullptr;
     size_t ws_bytes = 0;
@@ -308,15 +320,17 @@ static std::vector<uint64_t> level_qps(const fhe_ckks_ctx* ck, size_t l) {
 // Ckks::key_switch core (ckks.rs:284-293) on `count` polynomials a (coefficient form [count][l][n]) whose evaluation form
 // a_eval [count][l][n] is already available: r [count][2][l][n] = rescale_k(ksk * extend(a), L) (+ post on the b half).
 // scratch: xp [count][L][n], kk [count][2][l+L][n]
+// d01_eval (optional, [count][2][l][n] evaluation form): added to the result (see ckks_keymul_kernel)
 static fhe_status key_switch_core(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* ksk, size_t l, size_t count, const uint64_t* a_coeff,
-                                  const uint64_t* a_eval, uint64_t* xp, uint64_t* kk, const uint64_t* post, uint64_t* r) {
+                                  const uint64_t* a_eval, uint64_t* xp, uint64_t* kk, const uint64_t* post, uint64_t* r,
+                                  const uint64_t* d01_eval = nullptr) {
     const unsigned log_n = ck->log_n;
     const size_t L = ck->big_l;
     const std::vector<uint64_t> qs = level_qs(ck, l), qps = level_qps(ck, l);
     FHE_CHECK(run_extend(ctx, qs, ck->ps, log_n, count, a_coeff, (int)l, 0, xp, (int)L, 0));
     FHE_CHECK(launch_ntt_rns_u64(ctx, ck->ps.data(), L, log_n, count * L, xp, true));
     ckks_keymul_kernel<<<stream_grid(ctx, (unsigned long long)count * (l + L) << log_n), 256, 0, ctx->stream>>>(
-        ck->d_mods, (int)l, (int)L, (int)log_n, count, a_eval, xp, ksk->d_eval, kk);
+        ck->d_mods, (int)l, (int)L, (int)log_n, count, a_eval, xp, ksk->d_eval, d01_eval, ck->d_pmod, kk);
     FHE_CHECK(after_launch(ctx, "ckks_keymul_kernel"));
     FHE_CHECK(launch_ntt_rns_u64(ctx, qps.data(), l + L, log_n, count * 2 * (l + L), kk, false));
     return run_rescale(ctx, qps, L, log_n, count * 2, kk, nullptr, post, true, r);
@@ -370,7 +384,16 @@ fhe_status fhe_ckks_create(fhe_ctx* ctx, unsigned log_n, const uint64_t* qs, con
     std::vector<Mod64> m(2 * big_l);
     for (size_t i = 0; i < 2 * big_l; ++i) m[i] = make_mod<Mod64>(all[i]);
     ck->d_mods = upload_vec(m);
-    if (!ck->d_mods) {
+    std::vector<uint64_t> pmod(big_l);
+    for (size_t j = 0; j < big_l; ++j) {
+        uint64_t v = 1 % qs[j];
+        for (size_t i = 0; i < big_l; ++i) v = host_mulmod(v, ps[i] % qs[j], qs[j]);
+        pmod[j] = v;
+    }
+    ck->d_pmod = upload_vec(pmod);
+    if (!ck->d_mods || !ck->d_pmod) {
+        if (ck->d_mods) cudaFree(ck->d_mods);
+        if (ck->d_pmod) cudaFree(ck->d_pmod);
         delete ck;
         return fail(ctx, FHE_ENOMEM, "CKKS modulus table upload failed");
     }
@@ -381,6 +404,7 @@ void fhe_ckks_destroy(fhe_ctx* ctx, fhe_ckks_ctx* ck) {
     if (!ck) return;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     if (ck->d_mods) cudaFree(ck->d_mods);
+    if (ck->d_pmod) cudaFree(ck->d_pmod);
     if (ck->ws) cudaFree(ck->ws);
     if (ck->ws2) cudaFree(ck->ws2);
     delete ck;
@@ -449,10 +473,9 @@ fhe_status fhe_ckks_mul_relin_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, cons
                                                                                                          d01, d2e);
         FHE_CHECK(after_launch(ctx, "ckks_tensor_kernel"));
         FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * l, d2e, d2c, false));
-        FHE_CHECK(key_switch_core(ctx, ck, rlk, l, c, d2c, d2e, xp, kk, nullptr, r));  // relinearize(d2): ct_b = 0
-        FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, c * 2 * l, d01, false));
-        // (d0, d1) + relin, then rescale (ckks.rs:266, 123-125)
-        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, d01, r, nullptr, false, d_out + base * 2 * (l - 1) * n));
+        // relinearize(d2) with ct_b = 0, plus (d0, d1) folded in before the inverse transforms; then rescale (ckks.rs:266, 123-125)
+        FHE_CHECK(key_switch_core(ctx, ck, rlk, l, c, d2c, d2e, xp, kk, nullptr, r, d01));
+        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, r, nullptr, nullptr, false, d_out + base * 2 * (l - 1) * n));
     }
     return FHE_OK;
 }
