@@ -162,7 +162,17 @@ HD void rns_rescale_coeff(const Tab& R, Load x, Emit emit) {
     };
     if (k == 1) {
         const uint64_t vp = rounded(l);  // non-centred value of the dropped limb (rns.rs:109-111)
-        for (int i = 0; i < l; ++i) finish(i, rns_reduce_u64(R.m_all[i], vp));
+        // this path is bound by global-memory latency: issue every load before the first use (static register indices)
+        uint64_t xk[RNS_MAXL];
+#pragma unroll
+        for (int i = 0; i < RNS_MAXL; ++i) xk[i] = i < l ? rounded(i) : 0;
+#pragma unroll
+        for (int i = 0; i < RNS_MAXL; ++i) {
+            if (i >= l) break;
+            const Mod64 m = R.m_all[i];
+            const uint64_t v = m.sub(xk[i], rns_reduce_u64(m, vp));
+            emit(i, m.redq(m.shoup_lazy(v, R.pinv[i], R.pinv_sh[i])));
+        }
     } else {
         uint64_t xs[RNS_MAXL];
 #pragma unroll
