@@ -28,7 +28,7 @@ for w in $WHAT; do
         ckks) TRAFFIC= run ckks 'rns_|ckks_' 8 python tools/tfhe_bench.py ckks --count 128 ;;
         launches)
             python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/plain_bench.log 2>&1 || { echo "plain bench failed"; continue; }
-            ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_bench_${TAG}.csv \
+            ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $OUT/launches_bench_${TAG}.csv \
                 python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_bench.log 2>&1 && echo "launches: ok" ;;
     esac
 done
