@@ -97,5 +97,53 @@ def main():
     print("wrote", os.path.join(HERE, "util_fhew.json"), os.path.getsize(os.path.join(HERE, "util_fhew.json")), "bytes")
 
 
+def main_tfhe_ckks():
+    """tests/golden/tfhe_ckks.json: the f64 FFT torus product, a TGGSW external product / CMUX, a TLWE key switch, rescale_k and a
+    whole Ckks::mul, all computed by pyref alone (no oracle, no CUDA) on seeded inputs."""
+    g = {}
+    M = 1 << 64
+    ff = []
+    for n, log_b in ((2, 8), (8, 8), (16, 23), (64, 12)):
+        a = rnd(300 + n, n, M)
+        b = [(x - (1 << (log_b - 1))) % M for x in rnd(400 + n, n, 1 << log_b)]
+        ff.append({"a": a, "b": b, "out": pyref.fft64_negacyclic_mul(a, b)})
+    g["fft64_mul"] = ff
+    k, d, log_b, n = 1, 2, 8, 16
+    rows = [[rnd(500 + 10 * r + c, n, M) for c in range(k + 1)] for r in range((k + 1) * d)]
+    ct0 = [rnd(600 + c, n, M) for c in range(k + 1)]
+    ct1 = [rnd(610 + c, n, M) for c in range(k + 1)]
+    g["tggsw"] = {"k": k, "d": d, "log_b": log_b, "n": n, "rows": rows, "ct0": ct0, "ct1": ct1,
+                  "external_product": pyref.tggsw_external_product(log_b, d, rows, ct0), "cmux": pyref.tggsw_cmux(log_b, d, rows, ct0, ct1)}
+    kn, n_out, ks_log_b, ks_d = 16, 5, 4, 5
+    ksk_a = [rnd(700 + i, n_out, M) for i in range(kn * ks_d)]
+    ksk_b = rnd(799, kn * ks_d, M)
+    a, b = rnd(800, kn, M), rnd(801, 1, M)[0]
+    oa, ob = pyref.tlwe_key_switch(ks_log_b, ks_d, ksk_a, ksk_b, a, b)
+    g["tlwe_key_switch"] = {"log_b": ks_log_b, "d": ks_d, "ksk_a": ksk_a, "ksk_b": ksk_b, "a": a, "b": b, "out": oa + [ob]}
+    primes = pyref.two_adic_primes(55, 4, 6)
+    rs = []
+    for nq, kk in ((4, 1), (6, 3), (5, 2)):
+        qs = primes[:nq]
+        x = [[rnd(900 + 7 * nq + i, 1, q)[0] for i, q in enumerate(qs)] for _ in range(6)] + [[q - 1 for q in qs], [0] * nq]
+        rs.append({"qs": qs, "k": kk, "x": x, "out": [pyref.rns_rescale_k(qs, kk, c) for c in x]})
+    g["rns_rescale_k"] = rs
+    n, big_l = 8, 3
+    qs, ps = primes[:big_l], primes[big_l:2 * big_l]
+    mods = qs + ps
+    rlk_b = [rnd(1000 + i, n, q) for i, q in enumerate(mods)]
+    rlk_a = [rnd(1010 + i, n, q) for i, q in enumerate(mods)]
+    ct0 = ([rnd(1020 + i, n, q) for i, q in enumerate(qs)], [rnd(1030 + i, n, q) for i, q in enumerate(qs)])
+    ct1 = ([rnd(1040 + i, n, q) for i, q in enumerate(qs)], [rnd(1050 + i, n, q) for i, q in enumerate(qs)])
+    pb, pa = pyref.ckks_mul(qs, ps, rlk_b, rlk_a, ct0, ct1)
+    sb, sa = pyref.ckks_key_switch(qs, ps, rlk_b, rlk_a, ct0[0], ct0[1])
+    g["ckks"] = {"log_n": 3, "qs": qs, "ps": ps, "ksk": [rlk_b, rlk_a], "ct0": [ct0[0], ct0[1]], "ct1": [ct1[0], ct1[1]],
+                 "mul": [pb, pa], "key_switch_ct0": [sb, sa]}
+    path = os.path.join(HERE, "tfhe_ckks.json")
+    with open(path, "w") as fh:
+        json.dump(g, fh, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
+    main_tfhe_ckks()

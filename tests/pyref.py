@@ -20,7 +20,11 @@ def zq_center_u64(q, v):  # zq.rs:83-89 (two's complement in a u64)
 
 
 def rust_round(x):  # f64::round: half away from zero
-    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+    if abs(x) >= 2.0 ** 52:  # already an integer (x + 0.5 would round to even there)
+        return x
+    f = math.floor(abs(x))
+    r = f + 1 if abs(x) - f >= 0.5 else f  # abs(x) - f is exact
+    return r if x >= 0 else -r
 
 
 def zq_from_f64(q, x):  # zq.rs:59-61
@@ -339,3 +343,175 @@ def rns_extend_bases(qs, ps, x):
         acc = sum((qh % p) * vi for qh, vi in zip(q_hats, vs)) % p
         out.append((acc - u * (big_q % p)) % p)
     return out
+
+
+def rns_rescale_k(qs, k, x):
+    """RnsRq::rescale_k (rns.rs:99-132) on one coefficient: x = residues mod qs (kept ++ dropped); returns residues mod kept.
+    round(): every limb += (P >> 1) mod q_i; k == 1: subtract the dropped limb's non-centred value, else subtract the
+    base extension (switch_bases) of the dropped limbs; div(): multiply by P^-1 mod q_i."""
+    kept, dropped = qs[:len(qs) - k], qs[len(qs) - k:]
+    p = math.prod(dropped)
+    r = [(xi + (p >> 1) % qi) % qi for xi, qi in zip(x, qs)]
+    rk, rd = r[:len(kept)], r[len(kept):]
+    if k == 1:
+        sub = [rd[0] % qi for qi in kept]  # Zq -= u64: the value is reduced mod q_i
+    else:
+        sub = rns_extend_bases(dropped, kept, rd)[k:]
+    return [((a - b) % qi) * pow(p % qi, qi - 2, qi) % qi for a, b, qi in zip(rk, sub, kept)]
+
+
+# ---- util/src/ring/fft/c64.rs + ring/fft.rs:7-35 (f64 negacyclic product of torus polynomials) ----------------------------------
+# Every f64 operation below is a separate Python float operation (IEEE double, round to nearest, never fused), in the order of
+# num_complex 0.4.6 `Mul` (re = a.re*b.re - a.im*b.im, im = a.re*b.im + a.im*b.re) and of the reference's loops.
+def f64_mod_u64(v):  # c64.rs:69-85
+    import struct
+    bits = struct.unpack("<Q", struct.pack("<d", v))[0]
+    sign, exponent = bits >> 63, (bits >> 52) & 0x7FF
+    mantissa = ((bits << 11) | 0x8000000000000000) & 0xFFFFFFFFFFFFFFFF
+    shift = 1086 - exponent
+    if -63 <= shift <= 0:
+        value = (mantissa << -shift) & 0xFFFFFFFFFFFFFFFF
+    elif 1 <= shift <= 64:
+        value = (((mantissa >> (shift - 1)) + 1) & 0xFFFFFFFFFFFFFFFF) >> 1
+    else:
+        value = 0
+    return value if sign == 0 else (-value) & 0xFFFFFFFFFFFFFFFF
+
+
+def _cmul(a, b):
+    return (a[0] * b[0] - a[1] * b[1], a[0] * b[1] + a[1] * b[0])
+
+
+def c64_twiddle(n):  # c64.rs:98-108: cis((i as f64 * PI) / n as f64), i < n
+    return [(math.cos((float(i) * math.pi) / float(n)), math.sin((float(i) * math.pi) / float(n))) for i in range(n)]
+
+
+def fft_in_place(a, tw_bo):  # fft.rs:7-18 (Butterfly::dit: tb = t * b; a + tb, a - tb)
+    n = len(a)
+    for layer in reversed(range(n.bit_length() - 1)):
+        size = 1 << layer
+        for c in range(n // (2 * size)):
+            t = tw_bo[c]
+            for j in range(size):
+                i0, i1 = c * 2 * size + j, c * 2 * size + size + j
+                tb = _cmul(t, a[i1])
+                a[i0], a[i1] = (a[i0][0] + tb[0], a[i0][1] + tb[1]), (a[i0][0] - tb[0], a[i0][1] - tb[1])
+
+
+def ifft_in_place(a, tw_inv_bo, n_inv):  # fft.rs:22-35 (Butterfly::dif: a + b, (a - b) * t; then *= n_inv)
+    n = len(a)
+    for layer in range(n.bit_length() - 1):
+        size = 1 << layer
+        for c in range(n // (2 * size)):
+            t = tw_inv_bo[c]
+            for j in range(size):
+                i0, i1 = c * 2 * size + j, c * 2 * size + size + j
+                s = (a[i0][0] + a[i1][0], a[i0][1] + a[i1][1])
+                d = _cmul((a[i0][0] - a[i1][0], a[i0][1] - a[i1][1]), t)
+                a[i0], a[i1] = s, d
+    for i in range(n):
+        a[i] = (a[i][0] * n_inv, a[i][1] * n_inv)
+
+
+def t64_to_i64(v):  # torus.rs:20-25
+    return v - (1 << 64) if v >> 63 else v
+
+
+def fft64_negacyclic_mul(a, b):
+    """nega_cyclic_fft64_mul_assign_rt (c64.rs:11-56) on torus words (u64): returns a * b over T64[X]/(X^n + 1)."""
+    n = len(a)
+    if n == 1:
+        return [(a[0] * b[0]) & 0xFFFFFFFFFFFFFFFF]
+    m = n // 2
+    tw_n = c64_twiddle(n)   # twist: entries i < n/2 of the table for n
+    tw_m = c64_twiddle(m)   # transform of the n/2 complex points: table for n/2, bit-reversed
+    tw_bo = bit_reverse(tw_m)
+    tw_inv_bo = bit_reverse([(c, -s) for c, s in tw_m])
+
+    def twisted(x):  # formula 8 of ePrint 2021/480
+        return [_cmul((float(t64_to_i64(x[i])), float(t64_to_i64(x[i + m]))), tw_n[i]) for i in range(m)]
+
+    ca, cb = twisted(a), twisted(b)
+    fft_in_place(ca, tw_bo)
+    fft_in_place(cb, tw_bo)
+    ca = [_cmul(x, y) for x, y in zip(ca, cb)]
+    ifft_in_place(ca, tw_inv_bo, 1.0 / float(m))
+    lo, hi = [], []
+    for i in range(m):  # formula 10
+        c = _cmul(ca[i], (tw_n[i][0], -tw_n[i][1]))
+        lo.append(f64_mod_u64(c[0]))
+        hi.append(f64_mod_u64(c[1]))
+    return lo + hi
+
+
+# ---- scheme/tfhe/src ------------------------------------------------------------------------------------------------------------
+def tggsw_external_product(log_b, d, rows, glwe):
+    """Tggsw::external_product (tggsw.rs:100-112): rows[(k+1) d][k+1][N] torus words (the TGLWE rows of one TGGSW ciphertext:
+    d rows per mask polynomial a_j, then d for the body), glwe[k+1][N] = (a_0 .. a_{k-1}, b).  Every row x limb product is
+    an f64 FFT product rounded to a torus word; the sum is wrapping."""
+    n = len(glwe[0])
+    limbs = []
+    for v in glwe:  # chain![a.., b].flat_map(decompose): limb-major per polynomial (decompose.rs:137-155)
+        per = [decompose_t64(log_b, d, x) for x in v]
+        limbs += [[per[i][j] for i in range(n)] for j in range(d)]
+    out = []
+    for c in range(len(glwe)):
+        acc = [0] * n
+        for row, limb in zip(rows, limbs):
+            prod = fft64_negacyclic_mul(list(row[c]), limb)
+            acc = [(x + y) & 0xFFFFFFFFFFFFFFFF for x, y in zip(acc, prod)]
+        out.append(acc)
+    return out
+
+
+def tggsw_cmux(log_b, d, rows, ct0, ct1):  # tggsw.rs:114-121: ct0 + external_product(b, ct1 - ct0)
+    M = 0xFFFFFFFFFFFFFFFF
+    diff = [[(y - x) & M for x, y in zip(p0, p1)] for p0, p1 in zip(ct0, ct1)]
+    ext = tggsw_external_product(log_b, d, rows, diff)
+    return [[(x + y) & M for x, y in zip(p0, e)] for p0, e in zip(ct0, ext)]
+
+
+def tlwe_key_switch(log_b, d, ksk_a, ksk_b, a, b):
+    """Tlwe::key_switch (tlwe.rs:144-153): a' = ksk.a . limbs, b' = ksk.b . limbs + b over the limb-major (flattened) digits of
+    a; the key encrypts the powered-up -sk1 (tlwe.rs:100-111), so the sums are added.  Wrapping u64 arithmetic."""
+    M = 0xFFFFFFFFFFFFFFFF
+    per = [decompose_t64(log_b, d, x) for x in a]
+    digs = [per[i][j] for j in range(d) for i in range(len(a))]
+    n = len(ksk_a[0])
+    out_a = [0] * n
+    out_b = b
+    for dg, ra, rb in zip(digs, ksk_a, ksk_b):
+        out_a = [(x + dg * y) & M for x, y in zip(out_a, ra)]
+        out_b = (out_b + dg * rb) & M
+    return out_a, out_b
+
+
+# ---- scheme/ckks/src/ckks.rs -------------------------------------------------------------------------------------------------------
+def _rns_poly(f, moduli, polys):  # apply a per-coefficient RNS map to limb-major polynomials
+    n = len(polys[0])
+    cols = [f([p[i] for p in polys]) for i in range(n)]
+    return [[c[j] for c in cols] for j in range(len(cols[0]))]
+
+
+def ckks_key_switch(qs_l, ps, ksk_b, ksk_a, ct_b, ct_a):
+    """Ckks::key_switch (ckks.rs:284-293): ct_a extended to qs_l ++ ps, multiplied limb-wise with the key (given on the same
+    limbs, coefficient form), rescale_k by the special primes; b += ct_b."""
+    moduli = list(qs_l) + list(ps)
+    ext = _rns_poly(lambda x: rns_extend_bases(list(qs_l), list(ps), x), moduli, ct_a)
+    prod_b = [schoolbook_negacyclic(k, e, m) for k, e, m in zip(ksk_b, ext, moduli)]
+    prod_a = [schoolbook_negacyclic(k, e, m) for k, e, m in zip(ksk_a, ext, moduli)]
+    rb = _rns_poly(lambda x: rns_rescale_k(moduli, len(ps), x), moduli, prod_b)
+    ra = _rns_poly(lambda x: rns_rescale_k(moduli, len(ps), x), moduli, prod_a)
+    return [[(x + y) % q for x, y in zip(p, c)] for p, c, q in zip(rb, ct_b, qs_l)], ra
+
+
+def ckks_mul(qs_l, ps, rlk_b, rlk_a, ct0, ct1):
+    """Ckks::mul (ckks.rs:255-272): tensor, relinearise d2 with ct_b = 0, add, rescale by the last prime."""
+    (b0, a0), (b1, a1) = ct0, ct1
+    mul = lambda x, y: [schoolbook_negacyclic(p, r, q) for p, r, q in zip(x, y, qs_l)]
+    add = lambda x, y: [[(u + v) % q for u, v in zip(p, r)] for p, r, q in zip(x, y, qs_l)]
+    d0, d1, d2 = mul(b0, b1), add(mul(b0, a1), mul(a0, b1)), mul(a0, a1)
+    zero = [[0] * len(d2[0]) for _ in qs_l]
+    rb, ra = ckks_key_switch(qs_l, ps, rlk_b, rlk_a, zero, d2)
+    sb, sa = add(d0, rb), add(d1, ra)
+    return (_rns_poly(lambda x: rns_rescale_k(list(qs_l), 1, x), qs_l, sb), _rns_poly(lambda x: rns_rescale_k(list(qs_l), 1, x), qs_l, sa))

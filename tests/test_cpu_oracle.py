@@ -188,3 +188,79 @@ def test_golden_fhew_tiny(orc):
         out[0, -1] = (int(out[0, -1]) + g["post_add"]) % P.big_q
         assert [int(x) for x in out[0]] == c["out"]
         assert [int(x) for x in K.op(g["table"], ct)[0]] == c["out"]
+
+
+def test_oracle_matches_pyref_f64_fft_and_tfhe(orc):
+    """A11/A12: the C++ oracle against the independent pure-Python restatement of c64.rs / fft.rs / tggsw.rs / tlwe.rs:
+    every torus word identical (the f64 operation order is part of the contract)."""
+    for log_n in range(0, 7):
+        n = 1 << log_n
+        a = orc.splitmix64(0x600 + log_n, n)
+        for log_b in (8, 23):
+            dig = (orc.splitmix64(0x700 + log_n + log_b, n) % np.uint64(1 << log_b)).astype(np.int64) - (1 << (log_b - 1))
+            b = dig.astype(np.uint64)
+            assert [int(x) for x in orc.fft64_mul(a, b)] == pyref.fft64_negacyclic_mul([int(x) for x in a], [int(x) for x in b]), (log_n, log_b)
+    for v in (0.0, 0.5, -0.5, 1.5, 2.5, -2.5, 2.0 ** 52 + 1, -(2.0 ** 63), 2.0 ** 63, 2.0 ** 64, 2.0 ** 64 + 4096, 3.0 * 2.0 ** 80, -1.0e30, 1e-30):
+        exact = int(pyref.rust_round(v)) if abs(v) < 2.0 ** 53 else int(v)
+        assert pyref.f64_mod_u64(v) == exact % (1 << 64), v
+    for k, d, log_b in ((1, 2, 8), (2, 3, 6), (1, 1, 23)):
+        P = orc.tfhe_testing_param()
+        P.n, P.big_n, P.k, P.bs_log_b, P.bs_d, P.ks_log_b, P.ks_d = 3, 16, k, log_b, d, 4, 5
+        K = orc.TfheKey(P, 0x5EED0021 + k)
+        ex = K.export()
+        glwe = orc.splitmix64(5 + k, (k + 1) * P.big_n).reshape(k + 1, P.big_n)
+        other = orc.splitmix64(9 + k, (k + 1) * P.big_n).reshape(k + 1, P.big_n)
+        L = lambda m: [[int(x) for x in r] for r in m]
+        for i in range(P.n):
+            rows = [L(r) for r in ex["brk"][i]]
+            assert L(K.external_product(i, glwe)) == pyref.tggsw_external_product(log_b, d, rows, L(glwe)), (k, i)
+            cm = pyref.tggsw_cmux(log_b, d, rows, L(glwe), L(other))
+            ref = glwe + K.external_product(i, other - glwe)
+            assert L(ref) == cm
+        ct = orc.splitmix64(77 + k, k * P.big_n + 1)
+        a_out, b_out = pyref.tlwe_key_switch(P.ks_log_b, P.ks_d, L(ex["ksk_a"]), [int(x) for x in ex["ksk_b"]], [int(x) for x in ct[:-1]], int(ct[-1]))
+        assert [int(x) for x in K.key_switch(ct)] == a_out + [b_out]
+
+
+def test_oracle_matches_pyref_rns_and_ckks(orc):
+    """A13/A14: rescale_k (both branches), key switch and Ckks::mul against the pure-Python big-integer restatement of
+    rns.rs:99-132, 331-345 and ckks.rs:255-293 (polynomial products by schoolbook)."""
+    primes = orc.two_adic_primes(55, 5, 8)
+    n = 8
+    for nq, k in ((4, 1), (6, 3), (8, 4), (2, 1)):
+        qs = primes[:nq]
+        x = np.stack([orc.residues(17 * nq + i, n, q) for i, q in enumerate(qs)])
+        x[:, 0] = [q - 1 for q in qs]
+        got = orc.rns_rescale_k(qs, k, x)
+        for c in range(n):
+            assert [int(v) for v in got[:, c]] == pyref.rns_rescale_k(qs, k, [int(v) for v in x[:, c]]), (nq, k, c)
+    log_n, big_l = 3, 3
+    K = orc.CkksKey(log_n, 55, big_l, 0x5EED0031, auto_ts=(5,))
+    L = lambda m: [[int(v) for v in r] for r in m]
+    rng = np.random.default_rng(5)
+    ksk = K.ksk(-1)  # [2 (b, a)][2L (qs then ps)][N]
+    for level in (3, 2):
+        ct0 = K.encrypt(rng.integers(-1000, 1000, size=K.n, dtype=np.int64), level, 1)
+        ct1 = K.encrypt(rng.integers(-1000, 1000, size=K.n, dtype=np.int64), level, 2)
+        idx = list(range(level)) + list(range(big_l, 2 * big_l))
+        kb, ka = L(ksk[0][idx]), L(ksk[1][idx])
+        qs_l = K.qs[:level]
+        ref = K.key_switch(-1, ct0, apply_auto=False)
+        b, a = pyref.ckks_key_switch(qs_l, K.ps, kb, ka, L(ct0[0]), L(ct0[1]))
+        assert L(ref[0]) == b and L(ref[1]) == a, level
+        prod = K.mul(ct0, ct1)
+        pb, pa = pyref.ckks_mul(qs_l, K.ps, kb, ka, (L(ct0[0]), L(ct0[1])), (L(ct1[0]), L(ct1[1])))
+        assert L(prod[0]) == pb and L(prod[1]) == pa, level
+
+
+GOLD2 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tfhe_ckks.json")))
+
+
+def test_golden_tfhe_ckks_primitives(orc):
+    """tests/golden/tfhe_ckks.json (written by pyref alone): the oracle reproduces the f64 FFT products and rescale_k words."""
+    for c in GOLD2["fft64_mul"]:
+        assert [int(x) for x in orc.fft64_mul(A(c["a"]), A(c["b"]))] == c["out"]
+    for c in GOLD2["rns_rescale_k"]:
+        x = A(c["x"]).T  # [limb][coefficient]
+        got = orc.rns_rescale_k(c["qs"], c["k"], x)
+        assert [[int(v) for v in got[:, i]] for i in range(x.shape[1])] == c["out"]
