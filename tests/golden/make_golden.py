@@ -120,6 +120,20 @@ def main_tfhe_ckks():
     a, b = rnd(800, kn, M), rnd(801, 1, M)[0]
     oa, ob = pyref.tlwe_key_switch(ks_log_b, ks_d, ksk_a, ksk_b, a, b)
     g["tlwe_key_switch"] = {"log_b": ks_log_b, "d": ks_d, "ksk_a": ksk_a, "ksk_b": ksk_b, "a": a, "b": b, "out": oa + [ob]}
+    # a whole programmable bootstrap at tiny parameters: n = 4, N = 16, k = 1, TGGSW (8, 2), key switch (4, 5), p = 2^4 + padding
+    n_lwe, nb, kk, bl, bd = 4, 16, 1, 8, 2
+    brk = [[[rnd(1100 + 100 * i + 10 * r + c, nb, M) for c in range(kk + 1)] for r in range((kk + 1) * bd)] for i in range(n_lwe)]
+    pk_a = [rnd(1500 + i, n_lwe, M) for i in range(kk * nb * 5)]
+    pk_b = rnd(1599, kk * nb * 5, M)
+    v = [i % 16 for i in range(nb)]
+    cts = [rnd(1600 + i, n_lwe + 1, M) for i in range(3)]
+    cts[1][0] = 0
+    outs = []
+    for ct in cts:
+        oa, ob = pyref.tfhe_bootstrap(4, 1, kk, bl, bd, 4, 5, brk, pk_a, pk_b, v, ct)
+        outs.append(oa + [ob])
+    g["tfhe_pbs"] = {"log_p": 4, "padding": 1, "n": n_lwe, "big_n": nb, "k": kk, "bs_log_b": bl, "bs_d": bd, "ks_log_b": 4, "ks_d": 5,
+                     "brk": brk, "ksk_a": pk_a, "ksk_b": pk_b, "v": v, "cts": cts, "out": outs}
     primes = pyref.two_adic_primes(55, 4, 6)
     rs = []
     for nq, kk in ((4, 1), (6, 3), (5, 2)):

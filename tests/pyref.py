@@ -515,3 +515,28 @@ def ckks_mul(qs_l, ps, rlk_b, rlk_a, ct0, ct1):
     rb, ra = ckks_key_switch(qs_l, ps, rlk_b, rlk_a, zero, d2)
     sb, sa = add(d0, rb), add(d1, ra)
     return (_rns_poly(lambda x: rns_rescale_k(list(qs_l), 1, x), qs_l, sb), _rns_poly(lambda x: rns_rescale_k(list(qs_l), 1, x), qs_l, sa))
+
+
+def t64_rounding_shr(v, bits):  # decompose.rs:115-118 on a torus word
+    return ((v + ((1 << bits) >> 1)) & 0xFFFFFFFFFFFFFFFF) >> bits
+
+
+def tfhe_bootstrap(log_p, padding, k, bs_log_b, bs_d, ks_log_b, ks_d, brk, ksk_a, ksk_b, v, ct):
+    """Bootstrapping::bootstrap (tfhe/bootstrapping.rs:78-110): v = test polynomial over Z_p (N entries), ct = TLWE [n + 1];
+    brk[n][(k+1) d][k+1][N].  blind_rotate: acc = (0, encode(v)).rotate(-b~), then acc = cmux(brk_i, acc, acc.rotate(a~_i));
+    sample_extract(0) (tglwe.rs:115-127); Tlwe::key_switch."""
+    M = 1 << 64
+    n_big = len(v)
+    log_delta = 64 - (log_p + padding)
+    pt = [(int(m) << log_delta) % M for m in v]  # Tlwe::encode (tlwe.rs:113-116)
+    rb = 64 - (2 * n_big).bit_length() + 1
+    a = [t64_rounding_shr(x, rb) for x in ct[:-1]]
+    b = t64_rounding_shr(ct[-1], rb)
+    acc = [[0] * n_big for _ in range(k)] + [pt]
+    acc = [monomial_mul(p, -b, M) for p in acc]
+    for rows, ai in zip(brk, a):
+        acc = tggsw_cmux(bs_log_b, bs_d, rows, acc, [monomial_mul(p, ai, M) for p in acc])
+    ext_a = []
+    for p in acc[:-1]:
+        ext_a += [p[0]] + [(-x) % M for x in reversed(p[1:])]
+    return tlwe_key_switch(ks_log_b, ks_d, ksk_a, ksk_b, ext_a, acc[-1][0])

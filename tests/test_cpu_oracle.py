@@ -222,6 +222,25 @@ def test_oracle_matches_pyref_f64_fft_and_tfhe(orc):
         assert [int(x) for x in K.key_switch(ct)] == a_out + [b_out]
 
 
+def test_oracle_matches_pyref_tfhe_bootstrap(orc):
+    """A11: whole programmable bootstraps (mod switch, n exact-FFT CMUX steps, sample extract, key switch) at tiny parameters."""
+    L = lambda m: [[int(x) for x in r] for r in m]
+    for k, d, log_b in ((1, 2, 8), (2, 1, 12)):
+        P = orc.tfhe_testing_param()
+        P.n, P.big_n, P.k, P.bs_log_b, P.bs_d, P.ks_log_b, P.ks_d = 4, 16, k, log_b, d, 4, 5
+        K = orc.TfheKey(P, 0x5EED0041 + k)
+        ex = K.export()
+        cts = K.encrypt(np.arange(4, dtype=np.uint64), 9)
+        cts[1, 0] = 0  # a zero mask word (the CUDA kernel skips that CMUX; the reference computes acc + ext(0))
+        v = K.lut_poly(np.arange(1 << P.log_p, dtype=np.uint64))
+        ref = K.bootstrap(v, cts)
+        brk = [[L(r) for r in ex["brk"][i]] for i in range(P.n)]
+        for c in range(4):
+            a, b = pyref.tfhe_bootstrap(P.log_p, P.padding, k, log_b, d, P.ks_log_b, P.ks_d, brk, L(ex["ksk_a"]), [int(x) for x in ex["ksk_b"]],
+                                        [int(x) for x in v], [int(x) for x in cts[c]])
+            assert [int(x) for x in ref[c]] == a + [b], (k, c)
+
+
 def test_oracle_matches_pyref_rns_and_ckks(orc):
     """A13/A14: rescale_k (both branches), key switch and Ckks::mul against the pure-Python big-integer restatement of
     rns.rs:99-132, 331-345 and ckks.rs:255-293 (polynomial products by schoolbook)."""

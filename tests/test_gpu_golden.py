@@ -40,6 +40,17 @@ def test_tggsw_and_tlwe_fixture(pkg, ctx):
     bk.free()
 
 
+def test_programmable_bootstrap_fixture(pkg, ctx):
+    from learn_fhe_b200 import tfhe
+    g = GOLD["tfhe_pbs"]
+    param = pkg.TfheParam(log_p=g["log_p"], padding=g["padding"], n=g["n"], ks_log_b=g["ks_log_b"], ks_d=g["ks_d"],
+                          log_big_n=g["big_n"].bit_length() - 1, k=g["k"], bs_log_b=g["bs_log_b"], bs_d=g["bs_d"])
+    bk = tfhe.BootstrappingKey(ctx, param, A(g["brk"]), A(g["ksk_a"]), A(g["ksk_b"]))
+    got = tfhe.Bootstrapping.bootstrap(bk, tfhe.encode_lut(bk.param, A(g["v"])), A(g["cts"]))
+    assert got.tolist() == g["out"]
+    bk.free()
+
+
 def test_rescale_and_ckks_fixture(pkg, ctx):
     from learn_fhe_b200 import ckks
     for c in GOLD["rns_rescale_k"]:
