@@ -150,8 +150,17 @@ def main_tfhe_ckks():
     ct1 = ([rnd(1040 + i, n, q) for i, q in enumerate(qs)], [rnd(1050 + i, n, q) for i, q in enumerate(qs)])
     pb, pa = pyref.ckks_mul(qs, ps, rlk_b, rlk_a, ct0, ct1)
     sb, sa = pyref.ckks_key_switch(qs, ps, rlk_b, rlk_a, ct0[0], ct0[1])
+    # rotation by t = 5, plaintext product, and a 2 x 2 BSGS matrix product (one absent diagonal) with two more keys
+    keys = [([rnd(1200 + 20 * w + i, n, q) for i, q in enumerate(mods)], [rnd(1210 + 20 * w + i, n, q) for i, q in enumerate(mods)]) for w in range(2)]
+    rot5 = pyref.ckks_rotate(qs, ps, 5, keys[0][0], keys[0][1], ct0[0], ct0[1])
+    pts = [[rnd(1300 + 10 * j + i, n, q) for i, q in enumerate(qs)] for j in range(3)]
+    mc = pyref.ckks_mul_constant(qs, pts[0], ct0[0], ct0[1])
+    baby, giant, present = [(0, None), (5, keys[0])], [(0, None), (2 * n - 1, keys[1])], [[1, 1], [0, 1]]
+    mm = pyref.ckks_mul_mat(qs, ps, baby, giant, present, pts, ct0[0], ct0[1])
     g["ckks"] = {"log_n": 3, "qs": qs, "ps": ps, "ksk": [rlk_b, rlk_a], "ct0": [ct0[0], ct0[1]], "ct1": [ct1[0], ct1[1]],
-                 "mul": [pb, pa], "key_switch_ct0": [sb, sa]}
+                 "mul": [pb, pa], "key_switch_ct0": [sb, sa], "rot_keys": [[k[0], k[1]] for k in keys], "rotate5_ct0": [rot5[0], rot5[1]],
+                 "pts": pts, "mul_constant_pt0_ct0": [mc[0], mc[1]], "mul_mat": {"baby_t": [0, 5], "giant_t": [0, 2 * n - 1], "present": present,
+                                                                              "out": [mm[0], mm[1]]}}
     path = os.path.join(HERE, "tfhe_ckks.json")
     with open(path, "w") as fh:
         json.dump(g, fh, separators=(",", ":"))

@@ -540,3 +540,40 @@ def tfhe_bootstrap(log_p, padding, k, bs_log_b, bs_d, ks_log_b, ks_d, brk, ksk_a
     for p in acc[:-1]:
         ext_a += [p[0]] + [(-x) % M for x in reversed(p[1:])]
     return tlwe_key_switch(ks_log_b, ks_d, ksk_a, ksk_b, ext_a, acc[-1][0])
+
+
+def ckks_rotate(qs_l, ps, t, ksk_b, ksk_a, ct_b, ct_a):
+    """Ckks::rotate / conjugate (ckks.rs:274-282): X -> X^t on both polynomials (limb-wise, avec.rs:34-50), then key_switch."""
+    rb = [automorphism(p, t, q) for p, q in zip(ct_b, qs_l)]
+    ra = [automorphism(p, t, q) for p, q in zip(ct_a, qs_l)]
+    return ckks_key_switch(qs_l, ps, ksk_b, ksk_a, rb, ra)
+
+
+def ckks_mul_constant(qs_l, pt, ct_b, ct_a):
+    """Ckks::mul_constant (ckks.rs:250-253) on an already encoded plaintext pt [l][N]: (pt * b, pt * a).rescale()."""
+    mul = lambda x: [schoolbook_negacyclic(p, r, q) for p, r, q in zip(pt, x, qs_l)]
+    res = lambda x: _rns_poly(lambda c: rns_rescale_k(list(qs_l), 1, c), qs_l, x)
+    return res(mul(ct_b)), res(mul(ct_a))
+
+
+def ckks_mul_mat(qs_l, ps, baby, giant, present, pts, ct_b, ct_a):
+    """Bootstrapping::mul_mat (ckks/src/bootstrapping.rs:92-108): baby / giant = [(t, (ksk_b, ksk_a) or None)], pts = encoded
+    diagonals in row-major (i, j) order of the present pairs.  out = sum_i rot_{g_i}(sum_j mul_constant(pt_ij, rot_{b_j}(ct)))."""
+    rot = lambda t, key, b, a: (b, a) if t == 0 else ckks_rotate(qs_l if len(b) == len(qs_l) else qs_l[:len(b)], ps, t, key[0], key[1], b, a)
+    add = lambda x, y, mods: [[(u + v) % q for u, v in zip(p, r)] for p, r, q in zip(x, y, mods)]
+    rots = [rot(t, key, ct_b, ct_a) for t, key in baby]
+    lower = qs_l[:-1]
+    out, it = None, iter(pts)
+    for i, (t, key) in enumerate(giant):
+        inner = None
+        for j in range(len(baby)):
+            if not present[i][j]:
+                continue
+            term = ckks_mul_constant(qs_l, next(it), rots[j][0], rots[j][1])
+            inner = term if inner is None else (add(inner[0], term[0], lower), add(inner[1], term[1], lower))
+        if t != 0:  # keys restricted to the limbs that remain after the rescale
+            kb = [key[0][x] for x in list(range(len(lower))) + list(range(len(qs_l), len(qs_l) + len(ps)))]
+            ka = [key[1][x] for x in list(range(len(lower))) + list(range(len(qs_l), len(qs_l) + len(ps)))]
+            inner = ckks_rotate(lower, ps, t, kb, ka, inner[0], inner[1])
+        out = inner if out is None else (add(out[0], inner[0], lower), add(out[1], inner[1], lower))
+    return out

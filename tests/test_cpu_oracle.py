@@ -270,6 +270,16 @@ def test_oracle_matches_pyref_rns_and_ckks(orc):
         prod = K.mul(ct0, ct1)
         pb, pa = pyref.ckks_mul(qs_l, K.ps, kb, ka, (L(ct0[0]), L(ct0[1])), (L(ct1[0]), L(ct1[1])))
         assert L(prod[0]) == pb and L(prod[1]) == pa, level
+        rk = K.ksk(0)  # rotation key for t = 5
+        rot = K.key_switch(0, ct0, apply_auto=True)
+        rb, ra = pyref.ckks_rotate(qs_l, K.ps, 5, L(rk[0][idx]), L(rk[1][idx]), L(ct0[0]), L(ct0[1]))
+        assert L(rot[0]) == rb and L(rot[1]) == ra, level
+        if level >= 2:
+            pt = [[int(v) for v in rng.integers(0, q, size=K.n, dtype=np.uint64)] for q in qs_l]
+            limb = np.stack([np.stack([orc.ntt_mul(q, ct0[h, t], A(pt[t])) for t, q in enumerate(qs_l)]) for h in range(2)])
+            mc = K.rescale(limb)
+            mb, ma = pyref.ckks_mul_constant(qs_l, pt, L(ct0[0]), L(ct0[1]))
+            assert L(mc[0]) == mb and L(mc[1]) == ma, level
 
 
 GOLD2 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tfhe_ckks.json")))

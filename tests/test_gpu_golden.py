@@ -63,5 +63,14 @@ def test_rescale_and_ckks_fixture(pkg, ctx):
     ct0, ct1 = A(g["ct0"])[None], A(g["ct1"])[None]
     assert ckks.Ckks.mul(P, rlk, ct0, ct1)[0].tolist() == g["mul"]
     assert ckks.Ckks.key_switch(P, rlk, ct0, 0)[0].tolist() == g["key_switch_ct0"]
+    keys = [ckks.CkksKeySwitchingKey(P, A(k)) for k in g["rot_keys"]]
+    assert ckks.Ckks.key_switch(P, keys[0], ct0, 5)[0].tolist() == g["rotate5_ct0"]
+    assert ckks.Ckks.mul_constant(P, A(g["pts"][0]), ct0)[0].tolist() == g["mul_constant_pt0_ct0"]
+    mm = g["mul_mat"]
+    baby = [(t, keys[0] if t else None) for t in mm["baby_t"]]
+    giant = [(t, keys[1] if t else None) for t in mm["giant_t"]]
+    assert ckks.Ckks.mul_mat(P, baby, giant, np.array(mm["present"], dtype=np.uint8), A(g["pts"]), ct0)[0].tolist() == mm["out"]
+    for k in keys:
+        k.free()
     rlk.free()
     P.free()
