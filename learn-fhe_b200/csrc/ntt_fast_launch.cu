@@ -6,6 +6,7 @@
 //                            inverse stages), coalesced along the row direction.
 // Replaces util/src/ring/fft/zq.rs:27-36 (+ ring/fft.rs:40-77) for every caller: fhe_ntt_*, CKKS limb batches, key
 // upload.  Moduli outside the lazy-reduction preconditions fall back to the generic kernels (ntt_launch.cu).
+#include <atomic>
 #include <cstdlib>
 #include <algorithm>
 
@@ -154,10 +155,12 @@ static fhe_status launch_fast_tile(fhe_ctx* ctx, FastArgs<L>& a) {
     typedef FastGeom<L, LOGT> G;
     auto kern = ntt_fast_tile_kernel<L, LOGT, FWD, FINAL>;
     const size_t smem = (size_t)G::PB * sizeof(typename L::W) << LOGT;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device: remember which devices of this process already have it (one bit per device ordinal)
+    static std::atomic<uint64_t> attr_done{0};
+    const uint64_t dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_done.load(std::memory_order_relaxed) & dev_bit)) {
         FHE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_done.fetch_or(dev_bit, std::memory_order_relaxed);
     }
     const unsigned long long grid = (a.n_items + G::PB - 1) / G::PB;
     if (grid == 0) return FHE_OK;

@@ -1,4 +1,5 @@
 // Launch logic + C ABI for the batched negacyclic NTT (fhe_ntt_*), host-slice wrappers included.
+#include <atomic>
 #include <algorithm>
 #include <cstdlib>
 
@@ -27,10 +28,12 @@ static fhe_status launch_tile(fhe_ctx* ctx, NttArgs<A>& a) {
     const size_t smem = sizeof(W) << a.c;
     int threads = std::max(32, std::min(1024, (1 << a.c) / 8));
     auto kern = ntt_tile_kernel<A, FWD>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device: remember which devices of this process already have it (one bit per device ordinal)
+    static std::atomic<uint64_t> attr_done{0};
+    const uint64_t dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_done.load(std::memory_order_relaxed) & dev_bit)) {
         FHE_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_done.fetch_or(dev_bit, std::memory_order_relaxed);
     }
     int occ = 1;
     FHE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
