@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINB) fhew_blind_rotate_fast_ke
             if (tid == 0) atomicExch(err, 1);
             ns = 0;
         }
-        for (uint32_t s = 0; s < ns; ++s) ff_step(P, S, steps[s], s + 1 == ns || ff_step_is_auto(steps[s + 1]), run);
+        ff_run_steps(P, S, steps, ns, run);
         const uint32_t* acc = S.acc;
         if (mode == 0) {
             ff_extract(P, acc, post_add, out + ct * (FF_N + 1), tid);

@@ -98,6 +98,27 @@ HD uint32_t ff_dec_step(const FhewFastDev& P, const DecompParam& dp, uint32_t& x
 }
 // Thread (g, h) holds the 8 coefficients at positions g + 64 j (values from acc_in[h] for an external product, from the
 // permuted a(X^t) for an automorphism) and walks the digits; digit k becomes polynomial `pbase + k` if lo <= k < hi.
+// where thread g parks coefficient g + 64 j of b(X^t) during an automorphism step: slot 7 at the SAME swizzled address the
+// thread itself uses for its digit stores, so that a later P1 writing slot 7 (fused with this step's P5) only ever overwrites
+// words its own thread has already consumed
+HD uint32_t ff_park(uint32_t g, int j) { return 7u * FF_N + (swzf(g) ^ swzf((uint32_t)j << 6)); }
+// digit walk of P1 on decomposition states st[8] (positions g + 64 j): digit k becomes polynomial `pbase + k` if lo <= k < hi
+HD void ff_p1_digits(const FhewFastDev& P, const FhewFastSmem& S, const DecompParam& dp, uint32_t* st, uint32_t g, uint32_t lo, uint32_t hi,
+                     uint32_t pbase) {
+    const uint32_t P0 = swzf(g);
+#pragma unroll 1
+    for (uint32_t k = 0; k < dp.d; ++k) {
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = ff_dec_step(P, dp, st[j]);
+        if (k >= lo && k < hi) {
+            fast_fwd_regs<Lz32, 3, FF_TW_NC != 0>(P.m, x, S.tw, 1u);
+            uint32_t* d = S.dig + ((pbase + k) << FF_LOGN);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[P0 ^ swzf((uint32_t)j << 6)] = x[j];
+        }
+    }
+}
 HD void ff_p1(const FhewFastDev& P, const FhewFastSmem& S, const DecompParam& dp, const uint32_t* acc_in, bool is_auto, uint32_t tinv,
               uint32_t g, uint32_t h, uint32_t lo, uint32_t hi, uint32_t pbase) {
     uint32_t st[8];
@@ -116,21 +137,9 @@ HD void ff_p1(const FhewFastDev& P, const FhewFastSmem& S, const DecompParam& dp
     }
     if (is_auto && h == 1) {  // park b(X^t) for P5: the accumulator is updated in place
 #pragma unroll
-        for (int j = 0; j < 8; ++j) S.dig[7 * FF_N + g + 64u * j] = ff_perm_coef(P, acc_in + FF_N, tinv, g + 64u * j);
+        for (int j = 0; j < 8; ++j) S.dig[ff_park(g, j)] = ff_perm_coef(P, acc_in + FF_N, tinv, g + 64u * j);
     }
-    const uint32_t P0 = swzf(g);
-#pragma unroll 1
-    for (uint32_t k = 0; k < dp.d; ++k) {
-        uint32_t x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = ff_dec_step(P, dp, st[j]);
-        if (k >= lo && k < hi) {
-            fast_fwd_regs<Lz32, 3, FF_TW_NC != 0>(P.m, x, S.tw, 1u);
-            uint32_t* d = S.dig + ((pbase + k) << FF_LOGN);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d[P0 ^ swzf((uint32_t)j << 6)] = x[j];
-        }
-    }
+    ff_p1_digits(P, S, dp, st, g, lo, hi, pbase);
 }
 // ---- P2: forward radix-16 pass (stages 3..6, stride 4) on polynomial `poly`, group `grp` in [0, 32) ------------------------------
 HD void ff_p2(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32_t grp) {
@@ -215,8 +224,9 @@ HD void ff_p4(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32
     for (int j = 0; j < 16; ++j) d[P0 ^ swzf((uint32_t)j << 2)] = x[j];
 }
 // ---- P5: inverse radix-8 pass (stages 2..0, n^-1 folded) of polynomial h, canonical result (+ add(j)) -> acc_out[h][g + 64 j] -------
+// v[j] = canonical coefficient g + 64 j of result polynomial h
 template <typename Add>
-HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, uint32_t g, uint32_t h, bool do_add, Add add) {
+HD void ff_p5_regs(const FhewFastDev& P, const FhewFastSmem& S, uint32_t g, uint32_t h, bool do_add, Add add, uint32_t* v) {
     const uint32_t P0 = swzf(g);
     const uint32_t* d = S.dig + ((h * FF_RB) << FF_LOGN);
     uint32_t x[8];
@@ -225,13 +235,19 @@ HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, ui
     fast_inv_regs<Lz32, 3, true, FF_TW_NC != 0>(P.m, x, S.itw, 1u, P.ninv, P.wninv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        uint32_t v = P.m.inv_canon(x[j]);
+        v[j] = P.m.inv_canon(x[j]);
         if (do_add) {
-            v = alu_add(v, add(j));
-            v = umin_(v, v - P.m.q);
+            v[j] = alu_add(v[j], add(j));
+            v[j] = umin_(v[j], v[j] - P.m.q);
         }
-        acc_out[(h << FF_LOGN) + g + 64u * j] = v;
     }
+}
+template <typename Add>
+HD void ff_p5(const FhewFastDev& P, const FhewFastSmem& S, uint32_t* acc_out, uint32_t g, uint32_t h, bool do_add, Add add) {
+    uint32_t v[8];
+    ff_p5_regs(P, S, g, h, do_add, add, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc_out[(h << FF_LOGN) + g + 64u * j] = v[j];
 }
 
 // One step on the accumulator S.acc (updated in place) as five phases.  Threads 0..63 form half 0, threads 64..127 half 1.
@@ -297,19 +313,50 @@ HD void ff_phase4(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, 
 HD void ff_phase5(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) {
     const uint32_t g = tid & 63u, h = tid >> 6;
     // key switch adds the (permuted) body: b' = sum ksk.b_k * limb_k + b(X^t)   (rlwe.rs:184)
-    ff_p5(P, S, S.acc, g, h, s.is_auto && h == 1, [&](int j) { return S.dig[7 * FF_N + g + 64u * j]; });
+    ff_p5(P, S, S.acc, g, h, s.is_auto && h == 1, [&](int j) { return S.dig[ff_park(g, j)]; });
 }
-// run(phase, scope): phase(tid) for every thread of the CTA, then a barrier of the given scope.  `first` = no earlier step
-// of this blind rotation (the caller has just executed a full barrier); `next_full` = the barrier after P5 must be a full
-// one (the next step is an automorphism, or there is no next step).
+// P5 of step `s` fused with P1 of the NEXT step `nx` when that one is an external product: thread (g, h) decomposes exactly the
+// coefficients g + 64 j of acc[h] that it has just produced, so they stay in registers - no barrier, no shared-memory round
+// trip, and acc itself is not written (nobody reads it before the next P5 rewrites it).  P5 reads result slot h FF_RB and P1
+// writes slots [h d, (h + 1) d) at the thread's own 8 positions only, all loads of the slot come first.
+HD void ff_phase51(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, const FfStep& nx, uint32_t tid) {
+    const uint32_t g = tid & 63u, h = tid >> 6;
+    uint32_t v[8];
+    ff_p5_regs(P, S, g, h, s.is_auto && h == 1, [&](int j) { return S.dig[ff_park(g, j)]; }, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ff_dec_start(P, P.g_dec, v[j]);
+    ff_p1_digits(P, S, P.g_dec, v, g, 0u, nx.d, h * nx.d);
+}
+// run(phase, scope): phase(tid) for every thread of the CTA, then a barrier of the given scope.  The caller has executed a
+// full barrier after initialising S.acc; a full barrier follows the last phase.
 template <typename Run>
-HD void ff_step(const FhewFastDev& P, const FhewFastSmem& S, uint32_t step, bool next_full, Run run) {
-    const FfStep s = ff_decode(P, step);
+HD void ff_run_steps(const FhewFastDev& P, const FhewFastSmem& S, const uint16_t* steps, uint32_t ns, Run run) {
+    if (ns == 0) return;
+    FfStep s = ff_decode(P, steps[0]);
     run([&](uint32_t tid) { ff_phase1(P, S, s, tid); }, FF_SYNC_HALF);
-    run([&](uint32_t tid) { ff_phase2(P, S, s, tid); }, FF_SYNC_FULL);
-    run([&](uint32_t tid) { ff_phase3(P, S, s, tid); }, FF_SYNC_FULL);
-    run([&](uint32_t tid) { ff_phase4(P, S, s, tid); }, FF_SYNC_HALF);
-    run([&](uint32_t tid) { ff_phase5(P, S, s, tid); }, next_full ? FF_SYNC_FULL : FF_SYNC_HALF);
+    for (uint32_t i = 0; i < ns; ++i) {
+        run([&](uint32_t tid) { ff_phase2(P, S, s, tid); }, FF_SYNC_FULL);
+        run([&](uint32_t tid) { ff_phase3(P, S, s, tid); }, FF_SYNC_FULL);
+        run([&](uint32_t tid) { ff_phase4(P, S, s, tid); }, FF_SYNC_HALF);
+        if (i + 1 == ns) {
+            run([&](uint32_t tid) { ff_phase5(P, S, s, tid); }, FF_SYNC_FULL);
+            break;
+        }
+        const FfStep nx = ff_decode(P, steps[i + 1]);
+        if (nx.is_auto) {  // the automorphism reads both halves of acc
+            run([&](uint32_t tid) { ff_phase5(P, S, s, tid); }, FF_SYNC_FULL);
+            run([&](uint32_t tid) { ff_phase1(P, S, nx, tid); }, FF_SYNC_HALF);
+        } else {
+            run([&](uint32_t tid) { ff_phase51(P, S, s, nx, tid); }, FF_SYNC_HALF);
+        }
+        s = nx;
+    }
+}
+// one isolated step (tests, util-level callers)
+template <typename Run>
+HD void ff_step(const FhewFastDev& P, const FhewFastSmem& S, uint32_t step, Run run) {
+    const uint16_t one = (uint16_t)step;
+    ff_run_steps(P, S, &one, 1u, run);
 }
 HD bool ff_step_is_auto(uint32_t step) { return (step & FHEW_STEP_AUTO) != 0; }
 
