@@ -408,6 +408,7 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     const uint64_t q = pp->big_q;
     FhewDev& P = key->P;
     if (!wide) P.m = make_mod<Mod32>(q);
+    P.lazy = 0;
     P.log_n = (int)pp->log_n;
     P.n_s = pp->n_s;
     P.w = pp->w;
@@ -431,6 +432,8 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
         W.g_dec = P.g_dec;
         W.r_dec = P.r_dec;
         W.small_digits = P.small_digits;
+        W.lazy = q < (1ull << 56) ? 1u : 0u;
+        W.lz = make_lz64(q);
         W.tw = (const TwPair<uint64_t>*)t->d_fwd;
         W.itw = (const TwPair<uint64_t>*)t->d_inv;
         W.ninv = make_twpair<uint64_t>(ninv, q);

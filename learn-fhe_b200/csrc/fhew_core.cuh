@@ -15,6 +15,7 @@
 
 #include "modarith.cuh"
 #include "ntt_core.cuh"
+#include "ntt_fast.cuh"
 
 namespace fhe {
 
@@ -161,8 +162,44 @@ struct FhewDevT {
     const KeyPair<W>* ak;   // [w+1][r_d][N] of {a, b} in evaluation form
     const uint16_t* dlog;
     uint32_t ak_t[40];  // automorphism exponents t mod 2N for ak[0..w]
+    // 64-bit moduli below 2^56: the transforms use the lazy butterflies of the fast NTT path (ntt_fast.cuh: no reduction in
+    // the forward direction - at most (1 + 4 log N) q < 128 q -, one Barrett per pass on the sum chain in the inverse)
+    uint32_t lazy;
+    Lz64 lz;
 };
 typedef FhewDevT<Mod32> FhewDev;
+template <int R>
+HD void fhew_fwd_group_lz(const Lz64& m, uint64_t* s, int c, int t0, uint32_t g, const TwPair<uint64_t>* __restrict__ tw) {
+    const int L = c - t0 - R;
+    const uint32_t lo = g & ((1u << L) - 1u), hi = g >> L;
+    const uint32_t base = (hi << (L + R)) | lo;
+    uint64_t x[1 << R];
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) x[j] = s[swz<uint64_t>(base | ((uint32_t)j << L))];
+    fast_fwd_regs<Lz64, R>(m, x, tw, (1u << t0) + hi);
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) s[swz<uint64_t>(base | ((uint32_t)j << L))] = x[j];
+}
+// pass invariant: every value < 16 q on entry and on exit; LAST (t0 == 0): n^-1 folded, canonical results
+template <int R, bool LAST>
+HD void fhew_inv_group_lz(const Lz64& m, uint64_t* s, int c, int t0, uint32_t g, const TwPair<uint64_t>* __restrict__ itw, TwPair<uint64_t> ninv,
+                          TwPair<uint64_t> wninv) {
+    const int L = c - t0 - R;
+    const uint32_t lo = g & ((1u << L) - 1u), hi = g >> L;
+    const uint32_t base = (hi << (L + R)) | lo;
+    uint64_t x[1 << R];
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) x[j] = s[swz<uint64_t>(base | ((uint32_t)j << L))];
+    fast_inv_regs<Lz64, R, LAST>(m, x, itw, (1u << t0) + hi, ninv, wninv);
+    if (LAST) {
+#pragma unroll
+        for (int j = 0; j < (1 << R); ++j) x[j] = m.inv_canon(x[j]);
+    } else {
+        x[0] = m.inv_pass_fix(x[0]);
+    }
+#pragma unroll
+    for (int j = 0; j < (1 << R); ++j) s[swz<uint64_t>(base | ((uint32_t)j << L))] = x[j];
+}
 
 // Shared-memory working set of one accumulator (all polynomials swizzled with swz<W>):
 //   acc_a[N], acc_b[N]   coefficient form, canonical
@@ -223,6 +260,12 @@ HD void fhew_fwd_pass(const FhewDevT<M>& P, typename M::W* polys, uint32_t npoly
     const uint32_t total = npoly << lg_groups;
     for (uint32_t u = tid; u < total; u += nthr) {
         const uint32_t poly = u >> lg_groups, g = u & ((1u << lg_groups) - 1u);
+        if constexpr (sizeof(typename M::W) == 8) {
+            if (P.lazy) {
+                fhew_fwd_group_lz<R>(P.lz, polys + ((size_t)poly << c), c, t0, g, P.tw);
+                continue;
+            }
+        }
         fwd_tile_group<M, R>(P.m, polys + ((size_t)poly << c), c, t0, 0, 0, g, P.tw);
     }
 }
@@ -233,6 +276,12 @@ HD void fhew_inv_pass(const FhewDevT<M>& P, typename M::W* polys, uint32_t npoly
     const uint32_t total = npoly << lg_groups;
     for (uint32_t u = tid; u < total; u += nthr) {
         const uint32_t poly = u >> lg_groups, g = u & ((1u << lg_groups) - 1u);
+        if constexpr (sizeof(typename M::W) == 8) {
+            if (P.lazy) {
+                fhew_inv_group_lz<R, LAST>(P.lz, polys + ((size_t)poly << c), c, t0, g, P.itw, P.ninv, P.wninv);
+                continue;
+            }
+        }
         inv_tile_group<M, R, LAST>(P.m, polys + ((size_t)poly << c), c, t0, 0, 0, g, P.itw, P.ninv, P.wninv);
     }
 }
@@ -288,7 +337,7 @@ HD void fhew_phase_mac(const FhewDevT<M>& P, typename M::W* smem, const KeyPair<
             W sa = 0, sb = 0;
             for (uint32_t k = 0; k < rows; ++k) {
                 const KeyPair<W> kv = key[(size_t)k * n + i];
-                const W dg = P.m.canon4(dig[(size_t)k * n + si]);
+                const W dg = P.lazy ? P.lz.canon(dig[(size_t)k * n + si]) : P.m.canon4(dig[(size_t)k * n + si]);
                 sa = P.m.add(sa, P.m.mul(kv.x, dg));
                 sb = P.m.add(sb, P.m.mul(kv.y, dg));
             }

@@ -110,12 +110,14 @@ def test_kernel_logic_fhew(H, orc, fhew_setup):
     H.sim_fhew_key_free(h)
 
 
-def test_kernel_logic_fhew_64bit_modulus(H, orc):
+@pytest.mark.parametrize("bits", [55, 60])
+def test_kernel_logic_fhew_64bit_modulus(H, orc, bits):
     """The generic FHEW kernels instantiated for a 64-bit modulus (fhew.cu `wide`: the parameter shape of
     examples/multi_key_uint8.rs:15-29 - 55-bit Q, decomposors (11, 5), LWE q = 2^20 - at N = 64): single steps, the LWE
-    prologue and whole gate bootstraps against the oracle, bit-exact."""
+    prologue and whole gate bootstraps against the oracle, bit-exact.  55 bits: lazy butterflies of the fast NTT path
+    (Q < 2^56); 60 bits: the generic per-butterfly reductions."""
     P = orc.fhew_testing_param()
-    P.log_n, P.big_q = 6, orc.two_adic_primes(55, 7, 1)[0]
+    P.log_n, P.big_q = 6, orc.two_adic_primes(bits, 7, 1)[0]
     P.rlwe_log_b = P.rgsw_log_b = 11
     P.rlwe_d = P.rgsw_d = 5
     P.n_s, P.q_ks, P.ks_log_b, P.ks_d, P.w = 12, 1 << 20, 4, 5, 10

@@ -174,11 +174,11 @@ def test_host_path_pipelining_matches_device_path(pkg, ctx, orc, fhew_setup):
 
 
 # ---- 64-bit modulus path (the parameter shape of examples/multi_key_uint8.rs:15-29) -------------------
-def _wide_setup(pkg, ctx, orc, log_n, n_s, seed):
+def _wide_setup(pkg, ctx, orc, log_n, n_s, seed, bits=55):
     """55-bit Q = two_adic_primes(55, log_n + 1).next(), RLWE / RGSW decomposor (11, 5), LWE q = 2^20 with (4, 5), w = 10."""
     from learn_fhe_b200 import fhew
     P = orc.fhew_testing_param()
-    P.log_n, P.big_q = log_n, orc.two_adic_primes(55, log_n + 1, 1)[0]
+    P.log_n, P.big_q = log_n, orc.two_adic_primes(bits, log_n + 1, 1)[0]
     P.rlwe_log_b = P.rgsw_log_b = 11
     P.rlwe_d = P.rgsw_d = 5
     P.n_s, P.q_ks, P.ks_log_b, P.ks_d, P.w = n_s, 1 << 20, 4, 5, 10
@@ -190,10 +190,11 @@ def _wide_setup(pkg, ctx, orc, log_n, n_s, seed):
     return P, K, param, key
 
 
-@pytest.mark.parametrize("log_n", [5, 8])
-def test_wide_modulus_steps_and_gates_reduced(pkg, ctx, orc, log_n):
+@pytest.mark.parametrize("log_n,bits", [(5, 55), (8, 55), (7, 60)])
+def test_wide_modulus_steps_and_gates_reduced(pkg, ctx, orc, log_n, bits):
+    """55-bit Q runs the lazy 64-bit butterflies (Q < 2^56), 60-bit Q the generic ones."""
     from learn_fhe_b200 import fhew
-    P, K, param, key = _wide_setup(pkg, ctx, orc, log_n, 24, 0x5EED0009)
+    P, K, param, key = _wide_setup(pkg, ctx, orc, log_n, 24, 0x5EED0009, bits)
     count = 6
     acc = orc.residues(19, count * 2 * P.n, P.big_q).reshape(count, 2, P.n)
     acc[0, 0, :3] = [0, P.big_q - 1, P.big_q // 2]
