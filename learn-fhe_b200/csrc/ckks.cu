@@ -177,14 +177,14 @@ __global__ void __launch_bounds__(256) ckks_keymul_kernel(const Mod64* __restric
 }
 // plaintext x ciphertext in the evaluation domain: e [C][2][l][n] *= pe [1 or C][l][n] (limb-wise)   (ckks.rs:250-253)
 __global__ void __launch_bounds__(256) ckks_ptmul_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long count, int pt_per_ct,
-                                                         const uint64_t* __restrict__ pe, uint64_t* __restrict__ e) {
+                                                         const uint64_t* __restrict__ pe, const uint64_t* src /* may be e */, uint64_t* e) {
     const size_t n = (size_t)1 << log_n, ln = (size_t)l * n;
     const unsigned long long total = count * 2 * ln, stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
         const unsigned long long c = idx / (2 * ln);
         const size_t r = (size_t)(idx % ln);
         const Mod64 m = mods[r >> log_n];
-        e[idx] = m.mul(e[idx], pe[(pt_per_ct ? c * ln : 0) + r]);
+        e[idx] = m.mul(src[idx], pe[(pt_per_ct ? c * ln : 0) + r]);
     }
 }
 // limb-wise modular addition of RNS polynomials: out = a + b over [polys][n] with modulus mods[poly % l]   (rns.rs Add impls)
@@ -562,7 +562,7 @@ fhe_status fhe_ckks_mul_plain_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, size
         const size_t c = std::min(chunk, count - base);
         FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * 2 * l, d_ct + base * per, e, true));
         ckks_ptmul_kernel<<<stream_grid(ctx, (unsigned long long)c * per), 256, 0, ctx->stream>>>(
-            ck->d_mods, (int)l, (int)log_n, c, pt_count == 1 ? 0 : 1, pe + (pt_count == 1 ? 0 : base * l * n), e);
+            ck->d_mods, (int)l, (int)log_n, c, pt_count == 1 ? 0 : 1, pe + (pt_count == 1 ? 0 : base * l * n), e, e);
         FHE_CHECK(after_launch(ctx, "ckks_ptmul_kernel"));
         FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, c * 2 * l, e, false));
         FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, e, nullptr, nullptr, false, d_out + base * 2 * (l - 1) * n));
@@ -589,7 +589,7 @@ fhe_status fhe_ckks_mul_mat(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t
         for (size_t j = 0; j < n_baby; ++j) any = any || present[i * n_baby + j];
         FHE_REQUIRE(ctx, any, "giant step %zu has no diagonal", i);
     }
-    const size_t words = n_baby * ct_in + 3 * ct_out;
+    const size_t words = n_baby * ct_in + ct_in + l * n + 3 * ct_out;
     if (ck->ws2_bytes < words * 8) {
         FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ck->ws2) cudaFree(ck->ws2);
@@ -598,8 +598,10 @@ fhe_status fhe_ckks_mul_mat(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t
         if (cudaMalloc(&ck->ws2, words * 8) != cudaSuccess) return fail(ctx, FHE_ENOMEM, "mul_mat workspace of %zu bytes", words * 8);
         ck->ws2_bytes = words * 8;
     }
-    uint64_t* rot = (uint64_t*)ck->ws2;             // [n_baby] rotated inputs
-    uint64_t* inner = rot + n_baby * ct_in;         // sum over baby steps of one giant step
+    uint64_t* rot = (uint64_t*)ck->ws2;             // [n_baby] rotated inputs, transformed ONCE to evaluation form
+    uint64_t* prod = rot + n_baby * ct_in;          // one plaintext product (evaluation -> coefficient form)
+    uint64_t* pe = prod + ct_in;                    // one diagonal in evaluation form
+    uint64_t* inner = pe + l * n;                   // sum over baby steps of one giant step
     uint64_t* tmp = inner + ct_out;
     uint64_t* tmp2 = tmp + ct_out;
     auto add = [&](const uint64_t* a, const uint64_t* b, uint64_t* o) -> fhe_status {
@@ -607,13 +609,16 @@ fhe_status fhe_ckks_mul_mat(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t
                                                                                                count * 2 * (l - 1), a, b, o);
         return after_launch(ctx, "rns_add_kernel");
     };
-    std::vector<const uint64_t*> rj(n_baby);
+    // every rotated input is used by up to n_giant diagonals: its forward transform is shared (the reference transforms
+    // inside each polynomial product; the products are exact, so the results are the same words)
+    const std::vector<uint64_t> qs = level_qs(ck, l);
     for (size_t j = 0; j < n_baby; ++j) {
+        uint64_t* e = rot + j * ct_in;
         if (baby[j].t == 0) {
-            rj[j] = d_ct;
+            FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, count * 2 * l, d_ct, e, true));
         } else {
-            FHE_CHECK(fhe_ckks_key_switch(ctx, ck, baby[j].key, baby[j].t, l, count, d_ct, rot + j * ct_in));
-            rj[j] = rot + j * ct_in;
+            FHE_CHECK(fhe_ckks_key_switch(ctx, ck, baby[j].key, baby[j].t, l, count, d_ct, e));
+            FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, count * 2 * l, e, true));
         }
     }
     size_t pt_idx = 0;
@@ -623,7 +628,13 @@ fhe_status fhe_ckks_mul_mat(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t
             if (!present[i * n_baby + j]) continue;
             const uint64_t* pt = d_pts + pt_idx * l * n;
             ++pt_idx;
-            FHE_CHECK(fhe_ckks_mul_plain_rescale_batch(ctx, ck, l, count, 1, pt, rj[j], first ? inner : tmp));
+            // mul_constant (ckks.rs:250-253): limb-wise product with the encoded diagonal, then rescale
+            FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, l, pt, pe, true));
+            ckks_ptmul_kernel<<<stream_grid(ctx, (unsigned long long)ct_in), 256, 0, ctx->stream>>>(ck->d_mods, (int)l, (int)log_n, count, 0, pe,
+                                                                                                    rot + j * ct_in, prod);
+            FHE_CHECK(after_launch(ctx, "ckks_ptmul_kernel"));
+            FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, count * 2 * l, prod, false));
+            FHE_CHECK(run_rescale(ctx, qs, 1, log_n, count * 2, prod, nullptr, nullptr, false, first ? inner : tmp));
             if (!first) FHE_CHECK(add(inner, tmp, inner));
             first = false;
         }

@@ -40,7 +40,8 @@ namespace fhe {
 
 static constexpr int BR_THREADS = 128;
 static constexpr int BR_THREADS_WIDE = 512;
-static constexpr int PRO_G = 4;
+static constexpr int PRO_G = 4;       // ciphertext slots per prologue CTA (key rows are loaded once per CTA iteration) ...
+static constexpr int PRO_G_BIG = 4;   // ... and when PRO_G slots of N * d digits would exceed the shared memory (N = 2048, d = 5: 4 x 40 KB)
 static constexpr int PRO_THREADS = 128;
 
 template <typename W>
@@ -55,7 +56,7 @@ __global__ void fhew_pack_rows_kernel(const W* __restrict__ ab /* [rows][2][N] e
     }
 }
 
-template <typename CT, typename OT>
+template <typename CT, typename OT, int PRO_G>
 __global__ void __launch_bounds__(PRO_THREADS) fhew_prologue_kernel(LweKsDev K, const CT* __restrict__ ct_in, OT* __restrict__ out,
                                                                       unsigned long long count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -307,18 +308,29 @@ static fhe_status run_prologue(fhe_ctx* ctx, const fhe_fhew_key* key, size_t cou
     LweKsDev K = key->K;
     K.switch_in = sw_in;
     K.switch_out = sw_out;
-    const size_t smem = ((size_t)PRO_G * K.n * K.ks_dec.d + PRO_G) * 4;
+    const bool big = ((size_t)PRO_G * K.n * K.ks_dec.d + PRO_G) * 4 > 160 * 1024;
+    const size_t g = big ? PRO_G_BIG : PRO_G;
+    const size_t smem = (g * K.n * K.ks_dec.d + g) * 4;
     unsigned grid;
-    unsigned long long groups = (count + PRO_G - 1) / PRO_G;
+    unsigned long long groups = (count + g - 1) / g;
+#define FHE_PROLOGUE_LAUNCH(OT_, G_, OUT_)                                                   \
+    do {                                                                                     \
+        auto kern = fhew_prologue_kernel<uint64_t, OT_, G_>;                                 \
+        FHE_CHECK(persistent_grid(ctx, kern, PRO_THREADS, smem, groups, &grid));             \
+        kern<<<grid, PRO_THREADS, smem, ctx->stream>>>(K, d_ct_in, OUT_, count);             \
+    } while (0)
     if (d_out32) {
-        auto kern = fhew_prologue_kernel<uint64_t, uint32_t>;
-        FHE_CHECK(persistent_grid(ctx, kern, PRO_THREADS, smem, groups, &grid));
-        kern<<<grid, PRO_THREADS, smem, ctx->stream>>>(K, d_ct_in, d_out32, count);
+        if (big)
+            FHE_PROLOGUE_LAUNCH(uint32_t, PRO_G_BIG, d_out32);
+        else
+            FHE_PROLOGUE_LAUNCH(uint32_t, PRO_G, d_out32);
     } else {
-        auto kern = fhew_prologue_kernel<uint64_t, uint64_t>;
-        FHE_CHECK(persistent_grid(ctx, kern, PRO_THREADS, smem, groups, &grid));
-        kern<<<grid, PRO_THREADS, smem, ctx->stream>>>(K, d_ct_in, d_out64, count);
+        if (big)
+            FHE_PROLOGUE_LAUNCH(uint64_t, PRO_G_BIG, d_out64);
+        else
+            FHE_PROLOGUE_LAUNCH(uint64_t, PRO_G, d_out64);
     }
+#undef FHE_PROLOGUE_LAUNCH
     return after_launch(ctx, "fhew_prologue_kernel");
 }
 
