@@ -639,13 +639,15 @@ fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, 
     FHE_CHECK(ensure_stage_d(ctx, 2, f_bytes, &d_f));
     FHE_REQUIRE(ctx, post_add < key->param.big_q, "post_add out of range");
     // Pipelined over chunks: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c (two copy streams + events)
-    const size_t nchunk = count >= 8192 ? 4 : (count >= 2048 ? 2 : 1);
+    size_t nchunk = count >= 8192 ? 4 : (count >= 2048 ? 2 : 1);  // measured: 8 or 16 chunks lose more to partial waves than they hide
+    if (const char* e = getenv("FHE_B200_HOST_CHUNKS")) nchunk = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), 64));  // tuning knob
     const size_t cs = (count + nchunk - 1) / nchunk, row = (size_t)n + 1;
     if (!ctx->copy_in) FHE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     if (!ctx->copy_out) FHE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
     void* scratch;
     FHE_CHECK(ensure_scratch(ctx, count * (key->P.n_s + 1) * 4, &scratch));
-    cudaEvent_t ev[9];
+    std::vector<cudaEvent_t> ev(2 * nchunk + 1);  // per chunk: input landed, kernels done; last: fence
+    const size_t fence = 2 * nchunk;
     for (auto& e : ev) FHE_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     fhe_status st = FHE_OK;
     auto cu = [&](cudaError_t e, const char* what) {
@@ -653,8 +655,8 @@ fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, 
     };
     cu(cudaMemcpyAsync(d_f, f, f_bytes, cudaMemcpyHostToDevice, ctx->stream), "H2D f");
     cu(cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream), "memset");
-    cu(cudaEventRecord(ev[8], ctx->stream), "event");  // staging buffers are free once earlier work on the stream is done
-    cu(cudaStreamWaitEvent(ctx->copy_in, ev[8], 0), "wait");
+    cu(cudaEventRecord(ev[fence], ctx->stream), "event");  // staging buffers are free once earlier work on the stream is done
+    cu(cudaStreamWaitEvent(ctx->copy_in, ev[fence], 0), "wait");
     for (size_t c = 0; c < nchunk && st == FHE_OK; ++c) {
         const size_t off = c * cs, cnt = std::min(cs, count - off);
         if (off >= count) break;
@@ -671,8 +673,8 @@ fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, 
         cu(cudaStreamWaitEvent(ctx->copy_out, ev[2 * c + 1], 0), "wait");
         cu(cudaMemcpyAsync(ct_out + off * row, dd_out, cnt * row * 8, cudaMemcpyDeviceToHost, ctx->copy_out), "D2H");
     }
-    cu(cudaEventRecord(ev[8], ctx->copy_out), "event");
-    cu(cudaStreamWaitEvent(ctx->stream, ev[8], 0), "wait");
+    cu(cudaEventRecord(ev[fence], ctx->copy_out), "event");
+    cu(cudaStreamWaitEvent(ctx->stream, ev[fence], 0), "wait");
     if (st == FHE_OK) st = check_err_flag(ctx, key);  // synchronises the stream (which now waits for the last D2H)
     else cudaDeviceSynchronize();
     for (auto& e : ev) cudaEventDestroy(e);
