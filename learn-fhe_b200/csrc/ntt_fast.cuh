@@ -22,6 +22,9 @@
 #ifndef FAST_HALF64
 #define FAST_HALF64 1
 #endif
+#ifndef FAST_HALF32
+#define FAST_HALF32 0
+#endif
 #ifndef FAST_MIN_NTHR
 #define FAST_MIN_NTHR 128  // smallest CTA: tiles covered by fewer threads are batched PB per CTA (128 measured 5-11 % faster than 256 at N = 2^10, 2^11)
 #endif
@@ -596,7 +599,7 @@ struct FastGeom {
     // 64-bit words: no pairing (twice the registers), but for the big tiles half the threads per tile, each walking two groups
     // per pass: 256-thread CTAs (4 per SM) interleave their load / compute / store phases better than 512-thread ones
     // (measured +6-13 % at 2^12, the tile of N = 2^12 and 2^16; smaller tiles already run 256-thread CTAs)
-    static constexpr int HALF = (L::BITS == 64 && FAST_HALF64 && LOGT >= 12) ? 1 : 0;
+    static constexpr int HALF = ((L::BITS == 64 && FAST_HALF64 && LOGT >= 12) || (L::BITS == 32 && FAST_HALF32 && LOGT >= 12)) ? 1 : 0;
     static constexpr int TPP = 1 << (LOGT - RMAX - PAIR - HALF);
     static constexpr int PB = TPP >= FAST_MIN_NTHR ? 1 : FAST_MIN_NTHR / TPP;
     static constexpr int NTHR = TPP * PB;
