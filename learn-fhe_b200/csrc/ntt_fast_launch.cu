@@ -84,8 +84,11 @@ ntt_fast_tile_kernel(FastArgs<L> a) {
     }
 }
 
+#ifndef FAST_COL_MINB
+#define FAST_COL_MINB 3  // 80 registers, 3 CTAs per SM: measured best for the HBM-bound column pass (4: spills; unbounded: 114-124 registers)
+#endif
 template <typename L, int S, bool FWD>
-__global__ void __launch_bounds__(256) ntt_fast_column_kernel(FastArgs<L> a) {
+__global__ void __launch_bounds__(256, FAST_COL_MINB) ntt_fast_column_kernel(FastArgs<L> a) {
     const int lc = a.log_n - S;
     const unsigned long long total = (unsigned long long)a.n_polys << lc;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
