@@ -52,6 +52,13 @@ class ClockSampler:
         self.lines = []  # (host monotonic time, csv line)
         self.t0 = self.t1 = None
 
+    def wait_ready(self, timeout=5.0):
+        """Block until nvidia-smi has produced its first sample (it needs 0.1-0.5 s to start), so that the 20 ms sampling is
+        already running when the timed region begins."""
+        t_end = time.monotonic() + timeout
+        while self.proc is not None and not self.lines and time.monotonic() < t_end:
+            time.sleep(0.01)
+
     def begin(self):
         self.t0 = time.monotonic()
 
@@ -518,6 +525,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
     for i in range(args.warmup):
         step(i)
     barrier()
