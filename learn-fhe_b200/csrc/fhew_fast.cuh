@@ -18,6 +18,12 @@
 #include "fhew_core.cuh"
 #include "ntt_fast.cuh"
 
+#ifndef FF_P3_UNROLL
+#define FF_P3_UNROLL 4  // rows of the P3 MAC loop unrolled together
+#endif
+#define FF_PRAGMA_(x) _Pragma(#x)
+#define FF_UNROLL(n) FF_PRAGMA_(unroll n)
+
 namespace fhe {
 
 static constexpr int FF_LOGN = 9;
@@ -180,7 +186,7 @@ HD void ff_p3(const FhewFastDev& P, const FhewFastSmem& S, const uint4* __restri
     const uint32_t P0 = swzf(t << 2);
     uint64_t sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
     const TwPair<uint32_t> t0 = ff_tw(S.tw + 128u + t), t1 = ff_tw(S.tw + 256u + 2u * t), t2 = ff_tw(S.tw + 257u + 2u * t);
-#pragma unroll 4
+    FF_UNROLL(FF_P3_UNROLL)
     for (uint32_t k = 0; k < rows; ++k) {
         uint32_t x[4];
         ff_ld4(S.dig + (k << FF_LOGN), P0, x);
