@@ -62,6 +62,8 @@ fhe_status fhe_prof_end(fhe_ctx* ctx, char* json_buf, size_t cap);
 /* measured integer-multiply peaks of this device in 10^12 thread-level operations per second: 32-bit IMAD, IMAD.HI
  * (__umulhi) and IMAD.WIDE (u32 x u32 + u64).  The modular kernels' "binding roofline" when they are not HBM-bound. */
 fhe_status fhe_diag_int32_peak(fhe_ctx* ctx, double* imad_tops, double* imad_hi_tops, double* imad_wide_tops);
+/* measured FP64 pipe rates (10^12 thread-instructions per second): DADD, DMUL, DFMA - the denominators of the TFHE roofline */
+fhe_status fhe_diag_fp64_peak(fhe_ctx* ctx, double* dadd_tops, double* dmul_tops, double* dfma_tops);
 
 fhe_status fhe_malloc(fhe_ctx* ctx, size_t bytes, void** d_ptr);
 fhe_status fhe_free(fhe_ctx* ctx, void* d_ptr);
@@ -199,7 +201,11 @@ void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key);
 /* Evaluation mode of every product made with this key.  0 (default): the reference's dataflow - each row * limb product is
  * inverse-transformed and rounded on its own (misc.rs:59-61), raw torus words bit-identical to the reference.  1: products
  * are summed in the Fourier domain and rounded once per output ((k+1) instead of (k+1)^2 d inverse FFTs per CMUX); torus
- * words then differ from the reference's by less than its own error bound (c64.rs:186-208), decryptions are identical. */
+ * words then differ from the reference's by less than its own error bound (c64.rs:186-208), decryptions are identical.
+ * 2: the fused bounded-error blind rotation (k = 1; N = 512, 1024, 2048): same digits and the same exact sums as mode 1, FMA
+ * butterflies, twist merged into the forward twiddles, one rounding per output coefficient; each CMUX output is within
+ * (k+1) d 2^(64 + log_b + log_n - 53) of the reference's, decryptions are identical (FHE_EUNSUPPORTED for other shapes).
+ * The stand-alone external product / CMUX entry points evaluate modes 1 and 2 alike. */
 fhe_status fhe_tfhe_key_set_mode(fhe_ctx* ctx, fhe_tfhe_key* key, int mode);
 /* device bytes held by the key (Fourier-domain bsk + ksk) and its one-time NCCL broadcast from `root` */
 size_t fhe_tfhe_key_bytes(const fhe_tfhe_key* key);

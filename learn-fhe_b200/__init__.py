@@ -97,6 +97,7 @@ def lib():
     L.fhe_prof_end.argtypes = [vp, C.c_char_p, sz]
     L.fhe_two_adic_primes.argtypes = [ui, ui, sz, vp]
     L.fhe_diag_int32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.fhe_diag_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.fhe_keys_broadcast.argtypes = [vp, vp, C.c_int, vp, sz]
     L.fhe_fhew_key_bytes.argtypes = [vp]
     L.fhe_fhew_key_bytes.restype = sz
@@ -235,6 +236,14 @@ class Context:
             self.ck(self.L.fhe_diag_int32_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
             self._int32_peak = {"imad": a.value, "imad_hi": b.value, "imad_wide": c.value}
         return dict(self._int32_peak)
+
+    def fp64_peak(self):
+        """Measured DADD / DMUL / DFMA rates of this device, 10^12 thread-instructions per second."""
+        if getattr(self, "_fp64_peak", None) is None:
+            a, b, c = C.c_double(), C.c_double(), C.c_double()
+            self.ck(self.L.fhe_diag_fp64_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
+            self._fp64_peak = {"dadd": a.value, "dmul": b.value, "dfma": c.value}
+        return dict(self._fp64_peak)
 
     @property
     def launches(self):

@@ -18,6 +18,7 @@
 
 #include "ctx.cuh"
 #include "tfhe_core.cuh"
+#include "tfhe_fast.cuh"
 #include "tfhe_tables.hpp"
 
 struct fhe_tfhe_key {
@@ -27,6 +28,13 @@ struct fhe_tfhe_key {
     void* d_brk = nullptr;  // Cx [n][(k+1)d][(k+1)][N/2]
     void* d_ksk = nullptr;  // u64 [(kN) d_ks][n+1]
     size_t brk_bytes = 0, ksk_bytes = 0;
+    // bounded-error fast path (tfhe_fast.cuh): second image of the bsk in that path's transform and layout, its tables
+    fhe::TfheFastDev F;
+    void* d_brk_fast = nullptr;
+    void* d_fast_tab = nullptr;
+    size_t brk_fast_bytes = 0;
+    bool fast_ok = false;  // a specialisation exists for (N, d) and k = 1
+    int mode = 0;          // 0 bit-identical reference dataflow, 1 Fourier-domain accumulation (generic kernels), 2 fast path
 };
 
 namespace fhe {
@@ -144,6 +152,65 @@ __global__ void __launch_bounds__(TFHE_THREADS, 2) tfhe_blind_rotate_kernel(Tfhe
             o[c] = x == 0 ? acc[(size_t)j * n] : (uint64_t)(0 - acc[(size_t)j * n + (n - x)]);
         }
         if (threadIdx.x == 0) o[(size_t)k * n] = acc[(size_t)k * n];
+        __syncthreads();
+    }
+}
+
+// ---- bounded-error fast path (tfhe_fast.cuh) ------------------------------------------------------------------------------------------
+static constexpr int TFHE_FAST_THREADS = 128;
+// key polynomial (step, r, o) [N] torus words -> forward spectrum in the coalesced P3 layout; one CTA per polynomial
+template <typename C>
+__global__ void __launch_bounds__(256) tfhe_fast_key_kernel(TfheFastDev P, unsigned long long polys, const uint64_t* __restrict__ src,
+                                                            Cx* __restrict__ dst) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx* s = reinterpret_cast<Cx*>(smem_raw);
+    for (unsigned long long item = blockIdx.x; item < polys; item += gridDim.x) {
+        const uint64_t* p = src + item * C::N;
+        for (uint32_t i = threadIdx.x; i < C::M; i += blockDim.x) s[i] = Cx{t64_to_f64(p[i]), t64_to_f64(p[i + C::M])};
+        __syncthreads();
+        for (int l = 0; l < C::LG; ++l) {
+            for (uint32_t b = threadIdx.x; b < C::M / 2; b += blockDim.x) tfhe_fast_key_level(s, C::LG, l, P.fft.W, b);
+            __syncthreads();
+        }
+        const uint32_t o = (uint32_t)(item % 2), r = (uint32_t)((item / 2) % C::NL), step = (uint32_t)(item / (2 * C::NL));
+        for (uint32_t i = threadIdx.x; i < C::M; i += blockDim.x) dst[tfhe_fast_key_index<C>(step, r, o, i)] = s[i];
+        __syncthreads();
+    }
+}
+// blind_rotate + sample_extract(0) for k = 1: ct_in [count][n_lwe+1] -> out [count][N+1]; persistent CTA per ciphertext,
+// accumulator (2 N torus words) and the exchange buffer (2 d N/2 complex) resident in shared memory across all n CMUX steps
+template <typename C>
+__global__ void __launch_bounds__(TFHE_FAST_THREADS, 3) tfhe_blind_rotate_fast_kernel(TfheFastDev P, const uint64_t* __restrict__ lut,
+                                                                                   const uint64_t* __restrict__ ct_in, unsigned long long count,
+                                                                                   uint64_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t N = C::N;
+    uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);
+    Cx* X = reinterpret_cast<Cx*>(acc + 2 * N);
+    uint16_t* ex = reinterpret_cast<uint16_t*>(X + (size_t)C::NL * C::M);
+    const uint32_t rb = 64 - (C::LG + 2);  // tfhe/bootstrapping.rs:99-104: switch to Z_{2N}
+    auto run = [&](uint32_t units, auto f) {
+        for (uint32_t u = threadIdx.x; u < units; u += TFHE_FAST_THREADS) f(u);
+        __syncthreads();
+    };
+    for (unsigned long long ct = blockIdx.x; ct < count; ct += gridDim.x) {
+        const uint64_t* src = ct_in + ct * (P.n_lwe + 1);
+        for (uint32_t i = threadIdx.x; i < P.n_lwe; i += TFHE_FAST_THREADS) ex[i] = (uint16_t)((uint32_t)t64_rounding_shr_dev(src[i], rb) & (2 * N - 1));
+        const uint32_t bt = (uint32_t)t64_rounding_shr_dev(src[P.n_lwe], rb) & (2 * N - 1);
+        const uint32_t e0 = (2 * N - bt) & (2 * N - 1);  // rotate(-b~)
+        for (uint32_t c = threadIdx.x; c < N; c += TFHE_FAST_THREADS) {
+            acc[c] = 0;
+            acc[N + c] = t64_rot_coef(lut, N, e0, c);
+        }
+        __syncthreads();
+        for (uint32_t i = 0; i < P.n_lwe; ++i) {
+            const uint32_t e = ex[i];
+            if (e == 0) continue;  // rotate(0) - acc = 0: the external product of zero is exactly zero
+            tfhe_fast_cmux<C>(P, acc, X, i, e, run);
+        }
+        uint64_t* o = out + ct * ((unsigned long long)N + 1);
+        for (uint32_t x = threadIdx.x; x < N; x += TFHE_FAST_THREADS) o[x] = x == 0 ? acc[0] : (uint64_t)(0 - acc[N - x]);
+        if (threadIdx.x == 0) o[N] = acc[N];
         __syncthreads();
     }
 }
@@ -275,11 +342,66 @@ static fhe_status run_key_switch(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t c
 
 static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_tfhe_key* key, const uint64_t* d_lut, size_t count, const uint64_t* d_in,
                                    uint64_t* d_out) {
+    if (key->mode == 2) {
+        fhe_status st = FHE_OK;
+        tfhe_fast_dispatch(key->P.log_n - 1, key->P.bs_dec.d, [&](auto cfg) {
+            typedef decltype(cfg) C;
+            const size_t smem = tfhe_fast_smem_bytes<C>(key->F.n_lwe);
+            auto kern = tfhe_blind_rotate_fast_kernel<C>;
+            int occ = 0;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TFHE_FAST_THREADS, smem) != cudaSuccess || occ < 1) {
+                st = fail(ctx, FHE_ECUDA, "tfhe_blind_rotate_fast_kernel does not fit (%zu bytes of shared memory)", smem);
+                return;
+            }
+            const unsigned grid = (unsigned)std::min<unsigned long long>(count, (unsigned long long)ctx->sm_count * occ);
+            kern<<<grid, TFHE_FAST_THREADS, smem, ctx->stream>>>(key->F, d_lut, d_in, count, d_out);
+            st = after_launch(ctx, "tfhe_blind_rotate_fast_kernel");
+        });
+        return st;
+    }
     const size_t smem = tfhe_smem_bytes(key->P.k, key->P.bs_dec.d, key->P.log_n);
     unsigned grid;
     FHE_CHECK(tfhe_grid(ctx, tfhe_blind_rotate_kernel, smem, count, &grid));
     tfhe_blind_rotate_kernel<<<grid, TFHE_THREADS, smem, ctx->stream>>>(key->P, d_lut, d_in, count, d_out);
     return after_launch(ctx, "tfhe_blind_rotate_kernel");
+}
+
+// second image of the bsk for the fast path, from the raw torus polynomials still on the device in d_raw ([polys][N])
+static fhe_status build_fast_key(fhe_ctx* ctx, fhe_tfhe_key* key, const uint64_t* d_raw, size_t polys) {
+    const fhe_tfhe_param& pp = key->param;
+    key->fast_ok = false;
+    if (pp.k != 1 || pp.bs_log_b * pp.bs_d > 31 || pp.n > 65535) return FHE_OK;
+    FastFftTabHost h;
+    fhe_status st = FHE_OK;
+    const bool have = tfhe_fast_dispatch((int)pp.log_big_n - 1, pp.bs_d, [&](auto cfg) {
+        typedef decltype(cfg) C;
+        h.build(pp.log_big_n);
+        const size_t tab_bytes = h.data.size() * sizeof(Cx);
+        key->brk_fast_bytes = (size_t)pp.n * C::KEY_STRIDE * sizeof(Cx);
+        if (cudaMalloc(&key->d_fast_tab, tab_bytes) != cudaSuccess || cudaMalloc(&key->d_brk_fast, key->brk_fast_bytes) != cudaSuccess ||
+            cudaMemcpyAsync(key->d_fast_tab, h.data.data(), tab_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            st = fail(ctx, FHE_ENOMEM, "fast-path bsk image alloc / upload failed");
+            return;
+        }
+        key->F.log_n = (int)pp.log_big_n;
+        key->F.n_lwe = pp.n;
+        key->F.dig = make_fast_digits(key->P.bs_dec);
+        key->F.fft = h.view((const Cx*)key->d_fast_tab);
+        key->F.key = (const Cx*)key->d_brk_fast;
+        const size_t smem = C::M * sizeof(Cx);
+        auto kern = tfhe_fast_key_kernel<C>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            st = fail(ctx, FHE_ECUDA, "tfhe_fast_key_kernel attribute");
+            return;
+        }
+        const unsigned grid = (unsigned)std::min<size_t>(polys, (size_t)ctx->sm_count * 8);
+        kern<<<grid, 256, smem, ctx->stream>>>(key->F, polys, d_raw, (Cx*)key->d_brk_fast);
+        st = after_launch(ctx, "tfhe_fast_key_kernel");
+        if (st == FHE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, FHE_ECUDA, "fast-path bsk transform failed");
+    });
+    if (st == FHE_OK) key->fast_ok = have;
+    return st;
 }
 
 }  // namespace fhe
@@ -372,6 +494,7 @@ fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uin
         }
     }
     if (st == FHE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, FHE_ECUDA, "bsk transform failed");
+    if (st == FHE_OK) st = build_fast_key(ctx, key, d_tmp, polys);
     if (d_tmp) cudaFree(d_tmp);
     // ksk: [(kN) d_ks][n] + [(kN) d_ks] -> [(kN) d_ks][n+1]
     if (st == FHE_OK) {
@@ -400,20 +523,27 @@ void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key) {
     if (ctx) cudaStreamSynchronize(ctx->stream);
     if (key->d_brk) cudaFree(key->d_brk);
     if (key->d_ksk) cudaFree(key->d_ksk);
+    if (key->d_brk_fast) cudaFree(key->d_brk_fast);
+    if (key->d_fast_tab) cudaFree(key->d_fast_tab);
     delete key;
 }
 fhe_status fhe_tfhe_key_set_mode(fhe_ctx* ctx, fhe_tfhe_key* key, int mode) {
     if (!ctx || !key) return FHE_EINVAL;
-    FHE_REQUIRE(ctx, mode == 0 || mode == 1, "mode must be 0 (reference dataflow, bit-identical) or 1 (Fourier-domain accumulation)");
+    FHE_REQUIRE(ctx, mode >= 0 && mode <= 2,
+                "mode must be 0 (reference dataflow, bit-identical), 1 (Fourier-domain accumulation) or 2 (bounded-error fused path)");
+    if (mode == 2 && !key->fast_ok)
+        return fail(ctx, FHE_EUNSUPPORTED, "the fused bounded-error path needs k = 1, log_b d <= 31, d <= 3 (2 at N = 2048) and N in {512, 1024, 2048}");
     FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    key->P.fourier_acc = (uint32_t)mode;
+    key->mode = mode;
+    key->P.fourier_acc = mode != 0;  // the stand-alone external product / CMUX entry points use the generic kernels
     return FHE_OK;
 }
-size_t fhe_tfhe_key_bytes(const fhe_tfhe_key* key) { return key ? key->brk_bytes + key->ksk_bytes : 0; }
+size_t fhe_tfhe_key_bytes(const fhe_tfhe_key* key) { return key ? key->brk_bytes + key->ksk_bytes + key->brk_fast_bytes : 0; }
 fhe_status fhe_tfhe_key_broadcast(fhe_ctx* ctx, fhe_tfhe_key* key, void* nccl_comm, int root) {
     if (!ctx || !key) return FHE_EINVAL;
     FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_brk, key->brk_bytes));
     FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ksk, key->ksk_bytes));
+    if (key->fast_ok) FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_brk_fast, key->brk_fast_bytes));
     FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FHE_OK;
 }

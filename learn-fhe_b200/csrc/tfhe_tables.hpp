@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "tfhe_core.cuh"
+#include "tfhe_fast.cuh"
 
 namespace fhe {
 
@@ -48,6 +49,51 @@ struct FftTabHost {
         T.tw_bo = base + 2 * m;
         T.tw_inv_bo = base + 2 * m + mb;
         T.m_inv = 1.0 / (double)m;
+        return T;
+    }
+};
+
+// Tables of the bounded-error fast path (tfhe_fast.cuh) for ring degree n = 2^log_n, m = n/2 = 2^lg, zeta = e^(i pi / n):
+// layout [W (m) | V (m/2, >= 1) | U (m)].  Angles are evaluated in long double and rounded once.
+struct FastFftTabHost {
+    std::vector<Cx> data;
+    size_t m = 0, mv = 0;
+    unsigned log_n = 0;
+    static Cx cis_pi(long double num, long double den) {
+        const long double ang = 3.14159265358979323846264338327950288L * num / den;
+        return Cx{(double)cosl(ang), (double)sinl(ang)};
+    }
+    void build(unsigned log_n_) {
+        log_n = log_n_;
+        const size_t n = (size_t)1 << log_n;
+        m = n / 2;
+        mv = m / 2 > 1 ? m / 2 : 1;
+        data.assign(2 * m + mv, Cx{1.0, 0.0});
+        unsigned lg = 0;
+        while (((size_t)1 << lg) < m) ++lg;
+        // exponent of the root of chunk c at level l: e(0, 0) = m; e(l+1, 2c) = e(l, c) / 2; e(l+1, 2c+1) = e(l, c) / 2 + n
+        std::vector<uint64_t> e{(uint64_t)m}, nx;
+        for (unsigned l = 0; l < lg; ++l) {
+            nx.assign(e.size() * 2, 0);
+            for (size_t c = 0; c < e.size(); ++c) {
+                nx[2 * c] = (e[c] / 2) % (2 * n);
+                nx[2 * c + 1] = (e[c] / 2 + n) % (2 * n);
+                data[((size_t)1 << l) + c] = cis_pi((long double)nx[2 * c], (long double)n);
+            }
+            e.swap(nx);
+        }
+        for (size_t i = 0; i < mv; ++i) data[m + i] = cis_pi(-2.0L * (long double)i, (long double)m);
+        for (size_t p = 0; p < m; ++p) {
+            const Cx u = cis_pi(-(long double)p, (long double)n);
+            data[m + mv + p] = Cx{u.re / (double)m, u.im / (double)m};
+        }
+    }
+    FastFftTab view(const Cx* base) const {
+        FastFftTab T;
+        T.W = base;
+        T.V = base + m;
+        T.U = base + m + mv;
+        for (size_t i = 0; i < 16; ++i) T.w0[i] = i < m ? data[i] : Cx{1.0, 0.0};
         return T;
     }
 };

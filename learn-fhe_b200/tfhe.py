@@ -52,10 +52,11 @@ class BootstrappingKey:
         except Exception:
             pass
 
-    def set_mode(self, fourier_acc):
-        """False (default): the reference's dataflow, bit-identical torus words; True: Fourier-domain accumulation (one
-        rounding per output coefficient; within the reference's error bound, decryptions identical)."""
-        self.ctx.call("fhe_tfhe_key_set_mode", self.h, 1 if fourier_acc else 0)
+    def set_mode(self, mode):
+        """0 / False (default): the reference's dataflow, bit-identical torus words; 1 / True: Fourier-domain accumulation (one
+        rounding per output coefficient; within the reference's error bound, decryptions identical); 2: the fused
+        bounded-error blind rotation (same contract as 1; k = 1, N in {512, 1024, 2048})."""
+        self.ctx.call("fhe_tfhe_key_set_mode", self.h, int(mode))
 
     @property
     def nbytes(self):

@@ -373,3 +373,62 @@ def test_kernel_logic_fhew_fast(H, orc, fhew_setup):
             assert H.sim_fhew_fast_blind_rotate_extract_drift(h, f, pro[i], q8, o2, drift) == 0
             assert (o2 == ref[i]).all(), drift
     H.sim_fhew_key_free(h)
+
+
+def _rot(poly, e):
+    """poly * X^e over T64[X]/(X^N + 1), e in [0, 2N) (ring.rs:299-313)."""
+    n = len(poly)
+    out = np.empty_like(poly)
+    for c in range(n):
+        src = (c - e) % (2 * n)
+        out[c] = poly[src % n] if src < n else np.uint64((1 << 64) - int(poly[src % n])) if poly[src % n] else np.uint64(0)
+    return out
+
+
+@pytest.mark.parametrize("bs_d,big_n,n,bs_log_b", [(1, 2048, 6, 23), (1, 1024, 6, 23), (3, 1024, 5, 7), (2, 512, 6, 10), (2, 2048, 3, 12), (3, 512, 4, 8)])
+def test_kernel_logic_tfhe_fast_mode(H, orc, bs_d, big_n, n, bs_log_b):
+    """Bounded-error TFHE path (tfhe_fast.cuh: 5 fused passes, Fourier-domain accumulation, FMA butterflies) against the oracle's
+    restatement of the reference dataflow: every CMUX output within (k+1)d * 2^(64 + log_b + log_n - 53) torus units of the
+    reference's (c64.rs:186-208 is the reference's own per-product bound), blind rotation decrypts to the same message."""
+    u64 = np.uint64
+    H.sim_tfhe_fast_key.restype = C.c_void_p
+    H.sim_tfhe_fast_key.argtypes = [C.c_uint] * 4 + [u64p]
+    H.sim_tfhe_fast_key_free.argtypes = [C.c_void_p]
+    H.sim_tfhe_fast_cmux.argtypes = [C.c_void_p, C.c_uint, C.c_uint, u64p]
+    H.sim_tfhe_fast_blind_rotate_extract.argtypes = [C.c_void_p, u64p, u64p, u64p]
+    P = _tfhe_small_param(orc, n=n, big_n=big_n, k=1, bs_d=bs_d, bs_log_b=bs_log_b)
+    K = orc.TfheKey(P, 0x5EED0003)
+    ex = K.export()
+    log_n = P.big_n.bit_length() - 1
+    h = H.sim_tfhe_fast_key(log_n, P.n, P.bs_log_b, P.bs_d, ex["brk"].reshape(-1))
+    assert h
+    bound = 2 * bs_d * 2.0 ** (64 + bs_log_b + log_n - 53)
+    acc = orc.splitmix64(19, 2 * P.big_n).reshape(2, P.big_n)
+    worst = 0
+    for step, e in ((0, 1), (P.n - 1, P.big_n), (1, 2 * P.big_n - 1), (2, 777 % (2 * P.big_n))):
+        rot = np.stack([_rot(acc[0], e), _rot(acc[1], e)])
+        ref = acc + K.external_product(step, rot - acc)
+        got = acc.copy()
+        assert H.sim_tfhe_fast_cmux(h, step, e, got.reshape(-1)) == 0
+        err = np.abs((got - ref).astype(np.int64)).max()
+        worst = max(worst, int(err))
+        assert err < bound, (step, e, err, bound)
+    assert worst > 0  # a different rounding order, not the bit-identical path
+    msgs = np.arange(3, dtype=np.uint64)
+    cts = K.encrypt(msgs, 5)
+    cts[0, 1] = 0  # a zero mask word: that CMUX is skipped
+    v = K.lut_poly(np.arange(1 << P.log_p, dtype=np.uint64))
+    lut = (v << u64(64 - (P.log_p + P.padding))).astype(np.uint64)
+    # after a digit flips the raw words are a different (equally valid) encryption: compare the phases b - <a, s> instead
+    sk = ex["s"].astype(np.int64).astype(np.uint64)
+    phase = lambda t: (int(t[-1]) - int((t[:-1] * sk).sum(dtype=np.uint64))) % (1 << 64)
+    dec = lambda ph: ((ph + (1 << (log_delta - 1))) >> log_delta) % (1 << (P.log_p + P.padding))
+    log_delta = 64 - (P.log_p + P.padding)
+    for ct in cts:
+        out = np.zeros(P.big_n + 1, dtype=np.uint64)
+        assert H.sim_tfhe_fast_blind_rotate_extract(h, lut, ct, out) == 0
+        ref = K.blind_rotate_extract(v, ct)
+        d = (phase(out) - phase(ref) + (1 << 63)) % (1 << 64) - (1 << 63)
+        assert abs(d) < 2 ** (log_delta - 4), (d, log_delta)
+        assert dec(phase(out)) == dec(phase(ref))
+    H.sim_tfhe_fast_key_free(h)

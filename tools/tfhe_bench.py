@@ -31,6 +31,8 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+if "peaks" in args:
+    print("fp64 peaks (T instr/s):", ctx.fp64_peak(), "int32:", ctx.int32_peak())
 if "tfhe" in args or not args:
     batch = int(args[args.index("--batch") + 1]) if "--batch" in args else 2048
     P = tfhe.bootstrapping_testing_param()
@@ -43,9 +45,12 @@ if "tfhe" in args or not args:
     lut = pkg.to_dev(rng.integers(0, 1 << 63, size=N, dtype=np.uint64))
     cts = pkg.to_dev(rng.integers(0, 1 << 63, size=(batch, n + 1), dtype=np.uint64))
     out = torch.empty_like(cts)
-    ctx.prof_begin()
-    ms = timed(lambda: tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out), 2)
-    print("tfhe pbs batch %d: %.2f ms -> %.0f PBS/s" % (batch, ms, batch / ms * 1e3), ctx.prof_end())
+    modes = [int(m) for m in args[args.index("--modes") + 1].split(",")] if "--modes" in args else [0, 1, 2]
+    for mode in modes:
+        bk.set_mode(mode)
+        ctx.prof_begin()
+        ms = timed(lambda: tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out), 2)
+        print("tfhe pbs mode %d batch %d: %.2f ms -> %.0f PBS/s" % (mode, batch, ms, batch / ms * 1e3), ctx.prof_end())
 if "ckks" in args:
     log_n, L = 16, 8
     count = int(args[args.index("--count") + 1]) if "--count" in args else 16
