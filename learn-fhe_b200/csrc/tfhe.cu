@@ -376,7 +376,7 @@ static fhe_status build_fast_key(fhe_ctx* ctx, fhe_tfhe_key* key, const uint64_t
     fhe_status st = FHE_OK;
     const bool have = tfhe_fast_dispatch((int)pp.log_big_n - 1, pp.bs_d, [&](auto cfg) {
         typedef decltype(cfg) C;
-        h.build(pp.log_big_n);
+        h.build(pp.log_big_n, C::R1, C::R2, C::R3);
         const size_t tab_bytes = h.data.size() * sizeof(Cx);
         key->brk_fast_bytes = (size_t)pp.n * C::KEY_STRIDE * sizeof(Cx);
         if (cudaMalloc(&key->d_fast_tab, tab_bytes) != cudaSuccess || cudaMalloc(&key->d_brk_fast, key->brk_fast_bytes) != cudaSuccess ||

@@ -94,7 +94,14 @@ struct FastFftTab {
     const Cx* W;  // [m]   forward chunk twiddles: level l, chunk c uses W[2^l + c] = zeta^e(l+1, 2c), zeta = e^(i pi / n)
     const Cx* V;  // [m/2] inverse position twiddles V[i] = e^(-2 pi i / m * i)
     const Cx* U;  // [m]   untwist and scale: zeta^(-p) / m
-    Cx w0[16];    // W[0..15]: twiddles of the first forward pass (levels 0..3), kept in the kernel's constant bank
+    // per-pass copies laid out so that the threads of a warp read consecutive 16-byte words (one twiddle index t per row):
+    const Cx* W2;  // [2^R2 - 1][2^R1]      P2: row (2^u - 1 + top), column hi   = W[2^(R1+u) + (hi << u) + top]
+    const Cx* W3;  // [2^R3 - 1][m >> R3]   P3: row (2^u - 1 + top), column g    = W[2^(R1+R2+u) + (g << u) + top]
+    const Cx* V4;  // [2^R2 - 1][2^R3]      P4: row (h - 1 + low), column lo     = V[((low << R3) | lo) << (R1+u)], h = 2^(R2-1-u)
+    const Cx* V5;  // [R1][m >> R1]         P5: row uu (h = 2^uu), column lo     = V[lo << (R1-1-uu)]; the twiddle of position
+                   //                           low > 0 is that times the constant e^(-i pi low / h)
+    Cx w0[16];     // W[0..15]: twiddles of the first forward pass (levels 0..3), kept in the kernel's constant bank
+    Cx u0[16];     // zeta^(-(i << (LG-R1))): U[lo + (i << L)] = U[lo] * u0[i] (P5 loads one untwist factor per thread)
 };
 struct TfheFastDev {
     int log_n;
@@ -119,15 +126,15 @@ HD void t64_digits(const FastDigits& fd, uint64_t v64, int32_t* dig) {
 }
 
 // forward register pass over levels l0 .. l0+R-1 of the group with chunk index `hi` at level l0; element j of the group
-// sits at distance j << L.  tw(l, c) returns W[2^l + c].
+// sits at distance j << L.  tw(u, top) returns W[2^(l0+u) + (hi << u) + top].
 template <int R, typename Tw>
-HD void fast_fwd_regs(Cx* x, int l0, uint32_t hi, Tw tw) {
+HD void fast_fwd_regs(Cx* x, Tw tw) {
 #pragma unroll
     for (int u = 0; u < R; ++u) {
         const int h = 1 << (R - 1 - u);
 #pragma unroll
         for (int top = 0; top < (1 << u); ++top) {
-            const Cx w = tw(l0 + u, (hi << u) + (uint32_t)top);
+            const Cx w = tw(u, top);
 #pragma unroll
             for (int low = 0; low < h; ++low) {
                 const int j = (top << (R - u)) | low;
@@ -138,15 +145,15 @@ HD void fast_fwd_regs(Cx* x, int l0, uint32_t hi, Tw tw) {
 }
 // inverse register pass over the same levels (processed from l0+R-1 down to l0): decimation in time with position
 // twiddles; the element pair at level l0+u has half-size 2^(L+R-1-u) and position ((low << L) | lo) inside its half block
-template <int R>
-HD void fast_inv_regs(Cx* x, int l0, int L, uint32_t lo, const Cx* __restrict__ V) {
+// tw(uu, low) returns V[((low << L) | lo) << (l0+u)], u = R-1-uu (stage with 2^uu positions `low`)
+template <int R, typename Tw>
+HD void fast_inv_regs(Cx* x, Tw tw) {
 #pragma unroll
     for (int uu = 0; uu < R; ++uu) {
         const int u = R - 1 - uu, h = 1 << uu;
 #pragma unroll
         for (int low = 0; low < h; ++low) {
-            const uint32_t pos = ((uint32_t)low << L) | lo;
-            const Cx w = ld_cx(V + ((size_t)pos << (l0 + u)));
+            const Cx w = tw(uu, low);
 #pragma unroll
             for (int top = 0; top < (1 << u); ++top) {
                 const int j = (top << (R - u)) | low;
@@ -154,6 +161,17 @@ HD void fast_inv_regs(Cx* x, int l0, int L, uint32_t lo, const Cx* __restrict__ 
             }
         }
     }
+}
+// b * e^(-i pi low / h) for h in {1, 2, 4, 8} (compile-time low, h after unrolling)
+HD Cx cx_rot_const(const Cx b, int low, int h) {
+    constexpr double S = 0.70710678118654752440, C8 = 0.92387953251128675613, S8 = 0.38268343236508977173;
+    if (low == 0) return b;
+    if (2 * low == h) return Cx{b.im, -b.re};
+    if (4 * low == h) return Cx{f64_mul_rn(f64_add_rn(b.re, b.im), S), f64_mul_rn(f64_sub_rn(b.im, b.re), S)};
+    if (4 * low == 3 * h) return Cx{f64_mul_rn(f64_sub_rn(b.im, b.re), S), f64_mul_rn(f64_add_rn(b.re, b.im), -S)};
+    // h = 8, odd low: (c - i s), c = cos(pi low / 8), s = sin(pi low / 8)
+    const double c = low == 1 ? C8 : low == 3 ? S8 : low == 5 ? -S8 : -C8, sn = (low == 1 || low == 7) ? S8 : C8;
+    return Cx{f64_fma_rn(b.im, sn, f64_mul_rn(b.re, c)), f64_fma_rn(-b.re, sn, f64_mul_rn(b.im, c))};
 }
 // the inverse pass adjacent to the pointwise product (L = 0, lo = 0): twiddles e^(-i pi low / h) are constants
 template <int R>
@@ -227,7 +245,7 @@ HD void tfhe_fast_p1(const TfheFastDev& P, const uint64_t* __restrict__ acc, Cx*
         Cx x[NE];
 #pragma unroll
         for (int i = 0; i < NE; ++i) x[i] = Cx{i32_to_f64(dig[k][i][0]), i32_to_f64(dig[k][i][1])};
-        fast_fwd_regs<C::R1>(x, 0, 0u, [&](int l, uint32_t c) { return P.fft.w0[(1u << l) + c]; });
+        fast_fwd_regs<C::R1>(x, [&](int u, int top) { return P.fft.w0[(1 << u) + top]; });
         Cx* f = X + ((size_t)(j * C::D + k) << C::LG);
         const uint32_t p0 = swz_cx(lo);
 #pragma unroll
@@ -246,9 +264,9 @@ HD void tfhe_fast_mid(const TfheFastDev& P, Cx* __restrict__ X, uint32_t unit) {
 #pragma unroll
     for (int i = 0; i < NE; ++i) x[i] = f[p0 ^ swz_cx((uint32_t)i << L)];
     if (FWD)
-        fast_fwd_regs<C::R2>(x, C::R1, hi, [&](int l, uint32_t c) { return ld_cx(P.fft.W + ((1u << l) + c)); });
+        fast_fwd_regs<C::R2>(x, [&](int u, int top) { return ld_cx(P.fft.W2 + (((1 << u) - 1 + top) << C::R1) + hi); });
     else
-        fast_inv_regs<C::R2>(x, C::R1, L, lo, P.fft.V);
+        fast_inv_regs<C::R2>(x, [&](int uu, int low) { return ld_cx(P.fft.V4 + (((1 << uu) - 1 + low) << C::R3) + lo); });
 #pragma unroll
     for (int i = 0; i < NE; ++i) f[p0 ^ swz_cx((uint32_t)i << L)] = x[i];
 }
@@ -267,7 +285,7 @@ HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restr
         Cx x[NE];
 #pragma unroll
         for (int i = 0; i < NE; ++i) x[i] = f[p0 ^ (uint32_t)i];  // swz_cx(i) = i for i < 8
-        fast_fwd_regs<C::R3>(x, C::R1 + C::R2, g, [&](int l, uint32_t c) { return ld_cx(P.fft.W + ((1u << l) + c)); });
+        fast_fwd_regs<C::R3>(x, [&](int u, int top) { return ld_cx(P.fft.W3 + (size_t)((1 << u) - 1 + top) * G + g); });
 #pragma unroll
         for (int i = 0; i < NE; ++i) {
             const Cx k0 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 0) * G + g));
@@ -296,11 +314,17 @@ HD void tfhe_fast_p5(const TfheFastDev& P, uint64_t* __restrict__ acc, const Cx*
     Cx x[NE];
 #pragma unroll
     for (int i = 0; i < NE; ++i) x[i] = f[p0 ^ swz_cx((uint32_t)i << L)];
-    fast_inv_regs<C::R1>(x, 0, L, lo, P.fft.V);
+    Cx base = Cx{1.0, 0.0};
+    fast_inv_regs<C::R1>(x, [&](int uu, int low) {
+        if (low == 0) base = ld_cx(P.fft.V5 + ((size_t)uu << L) + lo);
+        return cx_rot_const(base, low, 1 << uu);
+    });
+#pragma unroll
+    const Cx ul = ld_cx(P.fft.U + lo);
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
         const uint32_t p = lo + ((uint32_t)i << L);
-        const Cx u = ld_cx(P.fft.U + p);
+        const Cx u = i == 0 ? ul : Cx{f64_fma_rn(-ul.im, P.fft.u0[i].im, f64_mul_rn(ul.re, P.fft.u0[i].re)), f64_fma_rn(ul.im, P.fft.u0[i].re, f64_mul_rn(ul.re, P.fft.u0[i].im))};
         const double re = f64_fma_rn(-x[i].im, u.im, f64_mul_rn(x[i].re, u.re));
         const double im = f64_fma_rn(x[i].im, u.re, f64_mul_rn(x[i].re, u.im));
         a[p] += f64_to_torus(re);

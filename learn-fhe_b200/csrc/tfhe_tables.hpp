@@ -54,16 +54,18 @@ struct FftTabHost {
 };
 
 // Tables of the bounded-error fast path (tfhe_fast.cuh) for ring degree n = 2^log_n, m = n/2 = 2^lg, zeta = e^(i pi / n):
-// layout [W (m) | V (m/2, >= 1) | U (m)].  Angles are evaluated in long double and rounded once.
+// layout [W (m) | V (m/2, >= 1) | U (m) | W2 | W3 | V4 | V5] (the last four are the per-pass copies for the split r1 + r2 + r3).
+// Angles are evaluated in long double and rounded once.
 struct FastFftTabHost {
     std::vector<Cx> data;
-    size_t m = 0, mv = 0;
+    size_t m = 0, mv = 0, o_w2 = 0, o_w3 = 0, o_v4 = 0, o_v5 = 0;
     unsigned log_n = 0;
+    Cx u0[16];
     static Cx cis_pi(long double num, long double den) {
         const long double ang = 3.14159265358979323846264338327950288L * num / den;
         return Cx{(double)cosl(ang), (double)sinl(ang)};
     }
-    void build(unsigned log_n_) {
+    void build(unsigned log_n_, int r1, int r2, int r3) {
         log_n = log_n_;
         const size_t n = (size_t)1 << log_n;
         m = n / 2;
@@ -87,13 +89,37 @@ struct FastFftTabHost {
             const Cx u = cis_pi(-(long double)p, (long double)n);
             data[m + mv + p] = Cx{u.re / (double)m, u.im / (double)m};
         }
+        for (size_t i = 0; i < 16; ++i) u0[i] = (i << (lg - r1)) < m ? cis_pi(-(long double)(i << (lg - r1)), (long double)n) : Cx{1.0, 0.0};
+        const Cx *W = data.data(), *V = data.data() + m;
+        std::vector<Cx> ext;
+        o_w2 = data.size();
+        for (int u = 0; u < r2; ++u)
+            for (int top = 0; top < (1 << u); ++top)
+                for (size_t hi = 0; hi < ((size_t)1 << r1); ++hi) ext.push_back(W[((size_t)1 << (r1 + u)) + (hi << u) + top]);
+        o_w3 = data.size() + ext.size();
+        for (int u = 0; u < r3; ++u)
+            for (int top = 0; top < (1 << u); ++top)
+                for (size_t g = 0; g < (m >> r3); ++g) ext.push_back(W[((size_t)1 << (r1 + r2 + u)) + (g << u) + top]);
+        o_v4 = data.size() + ext.size();
+        for (int uu = 0; uu < r2; ++uu)
+            for (int low = 0; low < (1 << uu); ++low)
+                for (size_t lo = 0; lo < ((size_t)1 << r3); ++lo) ext.push_back(V[((((size_t)low << r3) | lo) << (r1 + r2 - 1 - uu))]);
+        o_v5 = data.size() + ext.size();
+        for (int uu = 0; uu < r1; ++uu)
+            for (size_t lo = 0; lo < (m >> r1); ++lo) ext.push_back(V[lo << (r1 - 1 - uu)]);
+        data.insert(data.end(), ext.begin(), ext.end());
     }
     FastFftTab view(const Cx* base) const {
         FastFftTab T;
         T.W = base;
         T.V = base + m;
         T.U = base + m + mv;
+        T.W2 = base + o_w2;
+        T.W3 = base + o_w3;
+        T.V4 = base + o_v4;
+        T.V5 = base + o_v5;
         for (size_t i = 0; i < 16; ++i) T.w0[i] = i < m ? data[i] : Cx{1.0, 0.0};
+        for (size_t i = 0; i < 16; ++i) T.u0[i] = u0[i];
         return T;
     }
 };

@@ -176,7 +176,9 @@ def test_fused_mode_equals_cpu_replay(pkg, ctx, orc, hostsim, bs_d, big_n, n, bs
 
 def test_pbs_fused_mode_reference_parameters(pkg, ctx, orc):
     """Mode 2 at TFHE-T (tfhe/bootstrapping.rs:141-152), all 16 messages x 3 LUTs x 8 fresh encryptions: decryptions identical
-    to the table (and to the bit-identical mode), phases within 2^52 of the reference dataflow's (plaintext scale 2^59)."""
+    to the table (and to the bit-identical mode).  Once one digit of one CMUX rounds the other way the two modes hold
+    different, equally valid encryptions, so their phases differ by the output noise itself (measured <= 2^52.4 here); both
+    stay within 2^55 of the encoded message, 1/8 of the decoding margin 2^58 (plaintext scale 2^59)."""
     from learn_fhe_b200 import tfhe
     P = orc.tfhe_testing_param()
     K = orc.TfheKey(P, 0x5EED0003)
@@ -195,7 +197,10 @@ def test_pbs_fused_mode_reference_parameters(pkg, ctx, orc):
         m_fast, ph_fast = K.decrypt(fast)
         m_exact, ph_exact = K.decrypt(exact)
         assert (m_fast == want).all() and (m_exact == want).all(), name
-        assert np.abs((ph_fast - ph_exact).astype(np.int64)).max() < 2 ** 52, name
+        enc = (want.astype(np.uint64) << np.uint64(64 - (P.log_p + P.padding))).astype(np.uint64)
+        assert np.abs((ph_fast - enc).astype(np.int64)).max() < 2 ** 55, name
+        assert np.abs((ph_exact - enc).astype(np.int64)).max() < 2 ** 55, name
+        assert np.abs((ph_fast - ph_exact).astype(np.int64)).max() < 2 ** 54, name
     bk.free()
 
 

@@ -24,7 +24,8 @@ for w in $WHAT; do
     case $w in
         fhew) TRAFFIC=fhew_blind_rotate_fast_kernel=16384 KEEP=1 run fhew fhew_blind_rotate_fast 1 python tools/prof_cmd.py fhew --batch 16384 ;;
         ntt) TRAFFIC= run ntt ntt_fast 12 python tools/prof_cmd.py ntt ;;
-        tfhe) TRAFFIC=tfhe_blind_rotate_kernel=16384 KEEP=1 run tfhe tfhe_blind_rotate 1 python tools/tfhe_bench.py tfhe --batch 16384 ;;
+        tfhe) TRAFFIC=tfhe_blind_rotate_fast_kernel=16384 KEEP=1 run tfhe tfhe_blind_rotate_fast 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 2 ;;
+        tfhe_exact) TRAFFIC=tfhe_blind_rotate_kernel=16384 KEEP=1 run tfhe_exact 'tfhe_blind_rotate_kernel' 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 0 ;;
         ckks) TRAFFIC= run ckks 'rns_|ckks_' 8 python tools/tfhe_bench.py ckks --count 128 ;;
         launches)
             python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/plain_bench.log 2>&1 || { echo "plain bench failed"; continue; }
