@@ -144,6 +144,21 @@ def fhew_algorithmic_counts(param, steps_ext, steps_auto):
     return ext + aut, mac
 
 
+WORKLOAD = ("FHEW NAND gate bootstrap (Fhew::op), FHEW-T (boolean.rs:225-239): N=512 Q=268409857 RGSW/RLWE B=2^7 d=4, "
+            "n_s=100 q_ks=2^16, w=10")
+
+
+def fhew_config(batch, world, strong):
+    """`config` of the JSON line, identical for the b200 arm and the reference arm of one invocation."""
+    total = batch if strong else batch * world
+    per = -(-total // world) if strong else batch
+    ct_words = per * 513
+    nset = max(2, int(np.ceil(160e6 / (2 * ct_words * 8))))
+    return {"workload": WORKLOAD, "batch_per_gpu": per, "global_batch": total,
+            "sharding": "by ciphertext, keys replicated (NCCL broadcast once)",
+            "l2": "inputs rotate over %d distinct in/out sets (%.0f MB) > L2" % (nset, nset * 2 * ct_words * 8 / 1e6)}
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle (port of the reference's algorithm and dataflow: u128 % modmul, 3 transforms per product,
     coefficient-form keys) on all host cores.  Rank 0 only."""
@@ -159,7 +174,7 @@ def run_reference(args, rank, world):
     bits = np.random.default_rng(3).integers(0, 2, size=2 * sample).astype(np.int32)
     cts = K.encrypt(bits, 3)
     lin = (cts[:sample] + cts[sample:]) % np.uint64(P.big_q)
-    for _ in range(args.warmup_ref):
+    for _ in range(args.warmup):  # W untimed warm-up steps, each one gate per host thread
         K.op([1, 1, 1, 0], lin[:cores], threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -168,11 +183,13 @@ def run_reference(args, rank, world):
     assert (K.decrypt(out) == 1 - (bits[:sample] & bits[sample:])).all()
     v = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.scaling == "strong" else "weak",
             "vs_baseline": None, "dtype": "u64 (u128 % modmul)", "data": "synthetic",
-            "config": {"workload": "FHEW NAND gate bootstrap, FHEW-T (boolean.rs:225-239): N=512 Q=268409857 d=4 n_s=100 w=10",
-                       "batch_per_step": sample, "note": "CPU restatement of the reference (Rust toolchain absent); bounded sample"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d gates/step x %d steps" % (sample, args.steps)},
+            "config": fhew_config(args.batch, world, args.scaling == "strong"),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "each step = %d gates of the workload (bounded sample) on %d threads, %d steps; CPU restatement of the "
+                                       "reference (no Rust toolchain in the image)" % (sample, cores, args.steps)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -248,6 +265,22 @@ def device_ms(torch, stream, fn, warmup, steps):
     return e0.elapsed_time(e1)
 
 
+def wall_s(torch, dist, world, fn, warmup, steps):
+    """Wall-clock seconds of `steps` calls of a host-slice (`_host`) entry point, barrier + synchronize on both sides."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    barrier()
+    return time.perf_counter() - t0
+
+
 def max_over_ranks(torch, dist, world, dev, x):
     t = torch.tensor([x], dtype=torch.float64, device=dev)
     if world > 1:
@@ -255,16 +288,24 @@ def max_over_ranks(torch, dist, world, dev, x):
     return float(t.item())
 
 
-def tfhe_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps, synthetic_n1024=False):
-    """BASELINE configs[2]: TFHE programmable bootstrapping at the reference parameter set (tfhe/bootstrapping.rs:141-152:
-    n=1024, N=2048, k=1, TGGSW B=2^23 d=1, key switch B=2^4 d=5), `batch` synthetic LWE ciphertexts per GPU, keys uploaded on
-    rank 0 and broadcast once.  Timing is value independent; parity (bit-exact vs the oracle) is in tests/test_gpu_tfhe.py."""
+def tfhe_param(pkg, synthetic_n1024):
     from learn_fhe_b200 import tfhe
+    if synthetic_n1024:  # BASELINE configs[2] also names N=1024, for which the reference has no parameter set
+        return pkg.TfheParam(log_p=2, padding=1, n=630, ks_log_b=2, ks_d=8, log_big_n=10, k=1, bs_log_b=7, bs_d=3)
+    return tfhe.bootstrapping_testing_param()
+
+
+def tfhe_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps, synthetic_n1024=False, strong=False):
+    """BASELINE configs[2]: TFHE programmable bootstrapping at the reference parameter set (tfhe/bootstrapping.rs:141-152:
+    n=1024, N=2048, k=1, TGGSW B=2^23 d=1, key switch B=2^4 d=5), `batch` synthetic LWE ciphertexts per GPU (strong=True:
+    `batch` in total, split contiguously over the ranks), keys uploaded on rank 0 and broadcast once.  Headline = mode 2, the
+    fused bounded-error blind rotation (north_star: floating-point path within a stated bound, decryptions identical); the
+    bit-identical reference dataflow (mode 0) is timed beside it.  Timing is value independent; parity of both modes is in
+    tests/test_gpu_tfhe.py and re-checked on a sample in the cpu_baseline leg."""
+    from learn_fhe_b200 import shard, tfhe
     dev = "cuda:%d" % local
     stream = torch.cuda.current_stream(local)
-    P = tfhe.bootstrapping_testing_param()
-    if synthetic_n1024:  # BASELINE configs[2] also names N=1024, for which the reference has no parameter set (SURVEY.md §8d C3)
-        P = pkg.TfheParam(log_p=2, padding=1, n=630, ks_log_b=2, ks_d=8, log_big_n=10, k=1, bs_log_b=7, bs_d=3)
+    P = tfhe_param(pkg, synthetic_n1024)
     n, N, k = P.n, P.big_n, P.k
     rng = np.random.default_rng(0x5EED0002)
     shapes = [(n, (k + 1) * P.bs_d, k + 1, N), (k * N * P.ks_d, n), (k * N * P.ks_d,)]
@@ -276,51 +317,104 @@ def tfhe_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps, synthetic_
     del key_np
     if world > 1:
         bk.broadcast(dist, root=0)
-    lut = pkg.to_dev(np.random.default_rng(5).integers(0, 1 << 63, size=N, dtype=np.uint64), local)
-    cts = torch.randint(-(1 << 62), 1 << 62, (batch, n + 1), dtype=torch.int64, device=dev)
+    total = batch if strong else batch * world
+    mine = (lambda lo_hi: lo_hi[1] - lo_hi[0])(shard.shard_range(total, rank, world)) if strong else batch
+    lut_np = np.random.default_rng(5).integers(0, 1 << 63, size=N, dtype=np.uint64)
+    lut = pkg.to_dev(lut_np, local)
+    cts = torch.randint(-(1 << 62), 1 << 62, (mine, n + 1), dtype=torch.int64, device=dev)
     out = torch.empty_like(cts)
-    tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out)  # warm-up (allocations, tables)
-    ctx.prof_begin()
-    ms = device_ms(torch, stream, lambda: tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out), 0, steps)
-    prof = ctx.prof_end()
-    ms = max_over_ranks(torch, dist, world, dev, ms)
-    br = prof.get("tfhe_blind_rotate_kernel", {"ms": 0.0, "launches": 1})
-    br_ms = br["ms"] / max(1, br["launches"])
-    # f64 operations of the reference dataflow per PBS: n CMUX x [(k+1)d forward + (k+1)^2 d inverse] FFTs of N/2 points,
-    # 10 flops per radix-2 butterfly (4 mul + 6 add, never fused) + twist / pointwise / untwist
+    step = lambda: tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out)
+    res = {"metric": "tfhe_pbs_per_sec", "unit": "PBS/s", "batch_per_gpu": mine, "global_batch": total, "steps": steps,
+           "scaling": "strong" if strong else "weak",
+           "config": ("synthetic, not from the reference: n=630 N=1024 k=1 B=2^7 d=3, ks B=2^2 d=8" if synthetic_n1024 else
+                      "TFHE-T (tfhe/bootstrapping.rs:141-152): n=1024 N=2048 k=1 B=2^23 d=1, ks B=2^4 d=5"),
+           "key_bytes": bk.nbytes}
     m, lg, nl = N // 2, (N // 2).bit_length() - 1, (k + 1) * P.bs_d
-    ffts = n * (nl + (k + 1) * nl)
-    flops = ffts * (m // 2) * lg * 10 + n * (nl * m * 6 + (k + 1) * nl * m * (6 + 8))
-    # The reference rounds every product and every sum separately (c64.rs / fft.rs use plain f64 * and +), so a bit-identical
-    # kernel cannot contract them into FMAs: the binding rate is one f64 operation per lane per clock.  Nominal B200 figure
-    # (64 FP64 lanes per SM per clock at the maximum SM clock; MEASURED_PEAKS.json has no f64 entry).
-    fp64_ops_peak = 148 * 64 * 1.965e9
-    res = {"metric": "tfhe_pbs_per_sec", "value": batch * world * steps / (ms * 1e-3), "unit": "PBS/s", "batch_per_gpu": batch,
-           "steps": steps, "ms_per_step": ms / steps,
-           "config": ("synthetic, not from the reference: n=630 N=1024 k=1 B=2^7 d=3, ks B=2^2 d=8; bit-exact f64 FFT dataflow" if synthetic_n1024 else
-                      "TFHE-T (tfhe/bootstrapping.rs:141-152): n=1024 N=2048 k=1 B=2^23 d=1, ks B=2^4 d=5; bit-exact f64 FFT dataflow"),
-           "key_bytes": bk.nbytes,
-           "kernels": {kk: {"ms_per_launch": v["ms"] / v["launches"], "launches": v["launches"]} for kk, v in prof.items()},
-           "roofline": {"bound": "fp64", "kernel": "tfhe_blind_rotate_kernel", "achieved": flops * batch / (br_ms * 1e-3) / 1e12 if br_ms else None,
-                        "peak": fp64_ops_peak / 1e12,
-                        "unit": "Tflop/s f64 (algorithmic unfused multiplies and adds of the reference dataflow; peak = nominal "
-                                "non-FMA issue rate, 64 lanes/SM/clk x 148 SMs x 1.965 GHz)",
-                        "frac": flops * batch / (br_ms * 1e-3) / fp64_ops_peak if br_ms else None,
-                        "frac_vs_fma_peak": flops * batch / (br_ms * 1e-3) / (2 * fp64_ops_peak) if br_ms else None,
-                        "traffic": ncu_traffic("tfhe_blind_rotate_kernel", batch), "flops_per_pbs": flops}}
-    # optional evaluation mode: products summed in the Fourier domain (within the reference's error bound, decryptions
-    # identical; NOT bit-identical, so it is reported beside the headline, never as it)
-    bk.set_mode(True)
-    tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out)
-    ms2 = device_ms(torch, stream, lambda: tfhe.Bootstrapping.bootstrap_dev(bk, lut, cts, out), 0, steps)
-    ms2 = max_over_ranks(torch, dist, world, dev, ms2)
-    res["fourier_acc_mode"] = {"value": batch * world * steps / (ms2 * 1e-3), "unit": "PBS/s", "ms_per_step": ms2 / steps,
-                               "parity": "decryptions identical; torus words within 2^52 of the reference dataflow (tests/test_gpu_tfhe.py)"}
-    bk.set_mode(False)
+    pk = ctx.fp64_peak()
+    for mode, name in ((2, "fused"), (0, "bit_exact")):
+        bk.set_mode(mode)
+        step()  # warm-up (allocations, tables)
+        ctx.prof_begin()
+        ms = device_ms(torch, stream, step, 1, steps)
+        prof = ctx.prof_end()
+        ms = max_over_ranks(torch, dist, world, dev, ms)
+        kname = "tfhe_blind_rotate_fast_kernel" if mode == 2 else "tfhe_blind_rotate_kernel"
+        br = prof.get(kname, {"ms": 0.0, "launches": 1})
+        br_ms = br["ms"] / max(1, br["launches"])
+        # algorithmic f64 work per PBS: n CMUX x [(k+1)d forward + I inverse] FFTs of N/2 points, 10 flops per radix-2 butterfly
+        # (4 mul + 6 add) + pointwise products (6 flops) and sums (2); I = (k+1) when the products are summed in the Fourier
+        # domain (mode 2), (k+1)^2 d in the reference dataflow (mode 0, every product rounded on its own)
+        inv = (k + 1) if mode == 2 else (k + 1) * nl
+        flops = n * ((nl + inv) * (m // 2) * lg * 10 + (k + 1) * nl * m * 8)
+        # peak: MEASURED on this device by fhe_diag_fp64_peak (csrc/diag.cu): DFMA counts two flops; the bit-identical mode may
+        # not contract (the reference rounds every product and sum), so its binding rate is the DADD / DMUL issue rate
+        peak = 2e12 * pk["dfma"] if mode == 2 else 1e12 * min(pk["dadd"], pk["dmul"])
+        ach = flops * mine / (br_ms * 1e-3) if br_ms else None
+        r = {"value": total * steps / (ms * 1e-3), "unit": "PBS/s", "ms_per_step": ms / steps,
+             "kernels": {kk: {"ms_per_launch": v["ms"] / v["launches"], "launches": v["launches"]} for kk, v in prof.items()},
+             "roofline": {"bound": "fp64", "kernel": kname, "achieved": ach / 1e12 if ach else None, "peak": peak / 1e12,
+                          "unit": "Tflop/s f64 (algorithmic; peak = measured %s rate of this device, csrc/diag.cu)" % ("DFMA x 2" if mode == 2 else "DADD/DMUL"),
+                          "frac": ach / peak if ach else None, "traffic": ncu_traffic(kname, mine), "flops_per_pbs": flops,
+                          "fp64_peaks_tinstr": pk,
+                          "ncu": "profiles/r02_ncu_full_tfhe_fused_b16384.csv: the busiest unit is the shared-memory / L1 data path "
+                                 "(LSU wavefronts 74 %), FP64 pipe 43 % of issue slots" if mode == 2 else "profiles/r01_ncu_full_tfhe_b16384.csv"}}
+        if mode == 2:
+            r["parity"] = "same digits and exact sums as the reference; one rounding per output; |CMUX output - reference| < (k+1) d 2^(64+log_b+log_n-53); decryptions identical"
+            res.update(r)
+            res["mode"] = "fused bounded-error blind rotation (fhe_tfhe_key_set_mode 2)"
+        else:
+            r["parity"] = "raw torus words bit-identical to the reference dataflow"
+            res["bit_exact_mode"] = r
+    # e2e: the host-slice C-ABI call with pinned host buffers, H2D + D2H inside the timed region (mode 2)
+    bk.set_mode(2)
+    h_in = torch.empty((mine, n + 1), dtype=torch.int64).pin_memory()
+    h_out = torch.empty((mine, n + 1), dtype=torch.int64).pin_memory()
+    h_in.copy_(cts)
+    h_lut = torch.from_numpy(lut_np.view(np.int64)).pin_memory()
+    host = lambda: ctx.call("fhe_tfhe_pbs_batch_host", bk.h, pkg.hptr(h_lut.numpy()), mine, pkg.hptr(h_in.numpy()), pkg.hptr(h_out.numpy()))
+    sec = max_over_ranks(torch, dist, world, dev, wall_s(torch, dist, world, host, 1, steps))
+    res["e2e"] = {"value": total * steps / sec, "unit": "PBS/s", "h2d_bytes_per_step": int(mine * (n + 1) * 8 + N * 8),
+                  "d2h_bytes_per_step": int(mine * (n + 1) * 8), "api": "fhe_tfhe_pbs_batch_host"}
+    step()
+    torch.cuda.synchronize()
+    assert np.array_equal(pkg.to_host(out), h_out.numpy().view(np.uint64)), "TFHE device and host paths disagree"
     bk.free()
     del cts, out
     torch.cuda.empty_cache()
     return res
+
+
+def tfhe_cpu_leg(pkg, ctx, torch, local, cores, synthetic_n1024=False):
+    """cpu_baseline of the TFHE leg: the oracle's PBS (reference dataflow, f64 FFT of c64.rs) on all host threads, on real
+    encryptions under a real key; the same ciphertexts then go through the GPU: mode 0 must be bit-identical, mode 2 must
+    decrypt identically."""
+    from oracle import orc
+    from learn_fhe_b200 import tfhe
+    P = orc.tfhe_testing_param()
+    pp = tfhe_param(pkg, synthetic_n1024)
+    P.n, P.big_n, P.k, P.bs_log_b, P.bs_d, P.ks_log_b, P.ks_d, P.log_p, P.padding = (pp.n, pp.big_n, pp.k, pp.bs_log_b, pp.bs_d,
+                                                                                   pp.ks_log_b, pp.ks_d, pp.log_p, pp.padding)
+    K = orc.TfheKey(P, 0x5EED0003)
+    ex = K.export()
+    sample = 3 * cores
+    msgs = (np.arange(sample, dtype=np.uint64) * np.uint64(7)) % np.uint64(1 << P.log_p)
+    cts = K.encrypt(msgs, 11)
+    table = ((3 * np.arange(1 << P.log_p) + 1) % (1 << P.log_p)).astype(np.uint64)
+    v = K.lut_poly(table)
+    t0 = time.perf_counter()
+    ref = K.bootstrap(v, cts, threads=cores)
+    dt = time.perf_counter() - t0
+    bk = tfhe.BootstrappingKey(ctx, pp, ex["brk"], ex["ksk_a"], ex["ksk_b"])
+    lut = tfhe.encode_lut(pp, v)
+    exact = tfhe.Bootstrapping.bootstrap(bk, lut, cts)
+    assert np.array_equal(exact, ref), "TFHE mode 0 differs from the oracle"
+    bk.set_mode(2)
+    fused = tfhe.Bootstrapping.bootstrap(bk, lut, cts)
+    want = table[msgs.astype(np.int64)]
+    assert np.array_equal(K.decrypt(fused)[0], want) and np.array_equal(K.decrypt(ref)[0], want), "TFHE mode 2 decrypts differently"
+    bk.free()
+    return {"value": sample / dt, "unit": "PBS/s", "cores": cores, "kind": "port",
+            "sample": "%d PBS of the same parameter set on %d threads (%.1f s); GPU mode 0 bit-identical, mode 2 decryptions identical" % (sample, cores, dt)}
 
 
 def ckks_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps):
@@ -332,8 +426,14 @@ def ckks_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps):
     log_n, L = 16, 8
     P = ckks.CkksParam.new(ctx, log_n, 55, L)
     rng = np.random.default_rng(0x5EED0003)
-    ksk = np.stack([np.stack([rng.integers(0, q, size=P.n, dtype=np.uint64) for q in P.qs + P.ps]) for _ in range(2)])
+    if rank == 0:  # the relinearisation key exists on rank 0 only and reaches the other ranks by one NCCL broadcast
+        ksk = np.stack([np.stack([rng.integers(0, q, size=P.n, dtype=np.uint64) for q in P.qs + P.ps]) for _ in range(2)])
+    else:
+        ksk = np.zeros((2, 2 * L, P.n), dtype=np.uint64)
     rlk = ckks.CkksKeySwitchingKey(P, ksk)
+    del ksk
+    if world > 1:
+        rlk.broadcast(dist, root=0)
 
     def rand_ct():
         t = torch.empty((batch, 2, L, P.n), dtype=torch.int64, device=dev)
@@ -369,13 +469,85 @@ def ckks_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps):
         t_min = (n_bf + n_mm) * per * batch
         res["roofline"] = {"bound": "int32", "kernel": "whole Ckks::mul (ntt_fast_* 60 %, rns_rescale 20 %)", "achieved": 9 * (n_bf + n_mm) * batch / (ms / steps * 1e-3) / 1e12,
                            "peak": 9 / per / 1e12, "unit": "Tmul/s (algorithmic 32-bit products; peak = measured INT32 multiply-pipe rate for 3 IMAD.WIDE + 2 IMAD.HI + 4 IMAD)",
-                           "frac": t_min / (ms / steps * 1e-3), "traffic": None,
-                           "butterflies_per_mult": n_bf, "pointwise_modmuls_per_mult": n_mm}
+                           "frac": t_min / (ms / steps * 1e-3), "traffic": ncu_traffic("ckks_mul_whole_op", batch),
+                           "traffic_note": "sum of dram read + write bytes over every launch of one Ckks::mul batch (profiles/ncu_traffic.json)",
+                           "algorithmic_bytes": io_bytes, "butterflies_per_mult": n_bf, "pointwise_modmuls_per_mult": n_mm}
+    # e2e: host-slice C-ABI call, pinned host ciphertexts in and out (bounded to 64 pairs: 1 GiB in + 0.44 GiB out per step)
+    eb = min(batch, 64)
+    h0 = torch.empty((eb, 2, L, P.n), dtype=torch.int64).pin_memory()
+    h1 = torch.empty((eb, 2, L, P.n), dtype=torch.int64).pin_memory()
+    ho = torch.empty((eb, 2, L - 1, P.n), dtype=torch.int64).pin_memory()
+    h0.copy_(ct0[:eb])
+    h1.copy_(ct1[:eb])
+    host = lambda: ctx.call("fhe_ckks_mul_relin_rescale_batch_host", P.h, rlk.h, L, eb, pkg.hptr(h0.numpy()), pkg.hptr(h1.numpy()), pkg.hptr(ho.numpy()))
+    sec = max_over_ranks(torch, dist, world, dev, wall_s(torch, dist, world, host, 1, steps))
+    res["e2e"] = {"value": eb * world * steps / sec, "unit": "mult/s", "batch_per_gpu": eb, "h2d_bytes_per_step": int(h0.numel() * 16),
+                  "d2h_bytes_per_step": int(ho.numel() * 8), "api": "fhe_ckks_mul_relin_rescale_batch_host"}
+    torch.cuda.synchronize()
+    assert torch.equal(ho, out[:eb].cpu()), "CKKS device and host paths disagree"
+    del h0, h1, ho
     rlk.free()
     P.free()
     del ct0, ct1, out
     torch.cuda.empty_cache()
     return res
+
+
+def ckks_cpu_leg(pkg, ctx, cores):
+    """cpu_baseline of the CKKS leg: the oracle's Ckks::mul (reference dataflow: coefficient-form products of 3 transforms
+    each, u128 % arithmetic) at N=2^16, L=8 on all host threads, one pair per thread; the same pairs then go through the GPU
+    path and must come back bit-identical."""
+    from oracle import orc
+    from learn_fhe_b200 import ckks
+    log_n, L = 16, 8
+    K = orc.CkksKey(log_n, 55, L, 0x5EED0004)
+    n = 1 << log_n
+    c0 = np.stack([K.encrypt((np.arange(n, dtype=np.int64) * (i + 3)) % 17 - 8, L, 70 + i) for i in range(cores)])
+    c1 = np.stack([K.encrypt((np.arange(n, dtype=np.int64) * (i + 5)) % 5 - 2, L, 90 + i) for i in range(cores)])
+    t0 = time.perf_counter()
+    ref = K.mul(c0, c1, threads=cores)
+    dt = time.perf_counter() - t0
+    P = ckks.CkksParam(ctx, log_n, K.qs, K.ps)
+    rlk = ckks.CkksKeySwitchingKey(P, K.ksk(-1))
+    got = ckks.Ckks.mul(P, rlk, c0, c1)
+    assert np.array_equal(got, ref), "CKKS GPU output differs from the oracle"
+    rlk.free()
+    P.free()
+    return {"value": cores / dt, "unit": "mult/s", "cores": cores, "kind": "port",
+            "sample": "%d ciphertext pairs at N=2^16, L=8 on %d threads (%.1f s); GPU outputs bit-identical" % (cores, cores, dt)}
+
+
+def ntt_cpu_leg(pkg, ctx, cores, log_ns):
+    """cpu_baseline of the NTT sweep: the oracle's radix-2 in-place transform (util/src/ring/fft.rs:40-54, u128 % butterflies)
+    on all host threads, 16 polynomials per thread per size; the GPU transform of the same data must be bit-identical."""
+    from oracle import orc
+    from learn_fhe_b200 import util
+    out = {}
+    for log_n in log_ns:
+        q = pkg.first_two_adic_prime(55, log_n + 1)
+        n, polys = 1 << log_n, 16 * cores
+        a = orc.residues(0x5EED0000 + log_n, polys * n, q).reshape(polys, n)
+        t0 = time.perf_counter()
+        ref = orc.ntt_fwd(q, a, threads=cores)
+        dt = time.perf_counter() - t0
+        x = a.copy()
+        util.nega_cyclic_ntt_in_place(ctx, q, x)
+        assert np.array_equal(x, ref), "GPU NTT differs from the oracle at log_n %d" % log_n
+        out[log_n] = {"value": 2.0 * polys * n * 8 / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                      "sample": "%d polynomials on %d threads (%.3f s); GPU output bit-identical" % (polys, cores, dt)}
+    return out
+
+
+def ntt_e2e(pkg, ctx, torch, log_n, batch, reps):
+    """fhe_ntt_fwd_host on pinned host polynomials (H2D + transform + D2H inside the timed region), u64 words."""
+    q = pkg.first_two_adic_prime(55, log_n + 1)
+    n = 1 << log_n
+    h = torch.empty((batch, n), dtype=torch.int64).pin_memory()
+    h.random_(0, 1 << 27)
+    fn = lambda: ctx.call("fhe_ntt_fwd_host", q, pkg.hptr(h.numpy()), n, batch)
+    sec = wall_s(torch, None, 1, fn, 1, reps)
+    return {"value": 2.0 * batch * n * 8 * reps / sec / 1e9, "unit": "GB/s", "log_n": log_n, "batch": batch, "h2d_bytes_per_step": batch * n * 8,
+            "d2h_bytes_per_step": batch * n * 8, "api": "fhe_ntt_fwd_host"}
 
 
 def next_rows_leg(pkg, ctx, torch, bk, param, local):
@@ -464,10 +636,12 @@ def main():
     ap.add_argument("--no-tfhe", action="store_true", help="skip the TFHE PBS leg (BASELINE configs[2])")
     ap.add_argument("--no-ckks", action="store_true", help="skip the CKKS hom-mult leg (BASELINE configs[3])")
     ap.add_argument("--no-next", action="store_true", help="skip the SURVEY 8(f) legs (u8 circuits, 64-bit FHEW, CKKS mul_mat)")
+    ap.add_argument("--no-strong", action="store_true", help="multi-GPU runs: skip the second (other) scaling curve")
     ap.add_argument("--tfhe-batch", type=int, default=16384, help="PBS per GPU per step")
     ap.add_argument("--ckks-batch", type=int, default=512, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch gates per GPU; strong: --batch gates in total, split contiguously over the ranks (configs[2]: 16384/R)")
     args = ap.parse_args()
-    args.warmup_ref = max(1, min(args.warmup, 1))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -486,8 +660,9 @@ def main():
     dev = "cuda:%d" % local
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+        # NCCL_DEBUG is left to the caller (default WARN); its log goes to stderr so that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(dev))
     hbm_peak, peak_src, peak_json = peaks()
     ctx = pkg.Context(local)
@@ -507,7 +682,11 @@ def main():
     f_np = fhew.gate_poly(param, table)
     post = fhew.big_q_by_8(param)
     f_dev = pkg.to_dev(f_np, local)
-    B = args.batch
+    from learn_fhe_b200 import shard
+    strong = args.scaling == "strong"
+    total = args.batch if strong else args.batch * world
+    lo, hi = shard.shard_range(total, rank, world) if strong else (0, args.batch)
+    B = hi - lo  # gates of this rank per step
     ct_words = B * (param.n + 1)
     # rotate over enough distinct input/output sets to exceed L2 (126 MB)
     nset = max(2, int(np.ceil(160e6 / (2 * ct_words * 8))))
@@ -546,7 +725,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = B * world * args.steps / (ms_total * 1e-3)
+    value = total * args.steps / (ms_total * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
     # dominant kernel timed alone on its stream (blind rotation): live CUDA events around the kernel launch only
@@ -572,7 +751,7 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * args.steps / float(t.item())
+    e2e_value = total * args.steps / float(t.item())
     # device-path outputs must equal host-path outputs on the same inputs (consistency, cheap)
     chk_in = pkg.to_dev(h_in.numpy().view(np.uint64)[:64].copy(), local)
     chk_out = torch.empty_like(chk_in)
@@ -591,13 +770,39 @@ def main():
     ntt = None
     if rank == 0 and not args.no_ntt:
         ntt = ntt_sweep(pkg, ctx, torch, hbm_peak, args.ntt_reps, list(range(10, 17)), 4096)
+        ntt_host = ntt_e2e(pkg, ctx, torch, 16, 1024, 3)
 
     # free the FHEW batch buffers before the wider legs
     del ins, outs
     torch.cuda.empty_cache()
-    tfhe_res = None if args.no_tfhe else tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, max(1, min(args.steps, 2)))
-    tfhe_res_1024 = None if args.no_tfhe else tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, max(1, min(args.steps, 2)), True)
+    tsteps = max(1, min(args.steps, 2))
+    tfhe_res = None if args.no_tfhe else tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, tsteps, False, strong)
+    tfhe_res_1024 = None if args.no_tfhe else tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, tsteps, True, strong)
     ckks_res = None if args.no_ckks else ckks_leg(pkg, ctx, torch, dist, world, rank, local, args.ckks_batch, max(1, min(args.steps, 3)))
+
+    # the other scaling curve (configs[2]: the 16 384 batch split 16 384 / R): measured in the same run when there is more than one
+    # rank, so that one driver sweep over N yields both the weak and the strong line
+    other = None
+    if world > 1 and not args.no_strong:
+        o_strong = not strong
+        o_total = args.batch if o_strong else args.batch * world
+        olo, ohi = shard.shard_range(o_total, rank, world) if o_strong else (0, args.batch)
+        ob = ohi - olo
+        o_in = pkg.to_dev(synth_cts(param, ob, 5000 + rank), local)
+        o_out = torch.empty_like(o_in)
+        ostep = lambda: fhew.Bootstrapping.bootstrap_dev(bk, f_dev, o_in, o_out, post_add=post)
+        for _ in range(args.warmup):
+            ostep()
+        barrier()
+        oms = max_over_ranks(torch, dist, world, dev, device_ms(torch, stream, ostep, 0, args.steps))
+        other = {"scaling": "strong" if o_strong else "weak", "metric": METRIC, "value": o_total * args.steps / (oms * 1e-3), "unit": UNIT,
+                 "global_batch": o_total, "batch_per_gpu": ob, "ms_per_step": oms / args.steps,
+                 "resident_ctas_per_gpu": 7 * ctx.sm_count,
+                 "note": "strong scaling is limited by the partial last wave: %d gates on %d resident CTAs per GPU = %.2f waves" % (ob, 7 * ctx.sm_count, ob / (7.0 * ctx.sm_count))}
+        if not args.no_tfhe:
+            t_o = tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, tsteps, False, o_strong)
+            other["tfhe_pbs"] = {kk: t_o[kk] for kk in ("value", "unit", "global_batch", "batch_per_gpu", "ms_per_step", "scaling")}
+        del o_in, o_out
 
     next_res = None
     if rank == 0 and not args.no_next:
@@ -629,15 +834,22 @@ def main():
             checked = False
         cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d gates of the same workload on %d threads (%.1f s)%s" % (sample, cores, dt, ", GPU outputs bit-identical" if checked else "")}
+        # the CPU path beside every other parameter set, same run, same box (north_star); each also re-checks GPU parity on its sample
+        if tfhe_res is not None:
+            tfhe_res["cpu_baseline"] = tfhe_cpu_leg(pkg, ctx, torch, local, cores, False)
+            tfhe_res_1024["cpu_baseline"] = tfhe_cpu_leg(pkg, ctx, torch, local, cores, True)
+        if ckks_res is not None:
+            ckks_res["cpu_baseline"] = ckks_cpu_leg(pkg, ctx, cores)
+        if ntt is not None:
+            ntt_cpu = ntt_cpu_leg(pkg, ctx, cores, [r["log_n"] for r in ntt if r["word_bits"] == 64])
+            for r in ntt:
+                r["cpu_baseline"] = ntt_cpu[r["log_n"]]
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "u32 (Q < 2^30 residues, u64 MAC accumulators)", "data": "synthetic",
-                "config": {"workload": "FHEW NAND gate bootstrap (Fhew::op), FHEW-T (boolean.rs:225-239): N=512 Q=268409857 "
-                                       "RGSW/RLWE B=2^7 d=4, n_s=100 q_ks=2^16, w=10",
-                           "batch_per_gpu": B, "global_batch": B * world, "sharding": "by ciphertext, keys replicated (NCCL broadcast once)",
-                           "l2": "inputs rotate over %d distinct in/out sets (%.0f MB) > L2" % (nset, nset * 2 * ct_words * 8 / 1e6)},
+                "config": fhew_config(args.batch, world, strong),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ct_words * 8 + param.n * 8),
                         "d2h_bytes_per_step": int(ct_words * 8)},
                 "gpu_launches": int(launches), "clocks": clocks,
@@ -647,14 +859,17 @@ def main():
             line["tfhe_pbs_n1024_synthetic"] = tfhe_res_1024
         if ckks_res is not None:
             line["ckks_mul"] = ckks_res
+        if other is not None:
+            line["other_scaling"] = other
         if next_res is not None:
             line["next_rows"] = next_res
         if ntt is not None:
             line["ntt"] = ntt
             best = max(ntt, key=lambda r: (r["log_n"], r["word_bits"]))
             line["roofline_ntt"] = {"bound": "hbm", "achieved": best["fwd_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                                    "frac": best["fwd_frac_hbm"], "traffic": None,
-                                    "kernel": "ntt fwd u64 N=2^%d batch 4096" % best["log_n"]}
+                                    "frac": best["fwd_frac_hbm"], "traffic": ncu_traffic("ntt_fwd_u64_2^16", 4096),
+                                    "algorithmic_bytes": 2 * 4096 * (1 << best["log_n"]) * 8,
+                                    "kernel": "ntt fwd u64 N=2^%d batch 4096" % best["log_n"], "e2e": ntt_host}
             # the transforms are bound by the INT32 multiply pipe, not by HBM: a 64-bit Shoup butterfly is 9 32-bit products
             # (3 IMAD.WIDE + 2 IMAD.HI + 4 IMAD), a 32-bit one 3 (2 IMAD + 1 IMAD.HI); same measured rates as `roofline`
             pk = kt["roofline"]["int32_peaks_tops"]

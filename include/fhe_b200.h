@@ -166,6 +166,10 @@ fhe_status fhe_fhew_bootstrap_batch(fhe_ctx* ctx, const fhe_fhew_key* key, const
                                     const uint64_t* d_ct_in, uint64_t* d_ct_out);
 fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* f, uint64_t post_add, size_t count,
                                          const uint64_t* ct_in, uint64_t* ct_out);
+/* The device-pointer entry points above are asynchronous and defer the reference's `unreachable!` check (an even non-zero
+ * blind-rotation exponent, bootstrapping.rs:217-222; cannot happen after mod_switch_odd): this call synchronises the context's
+ * stream and returns FHE_EINVAL if any bootstrap with this key met one since the flag was last reset (every launch resets it). */
+fhe_status fhe_fhew_key_check_error(fhe_ctx* ctx, const fhe_fhew_key* key);
 /* first three steps of bootstrap (mod_switch -> Lwe::key_switch -> mod_switch_odd; lwe.rs:90-99,151-160):
  * out [count][n_s+1] residues mod 2N */
 fhe_status fhe_fhew_prologue_batch(fhe_ctx* ctx, const fhe_fhew_key* key, size_t count, const uint64_t* d_ct_in, uint64_t* d_out);
@@ -238,6 +242,10 @@ typedef struct fhe_ckks_ksk fhe_ckks_ksk;
  * coefficient form; transformed once to evaluation form. */
 fhe_status fhe_ckks_ksk_upload(fhe_ctx* ctx, fhe_ckks_ctx* ck, const uint64_t* ksk, fhe_ckks_ksk** out);
 void fhe_ckks_ksk_free(fhe_ctx* ctx, fhe_ckks_ksk* ksk);
+/* device bytes of the evaluation-form key and its one-time NCCL broadcast from `root` (keys are generated / uploaded on one rank,
+ * 16 MiB per key-switching key at N = 2^16, L = 8) */
+size_t fhe_ckks_ksk_bytes(const fhe_ckks_ksk* ksk);
+fhe_status fhe_ckks_ksk_broadcast(fhe_ctx* ctx, fhe_ckks_ksk* ksk, void* nccl_comm, int root);
 /* Ckks::mul = tensor product + relinearize + rescale (ckks.rs:255-272) on `count` pairs at level l (l limbs):
  * ct layout [count][2 (b, a)][l][N] coefficient form (ckks.rs:112-121); out [count][2][l-1][N] */
 fhe_status fhe_ckks_mul_relin_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* rlk, size_t level, size_t count,

@@ -145,6 +145,7 @@ def lib():
     L.fhe_fhew_external_product.argtypes = [vp, vp, sz, vp, vp, vp]
     L.fhe_fhew_automorphism.argtypes = [vp, vp, sz, vp, vp, vp]
     L.fhe_fhew_blind_rotate_batch.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.fhe_fhew_key_check_error.argtypes = [vp, vp]
     # TFHE
     if hasattr(L, "fhe_tfhe_key_upload"):
         L.fhe_tfhe_key_upload.argtypes = [vp, C.POINTER(TfheParam), vp, vp, vp, C.POINTER(vp)]
@@ -168,6 +169,9 @@ def lib():
         L.fhe_ckks_ksk_upload.argtypes = [vp, vp, vp, C.POINTER(vp)]
         L.fhe_ckks_ksk_free.argtypes = [vp, vp]
         L.fhe_ckks_ksk_free.restype = None
+        L.fhe_ckks_ksk_bytes.argtypes = [vp]
+        L.fhe_ckks_ksk_bytes.restype = sz
+        L.fhe_ckks_ksk_broadcast.argtypes = [vp, vp, vp, C.c_int]
         L.fhe_ckks_mul_relin_rescale_batch.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
         L.fhe_ckks_mul_relin_rescale_batch_host.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
         L.fhe_ckks_key_switch.argtypes = [vp, vp, vp, i64, sz, sz, vp, vp]

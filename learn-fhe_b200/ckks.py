@@ -86,6 +86,16 @@ class CkksKeySwitchingKey:
             self.param.ctx.L.fhe_ckks_ksk_free(self.param.ctx.h, self.h)
             self.h = None
 
+    @property
+    def nbytes(self):
+        return int(self.param.ctx.L.fhe_ckks_ksk_bytes(self.h))
+
+    def broadcast(self, dist, root=0):
+        """One-time NCCL broadcast of the evaluation-form key from `root` (every rank holds a key object of the same shape)."""
+        from . import nccl_comm_ptr
+        comm = nccl_comm_ptr(dist, "cuda:%d" % self.param.ctx.device)
+        self.param.ctx.call("fhe_ckks_ksk_broadcast", self.h, comm, root)
+
     def __del__(self):
         try:
             self.free()

@@ -295,6 +295,7 @@ struct fhe_ckks_ctx {
 };
 struct fhe_ckks_ksk {
     uint64_t* d_eval = nullptr;  // [2 (b,a)][2L][n] evaluation form
+    size_t bytes = 0;
 };
 
 namespace fhe {
@@ -431,7 +432,15 @@ fhe_status fhe_ckks_ksk_upload(fhe_ctx* ctx, fhe_ckks_ctx* ck, const uint64_t* k
         delete k;
         return st;
     }
+    k->bytes = words * 8;
     *out = k;
+    return FHE_OK;
+}
+size_t fhe_ckks_ksk_bytes(const fhe_ckks_ksk* ksk) { return ksk ? ksk->bytes : 0; }
+fhe_status fhe_ckks_ksk_broadcast(fhe_ctx* ctx, fhe_ckks_ksk* ksk, void* nccl_comm, int root) {
+    if (!ctx || !ksk) return FHE_EINVAL;
+    FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, ksk->d_eval, ksk->bytes));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FHE_OK;
 }
 void fhe_ckks_ksk_free(fhe_ctx* ctx, fhe_ckks_ksk* ksk) {

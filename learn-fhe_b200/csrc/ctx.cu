@@ -5,6 +5,8 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
+
 #include <cstring>
 #include "host_tables.hpp"
 
@@ -100,6 +102,23 @@ fhe_status ensure_scratch(fhe_ctx* ctx, size_t bytes, void** out) {
     return FHE_OK;
 }
 
+__global__ void validate_below_kernel(const uint32_t* __restrict__ idx, size_t count, uint32_t limit, int* __restrict__ flag) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        if (idx[i] >= limit) atomicOr(flag, 1);
+}
+fhe_status validate_below(fhe_ctx* ctx, const uint32_t* d_idx, size_t count, uint32_t limit, const char* what) {
+    if (!ctx->d_flag) FHE_CUDA(ctx, cudaMalloc((void**)&ctx->d_flag, sizeof(int)));
+    FHE_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    const unsigned grid = (unsigned)std::min<size_t>((count + 255) / 256, 1024);
+    validate_below_kernel<<<grid, 256, 0, ctx->stream>>>(d_idx, count, limit, ctx->d_flag);
+    FHE_CHECK(after_launch(ctx, "validate_below_kernel"));
+    int h = 0;
+    FHE_CUDA(ctx, cudaMemcpyAsync(&h, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h) return fail(ctx, FHE_EINVAL, "%s out of range (must be < %u)", what, limit);
+    return FHE_OK;
+}
+
 fhe_status ensure_stage_d(fhe_ctx* ctx, int slot, size_t bytes, void** out) {
     if (ctx->stage_d_bytes[slot] < bytes) {
         FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -157,6 +176,7 @@ void fhe_ctx_destroy(fhe_ctx* ctx) {
     for (auto& fn : ctx->cleanup) fn();
     for (auto& kv : ctx->fast_limbs) cudaFree(kv.second);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
     for (int i = 0; i < 3; ++i)
         if (ctx->stage_d[i]) cudaFree(ctx->stage_d[i]);
     for (auto& pe : ctx->prof_events) cudaEventDestroy(pe.second);

@@ -61,6 +61,7 @@ struct fhe_ctx {
     size_t stage_h_bytes[2] = {0, 0};
     void* stage_d[3] = {nullptr, nullptr, nullptr};
     size_t stage_d_bytes[3] = {0, 0, 0};
+    int* d_flag = nullptr;  // device word for the argument checks of the util-level entry points (validate_below)
 };
 
 namespace fhe {
@@ -112,6 +113,9 @@ fhe_status get_mod_info(fhe_ctx* ctx, uint64_t q, const ModInfo** out);
 fhe_status get_ntt_table(fhe_ctx* ctx, uint64_t q, int bits, size_t len, const NttTable** out);
 fhe_status get_ntt_table_locked(fhe_ctx* ctx, uint64_t q, int bits, size_t len, const NttTable** out);  // ctx->mu held
 fhe_status ensure_scratch(fhe_ctx* ctx, size_t bytes, void** out);
+// argument check of a device index array: FHE_EINVAL (naming `what`) unless every d_idx[i] < limit.  The reference panics on
+// such inputs (slice index out of bounds); here they must not become out-of-bounds device reads.  Synchronises the stream.
+fhe_status validate_below(fhe_ctx* ctx, const uint32_t* d_idx, size_t count, uint32_t limit, const char* what);
 // grow-only device staging buffer `slot` (0..2) for the *_host entry points
 fhe_status ensure_stage_d(fhe_ctx* ctx, int slot, size_t bytes, void** out);
 

@@ -379,6 +379,18 @@ static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_fhew_key* key, const 
     return after_launch(ctx, "fhew_blind_rotate_kernel");
 }
 
+// [count][n_s+1] u64 words mod 2N -> u32, checking what Bootstrapping::blind_rotate assumes of its input (bootstrapping.rs:217-222):
+// every word < 2N and every mask word odd or zero
+__global__ void fhew_narrow_check_kernel(const uint64_t* __restrict__ in, uint32_t* __restrict__ out, size_t words, uint32_t row, uint32_t two_n,
+                                         int* __restrict__ err) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t v = in[i];
+        const bool body = (i % row) == row - 1;
+        if (v >= two_n || (!body && v != 0 && (v & 1) == 0)) atomicOr(err, 1);
+        out[i] = (uint32_t)v;
+    }
+}
+
 static fhe_status check_err_flag(fhe_ctx* ctx, const fhe_fhew_key* key) {
     int h = 0;
     FHE_CUDA(ctx, cudaMemcpyAsync(&h, key->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -401,8 +413,9 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     FHE_REQUIRE(ctx, pp->log_n >= 2 && pp->log_n <= 11, "FHEW path supports 4 <= N <= 2048 (got log_n = %u)", pp->log_n);
     FHE_REQUIRE(ctx, pp->big_q < (1ull << 62), "FHEW path needs Q < 2^62");
     const bool wide = pp->big_q >= (1ull << 30);  // 64-bit residues (generic kernels only)
-    FHE_REQUIRE(ctx, wide ? (2 * pp->rgsw_d <= 32 && pp->rlwe_d <= 32) : 2 * pp->rgsw_d <= 16,
-                "too many digits: 2 * rgsw_d <= 16 for Q < 2^30 (64-bit MAC accumulator bound), <= 32 above");
+    FHE_REQUIRE(ctx, wide ? (2 * pp->rgsw_d <= 32 && pp->rlwe_d <= 32) : (2 * pp->rgsw_d <= 16 && pp->rlwe_d <= 16),
+                "too many digits: 2 * rgsw_d <= 16 and rlwe_d <= 16 for Q < 2^30 (a u64 accumulates that many unreduced q^2-sized "
+                "products), <= 32 above");
     FHE_REQUIRE(ctx, pp->q_ks >= 2 && pp->q_ks <= (1ull << 32) && (pp->q_ks & (pp->q_ks - 1)) == 0, "q_ks must be a power of two <= 2^32");
     FHE_REQUIRE(ctx, pp->w >= 1 && pp->w < 40, "window w must be in [1, 39]");
     FHE_REQUIRE(ctx, pp->rgsw_d >= 1 && pp->rlwe_d >= 1 && pp->ks_d >= 1 && pp->rgsw_log_b >= 1 && pp->rlwe_log_b >= 1 && pp->ks_log_b >= 1,
@@ -412,6 +425,11 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     // (the check against `wide` follows below, once it is known)
     FHE_REQUIRE(ctx, pp->n_s >= 1 && pp->n_s < 32768, "n_s out of range");
     const uint32_t n = 1u << pp->log_n;
+    // the LMKCDEY schedule scratch (u16 cnt[N] + sorted[n_s]) aliases the digit region of kmax * N residue words
+    FHE_REQUIRE(ctx, 2 * ((size_t)n + pp->n_s) <= (size_t)std::max(2 * pp->rgsw_d, pp->rlwe_d) * n * (wide ? 8 : 4),
+                "n_s = %u too large for N = %u with these decomposors (schedule scratch of 2 (N + n_s) bytes must fit the digit region)", pp->n_s, n);
+    for (size_t i = 0; i < (size_t)n * pp->ks_d * pp->n_s; ++i) FHE_REQUIRE(ctx, ksk_a[i] < pp->q_ks, "ksk_a word out of range (>= q_ks)");
+    for (size_t i = 0; i < (size_t)n * pp->ks_d; ++i) FHE_REQUIRE(ctx, ksk_b[i] < pp->q_ks, "ksk_b word out of range (>= q_ks)");
     const NttTable* t;
     FHE_CHECK(get_ntt_table(ctx, pp->big_q, wide ? 64 : 32, n, &t));
     fhe_fhew_key* key = new fhe_fhew_key();
@@ -572,6 +590,9 @@ static fhe_status fhew_step_api(fhe_ctx* ctx, const fhe_fhew_key* key, uint32_t 
                                 const uint64_t* d_acc_in, uint64_t* d_acc_out) {
     if (!ctx || !key) return FHE_EINVAL;
     if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_idx && d_acc_in && d_acc_out, "null pointer");
+    // brk[idx] needs idx < n_s, ak[idx] needs idx <= w (the reference panics on a slice index out of bounds)
+    FHE_CHECK(validate_below(ctx, d_idx, count, flag ? key->P.w + 1 : key->P.n_s, flag ? "automorphism key index" : "bootstrapping key index"));
     const uint32_t n = 1u << key->P.log_n;
     const size_t smem = (size_t)(2 + key->kmax) * n * (key->wide ? 8 : 4);
     unsigned grid;
@@ -599,17 +620,21 @@ fhe_status fhe_fhew_blind_rotate_batch(fhe_ctx* ctx, const fhe_fhew_key* key, co
                                        uint64_t* d_acc_out) {
     if (!ctx || !key) return FHE_EINVAL;
     if (count == 0) return FHE_OK;
-    // narrow the [count][n_s+1] u64 input to u32 through the prologue-free path: reuse scratch
+    FHE_REQUIRE(ctx, d_f && d_ct2n && d_acc_out, "null pointer");
+    // narrow the [count][n_s+1] u64 input to u32 on the device and validate it before any table is indexed with it
     void* scratch;
     const size_t words = count * (key->P.n_s + 1);
     FHE_CHECK(ensure_scratch(ctx, words * 4, &scratch));
-    std::vector<uint64_t> h(words);
-    FHE_CUDA(ctx, cudaMemcpyAsync(h.data(), d_ct2n, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<uint32_t> h32(words);
-    for (size_t i = 0; i < words; ++i) h32[i] = (uint32_t)h[i];
-    FHE_CUDA(ctx, cudaMemcpyAsync(scratch, h32.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream));
-    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FHE_CUDA(ctx, cudaMemsetAsync(key->d_err, 0, sizeof(int), ctx->stream));
+    fhew_narrow_check_kernel<<<(unsigned)std::min<size_t>((words + 255) / 256, 2048), 256, 0, ctx->stream>>>(
+        d_ct2n, (uint32_t*)scratch, words, key->P.n_s + 1, 2u << key->P.log_n, key->d_err);
+    FHE_CHECK(after_launch(ctx, "fhew_narrow_check_kernel"));
+    {
+        int h = 0;
+        FHE_CUDA(ctx, cudaMemcpyAsync(&h, key->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h) return fail(ctx, FHE_EINVAL, "blind rotation input must hold words < 2N with odd or zero mask words (bootstrapping.rs:217-222)");
+    }
     FHE_CHECK(run_blind_rotate<uint64_t>(ctx, key, d_f, (const uint32_t*)scratch, 0, count, d_acc_out, 1));
     return check_err_flag(ctx, key);
 }
@@ -679,6 +704,13 @@ fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, 
     else cudaDeviceSynchronize();
     for (auto& e : ev) cudaEventDestroy(e);
     return st;
+}
+
+// The device-resident entry points (fhe_fhew_bootstrap_batch) are asynchronous and do not read the key's error flag; this
+// call synchronises and reports it (FHE_EINVAL if a blind rotation since the last reset met an even non-zero exponent).
+fhe_status fhe_fhew_key_check_error(fhe_ctx* ctx, const fhe_fhew_key* key) {
+    if (!ctx || !key) return FHE_EINVAL;
+    return check_err_flag(ctx, key);
 }
 
 // one-time distribution of the (already transformed) key buffers from `root` (no upstream analogue)

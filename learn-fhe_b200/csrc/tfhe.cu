@@ -598,6 +598,7 @@ fhe_status fhe_tfhe_external_product(fhe_ctx* ctx, const fhe_tfhe_key* key, size
     if (!ctx || !key) return FHE_EINVAL;
     if (count == 0) return FHE_OK;
     FHE_REQUIRE(ctx, d_idx && d_glwe_in && d_glwe_out && d_glwe_in != d_glwe_out, "null or aliased pointer");
+    FHE_CHECK(validate_below(ctx, d_idx, count, key->P.n_lwe, "bootstrapping key index"));
     const size_t smem = tfhe_smem_bytes(key->P.k, key->P.bs_dec.d, key->P.log_n);
     unsigned grid;
     FHE_CHECK(tfhe_grid(ctx, tfhe_ext_kernel, smem, count, &grid));
@@ -610,6 +611,7 @@ fhe_status fhe_tfhe_cmux(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t count, co
     if (!ctx || !key) return FHE_EINVAL;
     if (count == 0) return FHE_OK;
     FHE_REQUIRE(ctx, d_idx && d_ct0 && d_ct1 && d_out && d_out != d_ct0 && d_out != d_ct1, "null or aliased pointer");
+    FHE_CHECK(validate_below(ctx, d_idx, count, key->P.n_lwe, "bootstrapping key index"));
     const size_t smem = tfhe_smem_bytes(key->P.k, key->P.bs_dec.d, key->P.log_n);
     unsigned grid;
     FHE_CHECK(tfhe_grid(ctx, tfhe_ext_kernel, smem, count, &grid));

@@ -147,6 +147,38 @@ def test_empty_batch_and_bad_parameters(pkg, ctx, orc, fhew_setup, bk):
         fhew.BootstrappingKey(ctx, bad, ex["ksk_a"], ex["ksk_b"], ex["brk"], ex["ak"], ex["ak_t"])
 
 
+def test_out_of_range_indices_and_exponents_are_rejected(pkg, ctx, orc, fhew_setup, bk):
+    """The reference panics on a key index out of bounds and on an even non-zero blind-rotation exponent
+    (bootstrapping.rs:217-222); the util-level device entry points return FHE_EINVAL before any table is indexed."""
+    from learn_fhe_b200 import fhew
+    P, K, ex = fhew_setup
+    acc = pkg.to_dev(orc.residues(9, 2 * 2 * P.n, P.big_q).reshape(2, 2, P.n))
+    out = torch.empty_like(acc)
+    for name, bad in (("fhe_fhew_external_product", P.n_s), ("fhe_fhew_external_product", 0x8001), ("fhe_fhew_automorphism", 11)):
+        d_idx = pkg.to_dev(np.array([0, bad], dtype=np.uint32))
+        with pytest.raises(pkg.FheError):
+            ctx.call(name, bk.h, 2, pkg.dptr(d_idx), pkg.dptr(acc), pkg.dptr(out))
+    _, _, lin = _inputs(K, P, 2, 6)
+    ct2n = K.prologue(lin)
+    f = pkg.to_dev(fhew.gate_poly(bk.param, [1, 1, 1, 0]))
+    o = torch.empty((2, 2, P.n), dtype=torch.int64, device="cuda")
+    for pos, val in ((3, 2 * P.n), (5, 6), (P.n_s, 2 * P.n + 1)):  # too large / even non-zero mask word / body too large
+        bad = ct2n.copy()
+        bad[1, pos] = val
+        d = pkg.to_dev(bad)
+        with pytest.raises(pkg.FheError):
+            ctx.call("fhe_fhew_blind_rotate_batch", bk.h, pkg.dptr(f), 2, pkg.dptr(d), pkg.dptr(o))
+    d = pkg.to_dev(ct2n)
+    ctx.call("fhe_fhew_blind_rotate_batch", bk.h, pkg.dptr(f), 2, pkg.dptr(d), pkg.dptr(o))  # the context stays usable
+    ctx.call("fhe_fhew_key_check_error", bk.h)
+    assert (pkg.to_host(o)[0] == K.blind_rotate(fhew.gate_poly(bk.param, [1, 1, 1, 0]), ct2n[0])).all()
+    # upload-time checks: key-switching key words must be < q_ks; n_s must leave room for the schedule scratch
+    ksk_bad = ex["ksk_a"].copy()
+    ksk_bad[0, 0] = P.q_ks
+    with pytest.raises(pkg.FheError):
+        fhew.BootstrappingKey(ctx, bk.param, ksk_bad, ex["ksk_b"], ex["brk"], ex["ak"], ex["ak_t"])
+
+
 def test_host_path_pipelining_matches_device_path(pkg, ctx, orc, fhew_setup):
     """fhe_fhew_bootstrap_batch_host splits large batches into chunks (copy streams overlapped with the kernels): every
     ciphertext must equal the device-resident path, chunk boundaries included (9001 is not a multiple of the chunk size)."""

@@ -212,3 +212,15 @@ def test_tfhe_parameter_errors(pkg, ctx, orc):
     bad = pkg.TfheParam(log_p=4, padding=1, n=P.n, ks_log_b=4, ks_d=5, log_big_n=6, k=1, bs_log_b=23, bs_d=3)  # 69 bits
     with pytest.raises(pkg.FheError):
         tfhe.BootstrappingKey(ctx, bad, ex["brk"], ex["ksk_a"], ex["ksk_b"])
+    # a bootstrapping-key index >= n is a slice index out of bounds in the reference: FHE_EINVAL, not a wild device read
+    good = pkg.TfheParam(log_p=P.log_p, padding=P.padding, n=P.n, ks_log_b=P.ks_log_b, ks_d=P.ks_d, log_big_n=6, k=1, bs_log_b=23, bs_d=1)
+    bk = tfhe.BootstrappingKey(ctx, good, ex["brk"], ex["ksk_a"], ex["ksk_b"])
+    glwe = orc.splitmix64(3, 2 * 2 * 64).reshape(2, 2, 64)
+    with pytest.raises(pkg.FheError):
+        tfhe.Tggsw.external_product(bk, np.array([0, P.n], dtype=np.uint32), glwe)
+    with pytest.raises(pkg.FheError):
+        tfhe.Tggsw.cmux(bk, np.array([P.n + 5, 0], dtype=np.uint32), glwe, glwe)
+    with pytest.raises(pkg.FheError):
+        bk.set_mode(2)  # no fused specialisation for N = 64
+    assert tfhe.Tggsw.external_product(bk, np.array([0, P.n - 1], dtype=np.uint32), glwe).shape == glwe.shape
+    bk.free()
