@@ -117,6 +117,10 @@ def lib():
         L.orc_tfhe_testing_param.restype = None
         L.orc_tfhe_keygen.argtypes = [C.POINTER(TfheParamC), C.c_uint64]
         L.orc_tfhe_keygen.restype = C.c_void_p
+        L.orc_tfhe_key_import.restype = C.c_void_p
+        L.orc_tfhe_key_import.argtypes = [C.c_void_p, u64p, u64p, u64p]
+        L.orc_ckks_key_import.restype = C.c_void_p
+        L.orc_ckks_key_import.argtypes = [C.c_uint, u64p, u64p, C.c_size_t, u64p, i64p, u64p, C.c_size_t]
         L.orc_tfhe_key_free.argtypes = [C.c_void_p]
         L.orc_tfhe_key_free.restype = None
         L.orc_tfhe_key_export.argtypes = [C.c_void_p] + [C.c_void_p] * 5
@@ -443,11 +447,17 @@ def tfhe_testing_param():
 
 
 class TfheKey:
-    def __init__(self, param, seed):
+    def __init__(self, param, seed, _handle=None):
         self.param = param
-        self.h = lib().orc_tfhe_keygen(C.byref(param), seed)
+        self.h = _handle if _handle is not None else lib().orc_tfhe_keygen(C.byref(param), seed)
         if not self.h:
             _ck(-1)
+
+    @classmethod
+    def from_arrays(cls, param, brk, ksk_a, ksk_b):
+        """Public evaluation keys only (no secrets: encrypt / decrypt are unavailable); layout as in export()."""
+        h = lib().orc_tfhe_key_import(C.byref(param), U(brk).reshape(-1), U(ksk_a).reshape(-1), U(ksk_b).reshape(-1))
+        return cls(param, 0, _handle=h)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -506,6 +516,21 @@ class TfheKey:
 
 # ------------------------------------------------------------------ CKKS
 class CkksKey:
+    @classmethod
+    def from_arrays(cls, log_n, qs, ps, rlk, auto=()):
+        """Public evaluation keys only: explicit moduli, rlk [2][2L][N] and automorphism keys [(t, ksk [2][2L][N]), ...]."""
+        self = cls.__new__(cls)
+        self.log_n, self.big_l, self.n = log_n, len(qs), 1 << log_n
+        self.qs, self.ps = [int(q) for q in qs], [int(p) for p in ps]
+        self.auto_ts = [int(t) for t, _ in auto]
+        ts = np.ascontiguousarray(self.auto_ts, dtype=np.int64)
+        ak = U(np.stack([U(k) for _, k in auto])).reshape(-1) if auto else np.zeros(1, dtype=np.uint64)
+        self.h = lib().orc_ckks_key_import(log_n, U(self.qs), U(self.ps), self.big_l, U(rlk).reshape(-1), ts if len(ts) else np.zeros(1, dtype=np.int64),
+                                           ak, len(auto))
+        if not self.h:
+            _ck(-1)
+        return self
+
     def __init__(self, log_n, log_qi, big_l, seed, auto_ts=()):
         self.log_n, self.big_l = log_n, big_l
         self.n = 1 << log_n

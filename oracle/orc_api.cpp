@@ -490,6 +490,34 @@ void* orc_tfhe_keygen(const orc_tfhe_param_c* c, u64 seed) {
         return nullptr;
     }
 }
+// public evaluation keys only, in the layout of orc_tfhe_key_export (known-answer replays: tests/test_cpu_refpin.py)
+void* orc_tfhe_key_import(const orc_tfhe_param_c* c, const u64* brk, const u64* ksk_a, const u64* ksk_b) {
+    try {
+        TfheKey* K = new TfheKey();
+        K->param = to_tparam(*c);
+        const TfheParam& P = K->param;
+        const size_t N = P.big_n, rows = (P.k + 1) * P.bs_d, polys = P.k + 1, kn = (size_t)P.k * N;
+        K->brk.resize(P.n);
+        for (size_t i = 0; i < P.n; ++i) {
+            K->brk[i].resize(rows);
+            for (size_t r = 0; r < rows; ++r) {
+                const u64* base = brk + ((i * rows + r) * polys) * N;
+                K->brk[i][r].a.resize(P.k);
+                for (unsigned j = 0; j < P.k; ++j) K->brk[i][r].a[j].assign(base + j * N, base + (j + 1) * N);
+                K->brk[i][r].b.assign(base + P.k * N, base + (P.k + 1) * N);
+            }
+        }
+        K->ksk.resize(kn * P.ks_d);
+        for (size_t i = 0; i < K->ksk.size(); ++i) {
+            K->ksk[i].a.assign(ksk_a + i * P.n, ksk_a + (i + 1) * P.n);
+            K->ksk[i].b = ksk_b[i];
+        }
+        return K;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 void orc_tfhe_key_free(void* h) { delete (TfheKey*)h; }
 // export: brk [n][(k+1)*d][(k+1) polys: a_0..a_{k-1}, b][N];  ksk_a [(kN)*d_ks][n], ksk_b [(kN)*d_ks]; z [n]; s [kN]
 int orc_tfhe_key_export(void* h, u64* brk, u64* ksk_a, u64* ksk_b, int64_t* z, int64_t* s) {
@@ -602,6 +630,31 @@ void* orc_ckks_keygen(unsigned log_n, unsigned log_qi, unsigned big_l, u64 seed,
         CkksParam P = ckks_param_new(log_n, log_qi, big_l);
         for (u64 q : P.qps()) twiddle(q);
         return new CkksKey(ckks_key_gen(P, seed, std::vector<i64>(auto_ts, auto_ts + n_ts)));
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+// public evaluation keys only: explicit moduli, rlk and n_auto automorphism keys [2 (b, a)][2L][N] each with exponents ts
+void* orc_ckks_key_import(unsigned log_n, const u64* qs, const u64* ps, size_t big_l, const u64* rlk, const int64_t* ts, const u64* autk,
+                          size_t n_auto) {
+    try {
+        CkksKey* K = new CkksKey();
+        K->param.log_n = log_n;
+        K->param.qs.assign(qs, qs + big_l);
+        K->param.ps.assign(ps, ps + big_l);
+        const Vec qps = K->param.qps();
+        for (u64 q : qps) twiddle(q);
+        const size_t n = K->param.n(), words = 2 * big_l * n;
+        auto wrap = [&](const u64* p) {
+            CkksCt c;
+            c.b = rns_wrap(qps.data(), 2 * big_l, p, n);
+            c.a = rns_wrap(qps.data(), 2 * big_l, p + words, n);
+            return c;
+        };
+        K->rlk = wrap(rlk);
+        for (size_t i = 0; i < n_auto; ++i) K->autk.emplace_back((i64)ts[i], wrap(autk + i * 2 * words));
+        return K;
     } catch (const std::exception& e) {
         g_err = e.what();
         return nullptr;
