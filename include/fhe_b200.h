@@ -170,6 +170,12 @@ fhe_status fhe_fhew_bootstrap_batch_host(fhe_ctx* ctx, const fhe_fhew_key* key, 
  * blind-rotation exponent, bootstrapping.rs:217-222; cannot happen after mod_switch_odd): this call synchronises the context's
  * stream and returns FHE_EINVAL if any bootstrap with this key met one since the flag was last reset (every launch resets it). */
 fhe_status fhe_fhew_key_check_error(fhe_ctx* ctx, const fhe_fhew_key* key);
+/* Rgsw::internal_product (scheme/fhew/src/rgsw.rs:130-150), the operation Bootstrapping::key_share_merge (bootstrapping.rs:295-320)
+ * folds the parties' brk shares with: `count` pairs of RGSW ciphertexts [count][2d rows][2 (a, b)][n] over Z_q (prime, NTT
+ * friendly, < 2^62), coefficient form in and out, decomposor (log_b, d); out[c] = internal_product(ct0[c], ct1[c]), every row
+ * bit-identical to Rgsw::external_product(ct0[c], row of ct1[c]).  d_out must not alias the inputs. */
+fhe_status fhe_rgsw_internal_product(fhe_ctx* ctx, uint64_t q, unsigned log_n, unsigned log_b, unsigned d, size_t count, const uint64_t* d_ct0,
+                                     const uint64_t* d_ct1, uint64_t* d_out);
 /* first three steps of bootstrap (mod_switch -> Lwe::key_switch -> mod_switch_odd; lwe.rs:90-99,151-160):
  * out [count][n_s+1] residues mod 2N */
 fhe_status fhe_fhew_prologue_batch(fhe_ctx* ctx, const fhe_fhew_key* key, size_t count, const uint64_t* d_ct_in, uint64_t* d_out);

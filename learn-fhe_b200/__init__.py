@@ -146,6 +146,7 @@ def lib():
     L.fhe_fhew_automorphism.argtypes = [vp, vp, sz, vp, vp, vp]
     L.fhe_fhew_blind_rotate_batch.argtypes = [vp, vp, vp, sz, vp, vp]
     L.fhe_fhew_key_check_error.argtypes = [vp, vp]
+    L.fhe_rgsw_internal_product.argtypes = [vp, u64, ui, ui, ui, sz, vp, vp, vp]
     # TFHE
     if hasattr(L, "fhe_tfhe_key_upload"):
         L.fhe_tfhe_key_upload.argtypes = [vp, C.POINTER(TfheParam), vp, vp, vp, C.POINTER(vp)]

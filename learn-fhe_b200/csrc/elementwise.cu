@@ -123,6 +123,31 @@ fhe_status pointwise_mul_dev(fhe_ctx* ctx, uint64_t q, size_t count, const uint6
     return launch_ew<OP_MUL>(ctx, q, count, a, b, 0, out);
 }
 
+// Rgsw::internal_product (scheme/fhew/src/rgsw.rs:130-150), evaluation-domain dot products: output row (c, r), component h' is
+//   sum over limbs (h, k) of e0[c][h d + k][h'] o dig[k][((c rows + r) 2 + h) n ..]      (all operands in evaluation form)
+// e0: ct0 rows transformed [count][rows][2][n]; dig: fhe_decompose_zq of the whole ct1 array, limb-major [d][count rows 2 n].
+__global__ void __launch_bounds__(256) rgsw_ip_mac_kernel(Mod64 m, uint32_t log_n, uint32_t d, unsigned long long count,
+                                                          const uint64_t* __restrict__ e0, const uint64_t* __restrict__ dig,
+                                                          uint64_t* __restrict__ out) {
+    const uint32_t n = 1u << log_n, rows = 2 * d;
+    const unsigned long long total = count * rows * n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long plane = count * rows * 2ull * n;  // words per digit plane
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const uint32_t i = (uint32_t)(idx & (n - 1));
+        const unsigned long long cr = idx >> log_n, c = cr / rows;
+        uint64_t sa = 0, sb = 0;
+        for (uint32_t h = 0; h < 2; ++h)
+            for (uint32_t k = 0; k < d; ++k) {
+                const uint64_t x = dig[k * plane + ((cr * 2 + h) << log_n) + i];
+                const uint64_t* row = e0 + (((c * rows + h * d + k) * 2) << log_n) + i;
+                sa = m.add(sa, m.mul(row[0], x));
+                sb = m.add(sb, m.mul(row[n], x));
+            }
+        out[((cr * 2) << log_n) + i] = sa;
+        out[((cr * 2 + 1) << log_n) + i] = sb;
+    }
+}
+
 }  // namespace fhe
 
 using namespace fhe;
@@ -236,6 +261,31 @@ fhe_status fhe_negacyclic_mul_host(fhe_ctx* ctx, uint64_t q, uint64_t* a, const 
     cudaFree(da);
     cudaFree(db);
     return st;
+}
+
+// Rgsw::internal_product (rgsw.rs:130-150) on `count` pairs of RGSW ciphertexts [count][2d rows][2 (a, b)][n] over Z_q, coefficient
+// form in and out: ct0's rows -> evaluation form, every row of ct1 decomposed (a digits then b digits, decompose.rs), limbs
+// transformed, dotted with ct0's a / b columns, transformed back.  out must not alias the inputs.
+fhe_status fhe_rgsw_internal_product(fhe_ctx* ctx, uint64_t q, unsigned log_n, unsigned log_b, unsigned d, size_t count, const uint64_t* d_ct0,
+                                     const uint64_t* d_ct1, uint64_t* d_out) {
+    if (!ctx) return FHE_EINVAL;
+    if (count == 0) return FHE_OK;
+    FHE_REQUIRE(ctx, d_ct0 && d_ct1 && d_out && d_out != d_ct0 && d_out != d_ct1, "null or aliased pointer");
+    FHE_REQUIRE(ctx, q >= 2 && q < (1ull << 62) && host_is_prime(q), "internal product needs an NTT-friendly prime modulus < 2^62");
+    FHE_REQUIRE(ctx, log_n >= 1 && log_n <= 16 && log_b >= 1 && d >= 1 && log_b < 63 && (unsigned long long)log_b * d <= 64, "bad parameters");
+    const size_t n = (size_t)1 << log_n, rows = 2 * (size_t)d, words = count * rows * 2 * n;
+    void* ws;
+    FHE_CHECK(ensure_scratch(ctx, (1 + (size_t)d) * words * 8, &ws));
+    uint64_t* e0 = (uint64_t*)ws;
+    uint64_t* dig = e0 + words;
+    FHE_CUDA(ctx, cudaMemcpyAsync(e0, d_ct0, words * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    FHE_CHECK(launch_ntt_u64(ctx, q, log_n, count * rows * 2, e0, true));
+    decompose_zq_kernel<<<ew_grid(ctx, words), 256, 0, ctx->stream>>>(q, make_decomp(q, log_b, d), words, d_ct1, dig);
+    FHE_CHECK(after_launch(ctx, "decompose_zq_kernel"));
+    FHE_CHECK(launch_ntt_u64(ctx, q, log_n, (size_t)d * count * rows * 2, dig, true));
+    rgsw_ip_mac_kernel<<<ew_grid(ctx, count * rows * n), 256, 0, ctx->stream>>>(make_mod<Mod64>(q), log_n, d, count, e0, dig, d_out);
+    FHE_CHECK(after_launch(ctx, "rgsw_ip_mac_kernel"));
+    return launch_ntt_u64(ctx, q, log_n, count * rows * 2, d_out, false);
 }
 
 }  // extern "C"

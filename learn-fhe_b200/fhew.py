@@ -158,6 +158,54 @@ class Bootstrapping:
         return out_dev
 
 
+class Rgsw:
+    @staticmethod
+    def internal_product(ctx, param, ct0, ct1):
+        """Rgsw::internal_product (rgsw.rs:130-150) on host batches of RGSW ciphertexts [count, 2d, 2 (a, b), N] (or one
+        ciphertext [2d, 2, N]) over Z_Q with the RGSW decomposor of `param`."""
+        import torch
+        from . import to_dev, to_host
+        ct0, ct1 = np.ascontiguousarray(ct0, dtype=np.uint64), np.ascontiguousarray(ct1, dtype=np.uint64)
+        single = ct0.ndim == 3
+        if single:
+            ct0, ct1 = ct0[None], ct1[None]
+        assert ct0.shape == ct1.shape and ct0.shape[1:] == (2 * param.rgsw_d, 2, param.n)
+        d0, d1 = to_dev(ct0, ctx.device), to_dev(ct1, ctx.device)
+        out = torch.empty_like(d0)
+        ctx.call("fhe_rgsw_internal_product", param.big_q, param.log_n, param.rgsw_log_b, param.rgsw_d, ct0.shape[0], dptr(d0), dptr(d1), dptr(out))
+        ctx.sync()
+        r = to_host(out)
+        return r[0] if single else r
+
+
+def key_share_merge(ctx, param, crs, shares):
+    """Bootstrapping::key_share_merge (bootstrapping.rs:295-320) on the device.  crs: dict(ksk [N ks_d, n_s] mod q_ks,
+    ak [w+1, rlwe_d, N] mod Q); every share: dict(ksk [N ks_d] mod q_ks, brk [n_s, 2 rgsw_d, 2, N], ak [w+1, rlwe_d, N]).
+    ksk / ak shares are summed (lwe.rs:228-238, rlwe.rs:294-326), the brk shares of each LWE index are folded with
+    Rgsw::internal_product, all n_s indices in one batched call per party.  Returns (ksk_a, ksk_b, brk, ak) in the layout of
+    BootstrappingKey / fhe_fhew_key_upload."""
+    import torch
+    from . import to_dev, to_host
+    from . import util
+    dev = lambda a: to_dev(np.ascontiguousarray(a, dtype=np.uint64), ctx.device)
+    ksk_b = dev(shares[0]["ksk"])
+    ak_b = dev(shares[0]["ak"])
+    brk = dev(shares[0]["brk"])
+    for sh in shares[1:]:
+        nxt = dev(sh["ksk"])
+        util.vec_add_dev(ctx, param.q_ks, ksk_b, nxt, ksk_b)
+        nxt_ak = dev(sh["ak"])
+        util.vec_add_dev(ctx, param.big_q, ak_b, nxt_ak, ak_b)
+        nxt_brk = dev(sh["brk"])
+        out = torch.empty_like(brk)
+        ctx.call("fhe_rgsw_internal_product", param.big_q, param.log_n, param.rgsw_log_b, param.rgsw_d, brk.shape[0], dptr(brk), dptr(nxt_brk), dptr(out))
+        ctx.sync()
+        brk = out
+    ctx.sync()
+    ak = np.stack([np.ascontiguousarray(crs["ak"], dtype=np.uint64), to_host(ak_b)], axis=2)  # [w+1][d][2 (a, b)][N]
+    return np.ascontiguousarray(crs["ksk"], dtype=np.uint64), to_host(ksk_b), to_host(brk), ak
+
+
 class Fhew:
     @staticmethod
     def linear(param, name, cts):

@@ -117,6 +117,7 @@ def lib():
         L.orc_tfhe_testing_param.restype = None
         L.orc_tfhe_keygen.argtypes = [C.POINTER(TfheParamC), C.c_uint64]
         L.orc_tfhe_keygen.restype = C.c_void_p
+        L.orc_rgsw_internal_product.argtypes = [C.c_uint64, C.c_uint, C.c_uint, C.c_uint, u64p, u64p, u64p]
         L.orc_tfhe_key_import.restype = C.c_void_p
         L.orc_tfhe_key_import.argtypes = [C.c_void_p, u64p, u64p, u64p]
         L.orc_ckks_key_import.restype = C.c_void_p
@@ -422,6 +423,14 @@ class FhewKey:
         out = np.zeros(self.param.n, dtype=np.uint64)
         _ck(lib().orc_rlwe_decrypt(self.h, U(acc).reshape(-1), out))
         return out
+
+
+def rgsw_internal_product(q, log_n, log_b, d, ct0, ct1):
+    """Rgsw::internal_product (rgsw.rs:130-150): RGSW ciphertexts [2d][2][n] over Z_q."""
+    ct0, ct1 = U(ct0), U(ct1)
+    out = np.zeros_like(ct0)
+    _ck(lib().orc_rgsw_internal_product(q, log_n, log_b, d, ct0.reshape(-1), ct1.reshape(-1), out.reshape(-1)))
+    return out
 
 
 def fhew_gate_poly(param, table):

@@ -415,6 +415,25 @@ int orc_fhew_external_product(void* h, size_t j, const u64* acc_in, u64* acc_out
         std::memcpy(acc_out + n, o.b.data(), n * 8);
     })
 }
+// Rgsw::internal_product (rgsw.rs:130-150): ct0, ct1, out are RGSW ciphertexts [2d rows][2 (a, b)][n] over Z_q
+int orc_rgsw_internal_product(u64 q, unsigned log_n, unsigned log_b, unsigned d, const u64* ct0, const u64* ct1, u64* out) {
+    ORC_TRY({
+        const size_t n = (size_t)1 << log_n, rows = 2 * (size_t)d;
+        auto wrap = [&](const u64* p) {
+            std::vector<RlweCt> v(rows);
+            for (size_t r = 0; r < rows; ++r) {
+                v[r].a.assign(p + (2 * r) * n, p + (2 * r + 1) * n);
+                v[r].b.assign(p + (2 * r + 1) * n, p + (2 * r + 2) * n);
+            }
+            return v;
+        };
+        const std::vector<RlweCt> o = rgsw_internal_product(q, n, DecomposorZq(q, log_b, d), wrap(ct0), wrap(ct1));
+        for (size_t r = 0; r < rows; ++r) {
+            std::memcpy(out + (2 * r) * n, o[r].a.data(), n * 8);
+            std::memcpy(out + (2 * r + 1) * n, o[r].b.data(), n * 8);
+        }
+    })
+}
 int orc_fhew_automorphism(void* h, size_t v, const u64* acc_in, u64* acc_out) {
     ORC_TRY({
         FhewKey& K = *(FhewKey*)h;

@@ -307,6 +307,37 @@ static inline RlweCt rgsw_external_product(const FhewParam& P, const std::vector
     o.b = dot_rows(P.big_q, n, rb, limbs);
     return o;
 }
+// rgsw.rs:130-150 internal_product: ct0's rows are moved to the evaluation domain once; every row of ct1 is decomposed, its limbs
+// transformed, dotted with ct0's a / b columns in the evaluation domain and transformed back (the reference's own dataflow)
+static inline std::vector<RlweCt> rgsw_internal_product(u64 q, size_t n, const DecomposorZq& dec, const std::vector<RlweCt>& ct0,
+                                                        const std::vector<RlweCt>& ct1) {
+    std::vector<Vec> e0a, e0b;
+    for (const RlweCt& r : ct0) {
+        e0a.push_back(r.a);
+        e0b.push_back(r.b);
+        nega_cyclic_ntt_in_place(q, e0a.back().data(), n);
+        nega_cyclic_ntt_in_place(q, e0b.back().data(), n);
+    }
+    std::vector<RlweCt> out;
+    for (const RlweCt& r : ct1) {
+        Vec limbs(2 * dec.d * n);
+        dec.decompose_vec(r.a.data(), n, limbs.data());
+        dec.decompose_vec(r.b.data(), n, limbs.data() + dec.d * n);
+        for (size_t k = 0; k < 2 * dec.d; ++k) nega_cyclic_ntt_in_place(q, limbs.data() + k * n, n);
+        RlweCt o;
+        o.a.assign(n, 0);
+        o.b.assign(n, 0);
+        for (size_t k = 0; k < 2 * dec.d; ++k)
+            for (size_t i = 0; i < n; ++i) {
+                o.a[i] = zq_add(q, o.a[i], zq_mul(q, e0a[k][i], limbs[k * n + i]));
+                o.b[i] = zq_add(q, o.b[i], zq_mul(q, e0b[k][i], limbs[k * n + i]));
+            }
+        nega_cyclic_intt_in_place(q, o.a.data(), n);
+        nega_cyclic_intt_in_place(q, o.b.data(), n);
+        out.push_back(o);
+    }
+    return out;
+}
 // rlwe.rs:177-186 key_switch
 static inline RlweCt rlwe_key_switch(const FhewParam& P, const std::vector<RlweCt>& ksk, const RlweCt& ct) {
     size_t n = P.n();

@@ -316,3 +316,43 @@ def test_reference_ring_sweep_45bit_primes_nine_digits(pkg, ctx, orc, log_n):
             lin = (cts[:4] + cts[4:]) % np.uint64(q)
             assert (fhew.Fhew.op(key, [1, 1, 1, 0], lin) == K.op([1, 1, 1, 0], lin, threads=2)).all(), (log_n, q)
         key.free()
+
+
+def test_multi_key_internal_product_and_key_share_merge(pkg, ctx, orc):
+    """SURVEY.md 8f rank 4: Rgsw::internal_product (rgsw.rs:130-150) bit-exact against the oracle - reduced ring and the
+    multi-key example's own size (N = 2048, 55-bit Q, decomposor (11, 5), examples/multi_key_uint8.rs:15-29) - and
+    Bootstrapping::key_share_merge (bootstrapping.rs:295-320) on the device: merged key == host merge, and the bootstrap under
+    it decrypts with the SUM of the parties' secrets."""
+    import multikey
+    from test_cpu_multikey import small_param
+    from learn_fhe_b200 import fhew
+    for log_n, bits, log_b, d in ((6, 45, 9, 5), (11, 55, 11, 5), (9, 28, 7, 4)):
+        q = orc.two_adic_primes(bits, log_n + 1, 1)[0]
+        n = 1 << log_n
+        param = pkg.FhewParam(log_n=log_n, big_q=q, p=4, rlwe_log_b=log_b, rlwe_d=d, rgsw_log_b=log_b, rgsw_d=d, n_s=4, q_ks=1 << 16, ks_log_b=4,
+                              ks_d=4, w=3)
+        ct0 = orc.residues(11 + log_n, 3 * 2 * d * 2 * n, q).reshape(3, 2 * d, 2, n)
+        ct1 = orc.residues(12 + log_n, 3 * 2 * d * 2 * n, q).reshape(3, 2 * d, 2, n)
+        got = fhew.Rgsw.internal_product(ctx, param, ct0, ct1)
+        for c in range(3 if log_n < 11 else 1):
+            assert (got[c] == orc.rgsw_internal_product(q, log_n, log_b, d, ct0[c], ct1[c])).all(), (log_n, c)
+    for parties in (2, 3):
+        P = small_param(orc)
+        M = multikey.MultiKey(orc, P, parties, 17 + parties)
+        param = pkg.FhewParam(log_n=P.log_n, big_q=P.big_q, p=P.p, rlwe_log_b=P.rlwe_log_b, rlwe_d=P.rlwe_d, rgsw_log_b=P.rgsw_log_b,
+                              rgsw_d=P.rgsw_d, n_s=P.n_s, q_ks=P.q_ks, ks_log_b=P.ks_log_b, ks_d=P.ks_d, w=P.w)
+        got = fhew.key_share_merge(ctx, param, M.crs, M.shares)
+        ref = M.merge_reference()
+        for g, r in zip(got, ref):
+            assert g.shape == r.shape and (g == r).all()
+        if parties > 2:
+            continue  # merge parity only: a third party's noise does not fit this reduced modulus (tests/test_cpu_multikey.py)
+        bk = fhew.BootstrappingKey(ctx, param, got[0], got[1], got[2], got[3], M.ak_t)
+        bits = np.array([0, 0, 1, 1, 0, 1, 0, 1])
+        cts = M.encrypt(bits)
+        lin = (cts[:4] + cts[4:]) % np.uint64(P.big_q)
+        out = fhew.Fhew.op(bk, [1, 1, 1, 0], lin)
+        assert (M.decrypt(out) == 1 - (bits[:4] & bits[4:])).all()
+        K = orc.FhewKey.from_arrays(P, *ref, M.ak_t)
+        assert (out == K.op([1, 1, 1, 0], lin)).all()
+        bk.free()
