@@ -154,6 +154,20 @@ typedef struct fhe_fhew_key fhe_fhew_key;
  * brk/ak rows are transformed once to evaluation form (u32) on the device. */
 fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* param, const uint64_t* ksk_a, const uint64_t* ksk_b,
                                const uint64_t* brk, const uint64_t* ak, const int64_t* ak_t, fhe_fhew_key** out);
+/* Key generation ON THE DEVICE: Bootstrapping::key_gen (bootstrapping.rs:122-146; rlwe.rs:109-156,
+ * rgsw.rs:84-105, lwe.rs:108-140) for the whole key, directly into the evaluation-form device buffers.  The reference takes
+ * its randomness from the caller's RngCore; here it is the counter-based stream of csrc/keygen_stream.cuh (splitmix64 of
+ * (seed, domain, index); uniform masks, discrete Gaussian sigma = 3.2 cut at 6 sigma).  z_out [N] / s_out [n_s] receive the
+ * RLWE / LWE secrets (int64, host).  The four *_out HOST pointers (reference layout of fhe_fhew_key_upload) are optional: a
+ * caller that only wants the key passes NULL and nothing but the two secrets ever leaves the device. */
+fhe_status fhe_fhew_keygen(fhe_ctx* ctx, const fhe_fhew_param* param, uint64_t seed, int64_t* z_out, int64_t* s_out, uint64_t* ksk_a_out,
+                           uint64_t* ksk_b_out, uint64_t* brk_out, uint64_t* ak_out, fhe_fhew_key** out);
+/* Serialised key (the reference has no key format): header {magic "FHEB200K", version 1} | fhe_fhew_param | ak_t[w+1] | the
+ * three device images (evaluation-form brk / ak rows, packed ksk).  Loading is three host-to-device copies, no transform.
+ * A blob of another version, of inconsistent section sizes or of the wrong length is rejected with FHE_EINVAL. */
+size_t fhe_fhew_key_serialized_size(const fhe_fhew_key* key);
+fhe_status fhe_fhew_key_serialize(fhe_ctx* ctx, const fhe_fhew_key* key, void* buf, size_t cap);
+fhe_status fhe_fhew_key_deserialize(fhe_ctx* ctx, const void* buf, size_t len, fhe_fhew_key** out);
 void fhe_fhew_key_free(fhe_ctx* ctx, fhe_fhew_key* key);
 /* device bytes held by the key (brk + ak + ksk) and its one-time NCCL broadcast from `root` (every rank must hold a
  * key object of the same parameters, e.g. uploaded from zeros; see fhe_keys_broadcast) */

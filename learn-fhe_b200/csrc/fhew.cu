@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cstring>
+
 #include "ctx.cuh"
 #include "fhew_core.cuh"
 #include "fhew_fast.cuh"
@@ -264,6 +266,8 @@ static fhe_status persistent_grid(fhe_ctx* ctx, K kern, int threads, size_t smem
 }
 
 template <typename W>
+static fhe_status rows_to_eval_t(fhe_ctx* ctx, const fhe_fhew_key* key, W* d_tmp, size_t rows, void** d_out, size_t* bytes);
+template <typename W>
 static fhe_status upload_rows_eval_t(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* rows_ab, size_t rows, void** d_out, size_t* bytes) {
     const uint32_t n = 1u << key->P.log_n;
     const size_t words = rows * 2 * n;
@@ -278,7 +282,18 @@ static fhe_status upload_rows_eval_t(fhe_ctx* ctx, const fhe_fhew_key* key, cons
     cudaError_t e = cudaMemcpyAsync(d_tmp, h.data(), words * sizeof(W), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     fhe_status st = e == cudaSuccess ? FHE_OK : fail(ctx, FHE_ECUDA, "key upload: %s", cudaGetErrorString(e));
-    if (st == FHE_OK) {
+    if (st == FHE_OK) st = rows_to_eval_t<W>(ctx, key, d_tmp, rows, d_out, bytes);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_tmp);
+    return st;
+}
+// device-resident coefficient-form rows [rows][2 (a, b)][N] (overwritten) -> evaluation-form KeyPair rows in a new buffer
+template <typename W>
+static fhe_status rows_to_eval_t(fhe_ctx* ctx, const fhe_fhew_key* key, W* d_tmp, size_t rows, void** d_out, size_t* bytes) {
+    const uint32_t n = 1u << key->P.log_n;
+    const uint64_t q = key->param.big_q;
+    fhe_status st = FHE_OK;
+    {
         if (sizeof(W) == 4)
             st = launch_ntt_u32(ctx, (uint32_t)q, (unsigned)key->P.log_n, rows * 2, (uint32_t*)d_tmp, true);
         else
@@ -294,8 +309,6 @@ static fhe_status upload_rows_eval_t(fhe_ctx* ctx, const fhe_fhew_key* key, cons
         fhew_pack_rows_kernel<W><<<grid, 256, 0, ctx->stream>>>(d_tmp, (KeyPair<W>*)*d_out, n, rows);
         st = after_launch(ctx, "fhew_pack_rows_kernel");
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_tmp);
     return st;
 }
 static fhe_status upload_rows_eval(fhe_ctx* ctx, const fhe_fhew_key* key, const uint64_t* rows_ab, size_t rows, void** d_out, size_t* bytes) {
@@ -405,11 +418,16 @@ using namespace fhe;
 
 extern "C" {
 
-fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uint64_t* ksk_a, const uint64_t* ksk_b, const uint64_t* brk,
-                               const uint64_t* ak, const int64_t* ak_t, fhe_fhew_key** out) {
+}  // extern "C"
+
+#include "fhew_key.cuh"
+fhe_status fhew_key_build(fhe_ctx* ctx, const fhe_fhew_param* pp, const int64_t* ak_t, const FhewKeySource& src, fhe_fhew_key** out) {
+    const uint64_t *ksk_a = src.host_ksk_a, *ksk_b = src.host_ksk_b, *brk = src.host_brk, *ak = src.host_ak;
     if (!ctx || !pp || !out) return FHE_EINVAL;
     *out = nullptr;
-    FHE_REQUIRE(ctx, ksk_a && ksk_b && brk && ak && ak_t, "null key pointer");
+    FHE_REQUIRE(ctx, ak_t && ((ksk_a && ksk_b && brk && ak) || (src.img_brk && src.img_ak && src.img_ksk) ||
+                              (src.dev_brk_rows && src.dev_ak_rows && src.dev_ksk)),
+                "null key pointer");
     FHE_REQUIRE(ctx, pp->log_n >= 2 && pp->log_n <= 11, "FHEW path supports 4 <= N <= 2048 (got log_n = %u)", pp->log_n);
     FHE_REQUIRE(ctx, pp->big_q < (1ull << 62), "FHEW path needs Q < 2^62");
     const bool wide = pp->big_q >= (1ull << 30);  // 64-bit residues (generic kernels only)
@@ -428,8 +446,10 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     // the LMKCDEY schedule scratch (u16 cnt[N] + sorted[n_s]) aliases the digit region of kmax * N residue words
     FHE_REQUIRE(ctx, 2 * ((size_t)n + pp->n_s) <= (size_t)std::max(2 * pp->rgsw_d, pp->rlwe_d) * n * (wide ? 8 : 4),
                 "n_s = %u too large for N = %u with these decomposors (schedule scratch of 2 (N + n_s) bytes must fit the digit region)", pp->n_s, n);
-    for (size_t i = 0; i < (size_t)n * pp->ks_d * pp->n_s; ++i) FHE_REQUIRE(ctx, ksk_a[i] < pp->q_ks, "ksk_a word out of range (>= q_ks)");
-    for (size_t i = 0; i < (size_t)n * pp->ks_d; ++i) FHE_REQUIRE(ctx, ksk_b[i] < pp->q_ks, "ksk_b word out of range (>= q_ks)");
+    if (ksk_a) {
+        for (size_t i = 0; i < (size_t)n * pp->ks_d * pp->n_s; ++i) FHE_REQUIRE(ctx, ksk_a[i] < pp->q_ks, "ksk_a word out of range (>= q_ks)");
+        for (size_t i = 0; i < (size_t)n * pp->ks_d; ++i) FHE_REQUIRE(ctx, ksk_b[i] < pp->q_ks, "ksk_b word out of range (>= q_ks)");
+    }
     const NttTable* t;
     FHE_CHECK(get_ntt_table(ctx, pp->big_q, wide ? 64 : 32, n, &t));
     fhe_fhew_key* key = new fhe_fhew_key();
@@ -471,8 +491,27 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
         for (unsigned v = 0; v <= pp->w; ++v) W.ak_t[v] = P.ak_t[v];
     }
     key->kmax = std::max(2 * pp->rgsw_d, pp->rlwe_d);
-    fhe_status st = upload_rows_eval(ctx, key, brk, (size_t)pp->n_s * 2 * pp->rgsw_d, &key->d_brk, &key->brk_bytes);
-    if (st == FHE_OK) st = upload_rows_eval(ctx, key, ak, (size_t)(pp->w + 1) * pp->rlwe_d, &key->d_ak, &key->ak_bytes);
+    const size_t n_brk_rows = (size_t)pp->n_s * 2 * pp->rgsw_d, n_ak_rows = (size_t)(pp->w + 1) * pp->rlwe_d;
+    fhe_status st = FHE_OK;
+    if (brk) {
+        st = upload_rows_eval(ctx, key, brk, n_brk_rows, &key->d_brk, &key->brk_bytes);
+        if (st == FHE_OK) st = upload_rows_eval(ctx, key, ak, n_ak_rows, &key->d_ak, &key->ak_bytes);
+    } else if (src.img_brk) {
+        const size_t pair = wide ? sizeof(KeyPair<uint64_t>) : sizeof(KeyPair<uint32_t>);
+        key->brk_bytes = n_brk_rows * n * pair;
+        key->ak_bytes = n_ak_rows * n * pair;
+        if (cudaMalloc(&key->d_brk, key->brk_bytes) != cudaSuccess || cudaMalloc(&key->d_ak, key->ak_bytes) != cudaSuccess ||
+            cudaMemcpy(key->d_brk, src.img_brk, key->brk_bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(key->d_ak, src.img_ak, key->ak_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            st = fail(ctx, FHE_ECUDA, "key image upload failed");
+    } else {
+        st = wide ? rows_to_eval_t<uint64_t>(ctx, key, (uint64_t*)src.dev_brk_rows, n_brk_rows, &key->d_brk, &key->brk_bytes)
+                  : rows_to_eval_t<uint32_t>(ctx, key, (uint32_t*)src.dev_brk_rows, n_brk_rows, &key->d_brk, &key->brk_bytes);
+        if (st == FHE_OK)
+            st = wide ? rows_to_eval_t<uint64_t>(ctx, key, (uint64_t*)src.dev_ak_rows, n_ak_rows, &key->d_ak, &key->ak_bytes)
+                      : rows_to_eval_t<uint32_t>(ctx, key, (uint32_t*)src.dev_ak_rows, n_ak_rows, &key->d_ak, &key->ak_bytes);
+        if (st == FHE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, FHE_ECUDA, "key transform failed");
+    }
     if (st == FHE_OK) {
         std::vector<uint16_t> dlog(2 * n);
         build_dlog_table(n, dlog.data());
@@ -490,15 +529,22 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
         K.ks_dec = make_decomp(pp->q_ks, pp->ks_log_b, pp->ks_d);
         K.switch_in = K.switch_out = 1;
         const size_t len = (size_t)n * pp->ks_d, ld = pp->n_s + 1;
-        std::vector<uint32_t> h(len * ld);
-        for (size_t idx = 0; idx < len && st == FHE_OK; ++idx) {
-            for (size_t j = 0; j < pp->n_s; ++j) h[idx * ld + j] = (uint32_t)ksk_a[idx * pp->n_s + j];
-            h[idx * ld + pp->n_s] = (uint32_t)ksk_b[idx];
+        key->ksk_bytes = len * ld * 4;
+        if (src.dev_ksk) {
+            key->d_ksk = src.dev_ksk;  // adopted
+        } else {
+            std::vector<uint32_t> h;
+            if (ksk_a) {
+                h.resize(len * ld);
+                for (size_t idx = 0; idx < len; ++idx) {
+                    for (size_t j = 0; j < pp->n_s; ++j) h[idx * ld + j] = (uint32_t)ksk_a[idx * pp->n_s + j];
+                    h[idx * ld + pp->n_s] = (uint32_t)ksk_b[idx];
+                }
+            }
+            if (cudaMalloc(&key->d_ksk, key->ksk_bytes) != cudaSuccess ||
+                cudaMemcpy(key->d_ksk, ksk_a ? (const void*)h.data() : src.img_ksk, key->ksk_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+                st = fail(ctx, FHE_ECUDA, "ksk upload failed");
         }
-        key->ksk_bytes = h.size() * 4;
-        if (cudaMalloc(&key->d_ksk, key->ksk_bytes) != cudaSuccess ||
-            cudaMemcpy(key->d_ksk, h.data(), key->ksk_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
-            st = fail(ctx, FHE_ECUDA, "ksk upload failed");
         K.ksk = (const uint32_t*)key->d_ksk;
     }
     if (st != FHE_OK) {
@@ -560,6 +606,95 @@ fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uin
     }
     *out = key;
     return FHE_OK;
+}
+
+extern "C" {
+
+fhe_status fhe_fhew_key_upload(fhe_ctx* ctx, const fhe_fhew_param* pp, const uint64_t* ksk_a, const uint64_t* ksk_b, const uint64_t* brk,
+                               const uint64_t* ak, const int64_t* ak_t, fhe_fhew_key** out) {
+    if (!ctx || !pp || !out) return FHE_EINVAL;
+    *out = nullptr;
+    FHE_REQUIRE(ctx, ksk_a && ksk_b && brk && ak && ak_t, "null key pointer");
+    FhewKeySource src;
+    src.host_ksk_a = ksk_a;
+    src.host_ksk_b = ksk_b;
+    src.host_brk = brk;
+    src.host_ak = ak;
+    return fhew_key_build(ctx, pp, ak_t, src, out);
+}
+
+// ---- serialised key: header | fhe_fhew_param | ak_t[w+1] | brk image | ak image | ksk image -------------------
+// The images are the device buffers themselves (evaluation-form rows, packed ksk), so loading a key is three host-to-device
+// copies and no transform.  Versioned; a blob written for another parameter struct size or version is rejected.
+struct FhewBlobHeader {
+    char magic[8];
+    uint32_t version, kind;
+    uint64_t param_bytes, n_ak_t, brk_bytes, ak_bytes, ksk_bytes;
+};
+static const char FHEW_BLOB_MAGIC[8] = {'F', 'H', 'E', 'B', '2', '0', '0', 'K'};
+size_t fhe_fhew_key_serialized_size(const fhe_fhew_key* key) {
+    if (!key) return 0;
+    return sizeof(FhewBlobHeader) + sizeof(fhe_fhew_param) + (key->param.w + 1) * sizeof(int64_t) + key->brk_bytes + key->ak_bytes + key->ksk_bytes;
+}
+fhe_status fhe_fhew_key_serialize(fhe_ctx* ctx, const fhe_fhew_key* key, void* buf, size_t cap) {
+    if (!ctx || !key || !buf) return FHE_EINVAL;
+    FHE_REQUIRE(ctx, cap >= fhe_fhew_key_serialized_size(key), "buffer too small for the serialised key");
+    FhewBlobHeader h;
+    memcpy(h.magic, FHEW_BLOB_MAGIC, 8);
+    h.version = 1;
+    h.kind = 1;
+    h.param_bytes = sizeof(fhe_fhew_param);
+    h.n_ak_t = key->param.w + 1;
+    h.brk_bytes = key->brk_bytes;
+    h.ak_bytes = key->ak_bytes;
+    h.ksk_bytes = key->ksk_bytes;
+    unsigned char* p = (unsigned char*)buf;
+    memcpy(p, &h, sizeof h);
+    p += sizeof h;
+    memcpy(p, &key->param, sizeof(fhe_fhew_param));
+    p += sizeof(fhe_fhew_param);
+    const uint32_t two_n = 2u << key->P.log_n;
+    for (unsigned v = 0; v <= key->param.w; ++v) {  // exponents are stored reduced mod 2N
+        const int64_t t = (int64_t)key->P.ak_t[v];
+        memcpy(p + v * sizeof(int64_t), &t, sizeof t);
+        (void)two_n;
+    }
+    p += h.n_ak_t * sizeof(int64_t);
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FHE_CUDA(ctx, cudaMemcpy(p, key->d_brk, key->brk_bytes, cudaMemcpyDeviceToHost));
+    p += key->brk_bytes;
+    FHE_CUDA(ctx, cudaMemcpy(p, key->d_ak, key->ak_bytes, cudaMemcpyDeviceToHost));
+    p += key->ak_bytes;
+    FHE_CUDA(ctx, cudaMemcpy(p, key->d_ksk, key->ksk_bytes, cudaMemcpyDeviceToHost));
+    return FHE_OK;
+}
+fhe_status fhe_fhew_key_deserialize(fhe_ctx* ctx, const void* buf, size_t len, fhe_fhew_key** out) {
+    if (!ctx || !buf || !out) return FHE_EINVAL;
+    *out = nullptr;
+    FhewBlobHeader h;
+    FHE_REQUIRE(ctx, len >= sizeof h, "serialised key truncated");
+    memcpy(&h, buf, sizeof h);
+    FHE_REQUIRE(ctx, memcmp(h.magic, FHEW_BLOB_MAGIC, 8) == 0 && h.kind == 1, "not a serialised FHEW key");
+    FHE_REQUIRE(ctx, h.version == 1 && h.param_bytes == sizeof(fhe_fhew_param), "serialised key of another format version");
+    const unsigned char* p = (const unsigned char*)buf + sizeof h;
+    fhe_fhew_param pp;
+    FHE_REQUIRE(ctx, len >= sizeof h + sizeof pp, "serialised key truncated");
+    memcpy(&pp, p, sizeof pp);
+    p += sizeof pp;
+    FHE_REQUIRE(ctx, h.n_ak_t == (uint64_t)pp.w + 1 && pp.w < 40 && pp.log_n <= 11, "serialised key header inconsistent");
+    const size_t n = (size_t)1 << pp.log_n, pair = pp.big_q >= (1ull << 30) ? 16 : 8;
+    FHE_REQUIRE(ctx, h.brk_bytes == (size_t)pp.n_s * 2 * pp.rgsw_d * n * pair && h.ak_bytes == (size_t)(pp.w + 1) * pp.rlwe_d * n * pair &&
+                         h.ksk_bytes == n * pp.ks_d * ((size_t)pp.n_s + 1) * 4,
+                "serialised key sections do not match its parameters");
+    FHE_REQUIRE(ctx, len == sizeof h + sizeof pp + h.n_ak_t * 8 + h.brk_bytes + h.ak_bytes + h.ksk_bytes, "serialised key length mismatch");
+    std::vector<int64_t> ak_t(h.n_ak_t);
+    memcpy(ak_t.data(), p, h.n_ak_t * 8);
+    p += h.n_ak_t * 8;
+    FhewKeySource src;
+    src.img_brk = p;
+    src.img_ak = p + h.brk_bytes;
+    src.img_ksk = p + h.brk_bytes + h.ak_bytes;
+    return fhew_key_build(ctx, &pp, ak_t.data(), src, out);
 }
 
 void fhe_fhew_key_free(fhe_ctx* ctx, fhe_fhew_key* key) {

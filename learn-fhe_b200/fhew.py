@@ -42,6 +42,45 @@ class BootstrappingKey:
         ctx.call("fhe_fhew_key_upload", C.byref(param), hptr(ksk_a), hptr(ksk_b), hptr(brk), hptr(ak), hptr(ak_t), C.byref(h))
         self.h = h
 
+    @classmethod
+    def _adopt(cls, ctx, param, h):
+        self = cls.__new__(cls)
+        self.ctx, self.param, self.h = ctx, param, h
+        return self
+
+    @classmethod
+    def key_gen(cls, ctx, param, seed, export=False):
+        """Bootstrapping::key_gen (bootstrapping.rs:122-146) on the device from the counter-based stream of `seed`.  Returns
+        (key, z, s) - the RLWE and LWE secrets as int64 arrays - and, with export=True, also the coefficient-form key in the
+        reference layout (ksk_a, ksk_b, brk, ak) for parity checks."""
+        z, s = np.zeros(param.n, dtype=np.int64), np.zeros(param.n_s, dtype=np.int64)
+        h = C.c_void_p()
+        ex = None
+        if export:
+            ex = dict(ksk_a=np.zeros((param.n * param.ks_d, param.n_s), dtype=np.uint64), ksk_b=np.zeros(param.n * param.ks_d, dtype=np.uint64),
+                      brk=np.zeros((param.n_s, 2 * param.rgsw_d, 2, param.n), dtype=np.uint64),
+                      ak=np.zeros((param.w + 1, param.rlwe_d, 2, param.n), dtype=np.uint64))
+        P = lambda k: hptr(ex[k]) if ex else None
+        ctx.call("fhe_fhew_keygen", C.byref(param), seed, hptr(z), hptr(s), P("ksk_a"), P("ksk_b"), P("brk"), P("ak"), C.byref(h))
+        key = cls._adopt(ctx, param, h)
+        return (key, z, s, ex) if export else (key, z, s)
+
+    def serialize(self):
+        """The key as bytes: header, parameters and the device images (fhe_fhew_key_serialize)."""
+        size = int(self.ctx.L.fhe_fhew_key_serialized_size(self.h))
+        buf = np.zeros(size, dtype=np.uint8)
+        self.ctx.call("fhe_fhew_key_serialize", self.h, hptr(buf), size)
+        return buf
+
+    @classmethod
+    def deserialize(cls, ctx, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        h = C.c_void_p()
+        ctx.call("fhe_fhew_key_deserialize", hptr(blob), blob.size, C.byref(h))
+        # the parameters travel in the blob: fhe_fhew_param follows the 56-byte header
+        param = FhewParam.from_buffer_copy(blob[56:56 + C.sizeof(FhewParam)].tobytes())
+        return cls._adopt(ctx, param, h)
+
     def free(self):
         if getattr(self, "h", None):
             self.ctx.L.fhe_fhew_key_free(self.ctx.h, self.h)

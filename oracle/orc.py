@@ -97,6 +97,7 @@ def lib():
         L.orc_fhew_key_free.restype = None
         L.orc_fhew_key_import.argtypes = [C.POINTER(FhewParamC), u64p, u64p, u64p, u64p, i64p]
         L.orc_fhew_key_import.restype = C.c_void_p
+        L.orc_fhew_keygen_ctr.restype = C.c_void_p
         L.orc_fhew_key_export.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         L.orc_fhew_encrypt.argtypes = [C.c_void_p, i32p, C.c_size_t, C.c_uint64, u64p]
         L.orc_fhew_decrypt.argtypes = [C.c_void_p, u64p, C.c_size_t, i32p]
@@ -336,6 +337,12 @@ class FhewKey:
         self.h = _handle if _handle is not None else lib().orc_fhew_keygen(C.byref(param), seed)
         if not self.h:
             _ck(-1)
+
+    @classmethod
+    def ctr(cls, param, seed):
+        """Key generation fed by the counter-based stream of the device keygen (oracle/orc_keygen.hpp): the checker of
+        fhe_fhew_keygen."""
+        return cls(param, seed, _handle=lib().orc_fhew_keygen_ctr(C.byref(param), seed))
 
     @classmethod
     def from_arrays(cls, param, ksk_a, ksk_b, brk, ak, ak_t):

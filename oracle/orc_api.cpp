@@ -6,6 +6,7 @@
 
 #include "orc_ckks.hpp"
 #include "orc_fhew.hpp"
+#include "orc_keygen.hpp"
 #include "orc_rns.hpp"
 #include "orc_tfhe.hpp"
 #include "orc_util.hpp"
@@ -239,6 +240,15 @@ void orc_fhew_testing_param(orc_fhew_param_c* o) {
 void* orc_fhew_keygen(const orc_fhew_param_c* c, u64 seed) {
     try {
         return new FhewKey(fhew_key_gen(to_param(*c), seed));
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+// the same key generation fed by the counter-based stream of the device keygen (oracle/orc_keygen.hpp)
+void* orc_fhew_keygen_ctr(const orc_fhew_param_c* c, u64 seed) {
+    try {
+        return new FhewKey(fhew_key_gen_ctr(to_param(*c), seed));
     } catch (const std::exception& e) {
         g_err = e.what();
         return nullptr;

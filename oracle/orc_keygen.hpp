@@ -1,0 +1,89 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_util.hpp header).
+// Key generation of scheme/fhew/src/bootstrapping.rs:122-146 (with rlwe.rs:109-132, rgsw.rs:84-105, lwe.rs:108-119) exactly as
+// fhew_key_gen (orc_fhew.hpp) states it, but drawing every random word from the COUNTER-BASED stream the device key generation
+// uses (learn-fhe_b200/csrc/keygen_stream.cuh) instead of a sequential generator: the reference takes its randomness from the
+// caller's RngCore, so which generator feeds the formulas is not part of the reference's semantics.  This is the checker of
+// fhe_fhew_keygen: same seed -> the same key, word for word.
+#pragma once
+#include "../learn-fhe_b200/csrc/keygen_stream.cuh"
+#include "orc_fhew.hpp"
+
+namespace orc {
+
+static inline FhewKey fhew_key_gen_ctr(const FhewParam& P, u64 seed) {
+    using namespace fhe;
+    FhewKey K;
+    K.param = P;
+    const size_t n = P.n();
+    const u64 Q = P.big_q;
+    K.z.resize(n);
+    for (size_t i = 0; i < n; ++i) K.z[i] = ks_gauss(seed, KS_FHEW_Z, i);          // rlwe.rs:94-96
+    K.s.resize(P.n_s);
+    for (size_t j = 0; j < P.n_s; ++j) K.s[j] = ks_gauss(seed, KS_FHEW_S, j);      // lwe.rs:103-106
+    // ksk (lwe.rs:108-119, 130-140): row idx = digit * N + coefficient, b = <a, s> + pt + e, pt = base_k * (-z_i)
+    DecomposorZq ksd = P.ks_dec();
+    for (unsigned k = 0; k < P.ks_d; ++k)
+        for (size_t i = 0; i < n; ++i) {
+            const u64 idx = (u64)k * n + i;
+            LweCt ct;
+            ct.a.resize(P.n_s);
+            u64 dot = 0;
+            for (size_t j = 0; j < P.n_s; ++j) {
+                ct.a[j] = ks_uniform(seed, KS_FHEW_KSK_A, idx * P.n_s + j, P.q_ks);
+                dot = zq_add(P.q_ks, dot, zq_mul(P.q_ks, ct.a[j], zq_from_i64(P.q_ks, K.s[j])));
+            }
+            const u64 pt = zq_mul(P.q_ks, ksd.base(k), zq_from_i64(P.q_ks, -K.z[i]));
+            ct.b = zq_add(P.q_ks, zq_add(P.q_ks, dot, pt), zq_from_i64(P.q_ks, ks_gauss(seed, KS_FHEW_KSK_E, idx)));
+            K.ksk.push_back(ct);
+        }
+    // RLWE encryption of `pt` in row R of domain (da, de): a uniform, b = a * z + e + pt   (rlwe.rs:146-156)
+    auto rlwe_row = [&](uint32_t da, uint32_t de, u64 R, const Vec& pt) {
+        RlweCt ct;
+        ct.a.resize(n);
+        for (size_t c = 0; c < n; ++c) ct.a[c] = ks_uniform(seed, da, R * n + c, Q);
+        Vec as = rq_mul_i64(Q, ct.a, K.z);
+        ct.b.resize(n);
+        for (size_t c = 0; c < n; ++c) ct.b[c] = zq_add(Q, zq_add(Q, as[c], zq_from_i64(Q, ks_gauss(seed, de, R * n + c))), pt[c]);
+        return ct;
+    };
+    DecomposorZq gd = P.rgsw_dec();
+    const Vec zero(n, 0);
+    for (size_t j = 0; j < P.n_s; ++j) {  // brk[j] = RGSW_z(X^{s_j})   (rgsw.rs:84-105)
+        Vec m(n, 0);
+        m[0] = 1 % Q;
+        monomial_mul_zq(Q, m.data(), n, K.s[j]);
+        std::vector<RlweCt> rows;
+        for (unsigned r = 0; r < 2 * P.rgsw_d; ++r) rows.push_back(rlwe_row(KS_FHEW_BRK_A, KS_FHEW_BRK_E, (u64)j * 2 * P.rgsw_d + r, zero));
+        for (unsigned k = 0; k < P.rgsw_d; ++k)
+            for (size_t i = 0; i < n; ++i) {
+                const u64 v = zq_mul(Q, m[i], gd.base(k));
+                rows[k].a[i] = zq_add(Q, rows[k].a[i], v);
+                rows[P.rgsw_d + k].b[i] = zq_add(Q, rows[P.rgsw_d + k].b[i], v);
+            }
+        K.brk.push_back(std::move(rows));
+    }
+    DecomposorZq rd = P.rlwe_dec();
+    K.ak_t = P.ak_t();
+    for (size_t v = 0; v < K.ak_t.size(); ++v) {  // ak[v] = ksk_gen(z, z(X^t))   (rlwe.rs:109-132)
+        const i64 t = K.ak_t[v], m2 = 2 * (i64)n;
+        const size_t tt = (size_t)(((t % m2) + m2) % m2);
+        std::vector<i64> za(n);
+        for (size_t i = 0; i < n; ++i) {
+            const size_t it = (i * tt) % (2 * n);
+            if (it < n)
+                za[it] = K.z[i];
+            else
+                za[it - n] = -K.z[i];
+        }
+        std::vector<RlweCt> rows;
+        for (unsigned k = 0; k < P.rlwe_d; ++k) {
+            Vec pt(n);
+            for (size_t i = 0; i < n; ++i) pt[i] = zq_mul(Q, rd.base(k), zq_from_i64(Q, -za[i]));
+            rows.push_back(rlwe_row(KS_FHEW_AK_A, KS_FHEW_AK_E, (u64)v * P.rlwe_d + k, pt));
+        }
+        K.ak.push_back(std::move(rows));
+    }
+    return K;
+}
+
+}  // namespace orc

@@ -1,0 +1,64 @@
+"""key generation on the device and the serialised key format.
+fhe_fhew_keygen evaluates Bootstrapping::key_gen (scheme/fhew/src/bootstrapping.rs:122-146) on the GPU from the counter-based
+stream of csrc/keygen_stream.cuh; oracle/orc_keygen.hpp evaluates the same formulas on the same stream on the CPU.  The two keys
+must be equal word for word, and gates evaluated under the device key must decrypt correctly with the returned secrets."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _param(pkg, orc, log_n, bits, log_b, d, n_s, q_ks_bits, ks, w):
+    q = orc.two_adic_primes(bits, log_n + 1, 1)[0]
+    kw = dict(log_n=log_n, big_q=q, p=4, rlwe_log_b=log_b, rlwe_d=d, rgsw_log_b=log_b, rgsw_d=d, n_s=n_s, q_ks=1 << q_ks_bits, ks_log_b=ks[0],
+              ks_d=ks[1], w=w)
+    P = orc.fhew_testing_param()
+    for k, v in kw.items():
+        setattr(P, k, v)
+    return pkg.FhewParam(**kw), P
+
+
+@pytest.mark.parametrize("shape", [(9, 28, 7, 4, 100, 16, (4, 4), 10),   # FHEW-T (fhew/boolean.rs:225-239): fast 32-bit kernels
+                                   (6, 28, 7, 4, 12, 16, (4, 4), 3),     # reduced ring: generic 32-bit kernels
+                                   (7, 45, 9, 5, 10, 20, (4, 5), 4)])    # 64-bit residues (the multi-key example's word size)
+def test_device_keygen_equals_host_keygen_on_the_same_stream(pkg, ctx, orc, shape):
+    from learn_fhe_b200 import fhew
+    param, P = _param(pkg, orc, *shape)
+    seed = 0x5EED0700 + shape[0]
+    bk, z, s, ex = fhew.BootstrappingKey.key_gen(ctx, param, seed, export=True)
+    K = orc.FhewKey.ctr(P, seed)
+    ref = K.export()
+    assert (z == ref["z"]).all() and (s == ref["s"]).all()
+    for k in ("ksk_a", "ksk_b", "brk", "ak"):
+        assert (ex[k] == ref[k]).all(), k
+    # the key object built on the device evaluates gates exactly like the oracle under the same key, and they decrypt
+    bits = np.random.default_rng(shape[0]).integers(0, 2, size=32).astype(np.int32)
+    cts = K.encrypt(bits, 9)
+    lin = (cts[:16] + cts[16:]) % np.uint64(P.big_q)
+    got = fhew.Fhew.op(bk, [1, 1, 1, 0], lin)
+    assert (got == K.op([1, 1, 1, 0], lin, threads=4)).all()
+    assert (K.decrypt(got) == 1 - (bits[:16] & bits[16:])).all()
+    # without the export nothing but the two secrets leaves the device; same key again
+    bk2, z2, s2 = fhew.BootstrappingKey.key_gen(ctx, param, seed)
+    assert (z2 == z).all() and (fhew.Fhew.op(bk2, [1, 1, 1, 0], lin) == got).all()
+    bk2.free()
+    # serialised format: round trip reproduces the key bit for bit (same outputs), damaged blobs are rejected
+    blob = bk.serialize()
+    bk3 = fhew.BootstrappingKey.deserialize(ctx, blob)
+    assert bk3.param.n_s == param.n_s and bk3.param.big_q == param.big_q
+    assert (fhew.Fhew.op(bk3, [1, 1, 1, 0], lin) == got).all()
+    assert (bk3.serialize() == blob).all()
+    bk3.free()
+    for damage in ("magic", "version", "truncate", "section"):
+        bad = blob.copy()
+        if damage == "magic":
+            bad[0] ^= 0xFF
+        elif damage == "version":
+            bad[8] = 9
+        elif damage == "truncate":
+            bad = bad[:-8]
+        else:
+            bad[32] ^= 1  # brk_bytes
+        with pytest.raises(pkg.FheError):
+            fhew.BootstrappingKey.deserialize(ctx, bad)
+    bk.free()
