@@ -550,6 +550,51 @@ def ntt_e2e(pkg, ctx, torch, log_n, batch, reps):
             "d2h_bytes_per_step": batch * n * 8, "api": "fhe_ntt_fwd_host"}
 
 
+def ckks_s2c_leg(pkg, ctx, torch, dist, world, rank, local, count, steps):
+    """BASELINE configs[4], the part the reference implements (scheme/ckks/src/bootstrapping.rs:73-108; EvalMod / ModRaise do not
+    exist there): Bootstrapping::slot_to_coeff at N = 2^16, L = 8, r = 3 - five grouped factor matrices, level 8 -> 3 - on `count`
+    ciphertexts per GPU.  Plans and diagonals are computed once on the host (complex128 encodings: timing only; the 256-bit path
+    and bit-exact parity are in tests/test_gpu_ckks_boot.py at log_n <= 9), the rotation keys exist on rank 0 and reach the other
+    ranks by NCCL broadcast."""
+    from learn_fhe_b200 import ckks, ckks_bootstrapping as cb
+    dev = "cuda:%d" % local
+    stream = torch.cuda.current_stream(local)
+    log_n, L = 16, 8
+    P = ckks.CkksParam.new(ctx, log_n, 55, L)
+    t0 = time.perf_counter()
+    bp = cb.BootstrappingParam(P, 3, "f64")
+    rng = np.random.default_rng(0x5EED0006)
+    mods = P.qs + P.ps
+
+    def ksk_for(j):
+        if rank != 0:
+            return np.zeros((2, 2 * L, P.n), dtype=np.uint64)
+        return np.stack([np.stack([rng.integers(0, m, size=P.n, dtype=np.uint64) for m in mods]) for _ in range(2)])
+
+    bk = cb.BootstrappingKey(bp, ksk_for, chains=("sfft",))
+    if world > 1:
+        bk.broadcast_keys(dist, root=0)
+    ct = torch.empty((count, 2, L, P.n), dtype=torch.int64, device=dev)
+    for i, m in enumerate(P.qs):
+        ct[:, :, i, :].random_(0, m)
+    out = cb.Bootstrapping.chain_dev(bk, "sfft", ct)  # warm-up: uploads the encoded diagonals of the five plans
+    setup_s = time.perf_counter() - t0
+    ms = device_ms(torch, stream, lambda: cb.Bootstrapping.chain_dev(bk, "sfft", ct), 1, steps)
+    ms = max_over_ranks(torch, dist, world, dev, ms)
+    plans = [bk.plan("sfft", i, L - (len(bp.sfft_fmats) - 1 - i)) for i in range(len(bp.sfft_fmats))]
+    res = {"metric": "ckks_slot_to_coeff_per_sec", "value": count * world * steps / (ms * 1e-3), "unit": "ciphertexts/s", "ciphertexts_per_gpu": count,
+           "ms_per_step": ms / steps, "config": "N=2^16, L=8, r=3: %d grouped matrices, level %d -> %d; synthetic keys, complex128-encoded diagonals" % (
+               len(bp.sfft_fmats), L, out.shape[2]),
+           "rotation_keys": len(bk.rtk), "rotation_key_bytes": bk.nbytes, "keys": "rank 0, NCCL broadcast" if world > 1 else "single GPU",
+           "rotations_per_ciphertext": sum(len(p["baby"]) - 1 + len(p["giant"]) - 1 for p in plans),
+           "plain_mults_per_ciphertext": int(sum(p["present"].sum() for p in plans)), "host_setup_s": setup_s}
+    bk.free()
+    P.free()
+    del ct, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def next_rows_leg(pkg, ctx, torch, bk, param, local):
     """Throughput of the SURVEY.md §8(f) rows built so far, one GPU (rank 0), small fixed sizes; parity of each is in tests/."""
     from learn_fhe_b200 import ckks, circuits, fhew
@@ -779,6 +824,7 @@ def main():
     tfhe_res = None if args.no_tfhe else tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, tsteps, False, strong)
     tfhe_res_1024 = None if args.no_tfhe else tfhe_leg(pkg, ctx, torch, dist, world, rank, local, args.tfhe_batch, tsteps, True, strong)
     ckks_res = None if args.no_ckks else ckks_leg(pkg, ctx, torch, dist, world, rank, local, args.ckks_batch, max(1, min(args.steps, 3)))
+    s2c_res = None if (args.no_ckks or args.no_next) else ckks_s2c_leg(pkg, ctx, torch, dist, world, rank, local, 8, 2)
 
     # the other scaling curve (configs[2]: the 16 384 batch split 16 384 / R): measured in the same run when there is more than one
     # rank, so that one driver sweep over N yields both the weak and the strong line
@@ -859,6 +905,8 @@ def main():
             line["tfhe_pbs_n1024_synthetic"] = tfhe_res_1024
         if ckks_res is not None:
             line["ckks_mul"] = ckks_res
+        if s2c_res is not None:
+            line["ckks_slot_to_coeff"] = s2c_res
         if other is not None:
             line["other_scaling"] = other
         if next_res is not None:

@@ -206,10 +206,10 @@ class BootstrappingParam:
         self.sfft_fmats = _group(sfft_fmats(B, self.l), r)
         self.sifft_fmats = _group(sifft_fmats(B, self.l), r)
 
-    def rotation_indices(self):
-        """bootstrapping.rs:61-65: every non-zero baby / giant index of every grouped matrix."""
+    def rotation_indices(self, chains=("sfft", "sifft")):
+        """bootstrapping.rs:61-65: every non-zero baby / giant index of every grouped matrix (of the chains asked for)."""
         js = []
-        for mat in self.sfft_fmats + self.sifft_fmats:
+        for mat in (self.sfft_fmats if "sfft" in chains else []) + (self.sifft_fmats if "sifft" in chains else []):
             for j in mat.bsgs().ijs():
                 if j != 0 and j not in js:
                     js.append(j)
@@ -249,10 +249,10 @@ class BootstrappingKey:
     `ksk_for(j)` returns the reference-layout key [2][2L][N] for rotation index j (rank 0; other ranks pass zeros of that shape
     and receive the key through broadcast_keys)."""
 
-    def __init__(self, bparam, ksk_for):
+    def __init__(self, bparam, ksk_for, chains=("sfft", "sifft")):
         self.bparam = bparam
-        self.rtk = {j: _ckks.CkksKeySwitchingKey(bparam.param, ksk_for(j)) for j in bparam.rotation_indices()}
-        self._plans = {}
+        self.rtk = {j: _ckks.CkksKeySwitchingKey(bparam.param, ksk_for(j)) for j in bparam.rotation_indices(chains)}
+        self._plans, self._dev_plans = {}, {}
 
     def broadcast_keys(self, dist, root=0):
         for j in sorted(self.rtk):
@@ -279,6 +279,37 @@ class Bootstrapping:
     @staticmethod
     def _rots(bk, idxs):
         return [(0, None) if j == 0 else (bk.bparam.rotation_exponent(j), bk.rtk[j]) for j in idxs]
+
+    @staticmethod
+    def mul_mat_dev(bk, which, idx, ct_dev, out_dev=None):
+        """Device-resident form of mul_mat: ct_dev [count][2][level][N] (torch int64 CUDA) -> [count][2][level-1][N]; the
+        encoded diagonals of the plan are uploaded once and stay on the device."""
+        import ctypes as C
+        import torch
+        from . import CkksRot, dptr, hptr, to_dev
+        P = bk.bparam.param
+        level, count = ct_dev.shape[2], ct_dev.shape[0]
+        key = (which, idx, level)
+        if key not in bk._dev_plans:
+            p = bk.plan(which, idx, level)
+            mk = lambda lst: (CkksRot * len(lst))(*[CkksRot(t, k.h if k is not None else None) for t, k in lst])
+            bk._dev_plans[key] = dict(nb=len(p["baby"]), ng=len(p["giant"]), baby=mk(Bootstrapping._rots(bk, p["baby"])),
+                                      giant=mk(Bootstrapping._rots(bk, p["giant"])), present=np.ascontiguousarray(p["present"], dtype=np.uint8),
+                                      pts=to_dev(p["pts"], P.ctx.device))
+        d = bk._dev_plans[key]
+        if out_dev is None:
+            out_dev = torch.empty((count, 2, level - 1, P.n), dtype=torch.int64, device=ct_dev.device)
+        P.ctx.call("fhe_ckks_mul_mat", P.h, level, count, d["nb"], C.cast(d["baby"], C.c_void_p), d["ng"], C.cast(d["giant"], C.c_void_p),
+                   hptr(d["present"]), dptr(d["pts"]), dptr(ct_dev), dptr(out_dev))
+        return out_dev
+
+    @staticmethod
+    def chain_dev(bk, which, ct_dev):
+        """slot_to_coeff (which = "sfft") / coeff_to_slot ("sifft") on a device-resident batch."""
+        mats = bk.bparam.sfft_fmats if which == "sfft" else bk.bparam.sifft_fmats
+        for idx in range(len(mats) - 1, -1, -1):
+            ct_dev = Bootstrapping.mul_mat_dev(bk, which, idx, ct_dev)
+        return ct_dev
 
     @staticmethod
     def mul_mat(bk, which, idx, ct):
