@@ -229,6 +229,34 @@ HD void ff_p4(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32
 #pragma unroll
     for (int j = 0; j < 16; ++j) d[P0 ^ swzf((uint32_t)j << 2)] = x[j];
 }
+// The same pass with the 16 elements of a group split over a LANE PAIR (lane, lane ^ 16): thread `part` runs the radix-8 half
+// (stages 6..4) on elements 8 part .. 8 part + 7 - exactly fast_inv_regs<3> with chunk index 2 (8 + hi) + part - and the two
+// threads then share the 8 butterflies of stage 3 (pairs (low, low + 8), one twiddle): part 0 takes low = 0..3, part 1
+// low = 4..7, each receiving the four partner values it needs by one __shfl_xor each.  All four warps of the CTA work on P4
+// (with ff_p4 only the first warp of each half did: r01 ncu, barrier stalls 22 %).  Same butterflies on the same values, so the
+// result is bit-identical to ff_p4, which tests/hostsim keeps replaying.
+#if defined(__CUDA_ARCH__)
+DEV void ff_p4_split(const FhewFastDev& P, const FhewFastSmem& S, uint32_t poly, uint32_t grp, uint32_t part) {
+    const uint32_t lo = grp & 3u, hi = grp >> 2;
+    const uint32_t P0 = swzf((hi << 6) | lo);
+    uint32_t* d = S.dig + (poly << FF_LOGN);
+    uint32_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = d[P0 ^ swzf((uint32_t)(part * 8 + j) << 2)];
+    fast_inv_regs<Lz32, 3, false, FF_TW_NC != 0>(P.m, x, S.itw, ((8u + hi) << 1) + part, P.ninv, P.wninv);
+    const TwPair<uint32_t> t = ff_tw(S.itw + 8u + hi);
+    // part 0 sends x[4..7] and keeps x[0..3]; part 1 sends x[0..3] (elements 8..11) and keeps x[4..7] (elements 12..15)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t send = part ? x[i] : x[4 + i];
+        const uint32_t recv = __shfl_xor_sync(0xFFFFFFFFu, send, 16);
+        uint32_t a = part ? recv : x[i], b = part ? x[4 + i] : recv;  // elements (4 part + i, 4 part + i + 8)
+        P.m.bf_inv(a, b, t, 3);
+        d[P0 ^ swzf((uint32_t)(4 * part + i) << 2)] = a;
+        d[P0 ^ swzf((uint32_t)(4 * part + i + 8) << 2)] = b;
+    }
+}
+#endif
 // ---- P5: inverse radix-8 pass (stages 2..0, n^-1 folded) of polynomial h, canonical result (+ add(j)) -> acc_out[h][g + 64 j] -------
 // v[j] = canonical coefficient g + 64 j of result polynomial h
 template <typename Add>
@@ -313,8 +341,20 @@ HD void ff_phase2(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, 
     for (uint32_t u = l; u < (hi - lo) * 32u; u += 64u) ff_p2(P, S, lo + (u >> 5), u & 31u);
 }
 HD void ff_phase3(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) { ff_p3(P, S, s.key, s.rows, tid); }
+// FF_P4_SPLIT = 1: P4 groups split over lane pairs with __shfl_xor, all four warps busy (ff_p4_split); 0: one warp per half.
+// Measured on B200 (r02, FHEW-T, batch 16 384, two runs each): split 489.6 k gates/s (32.60 ms per launch), one warp per half
+// 500.8 k (31.85 ms).  With 7 CTAs resident per SM the idle warps of one CTA are covered by the other CTAs, and the split adds
+// 4 shuffles + 8 selects per thread and doubles the threads that take part in the phase's barrier: it LOSES 2.2 %, so it is off.
+#ifndef FF_P4_SPLIT
+#define FF_P4_SPLIT 0
+#endif
 HD void ff_phase4(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) {
+#if defined(__CUDA_ARCH__) && FF_P4_SPLIT
+    // thread (half h, warp w of the half, lane): group 16 w + (lane & 15), part lane >> 4
+    ff_p4_split(P, S, (tid >> 6) * FF_RB, ((tid >> 5) & 1u) * 16u + (tid & 15u), (tid >> 4) & 1u);
+#else
     if ((tid & 32u) == 0) ff_p4(P, S, (tid >> 6) * FF_RB, tid & 31u);  // first warp of each half
+#endif
 }
 HD void ff_phase5(const FhewFastDev& P, const FhewFastSmem& S, const FfStep& s, uint32_t tid) {
     const uint32_t g = tid & 63u, h = tid >> 6;
