@@ -265,6 +265,18 @@ void fhe_ckks_ksk_free(fhe_ctx* ctx, fhe_ckks_ksk* ksk);
 /* device bytes of the evaluation-form key and its one-time NCCL broadcast from `root` (keys are generated / uploaded on one rank,
  * 16 MiB per key-switching key at N = 2^16, L = 8) */
 size_t fhe_ckks_ksk_bytes(const fhe_ckks_ksk* ksk);
+/* Key generation ON THE DEVICE: Ckks::sk_gen (ckks.rs:139-141), rlk_gen (164-167) and one automorphism key
+ * per exponent of auto_ts (cjk_gen / rtk_gen, 169-184: t = -1 or 5^j mod 2N), each a ksk_gen (154-162) whose masks and errors come
+ * from the counter-based stream of csrc/keygen_stream.cuh; the keys stay on the device in evaluation form.  keys_out receives
+ * 1 + n_auto handles (relinearisation key first), sk_out [N] the ternary secret (int64, host); export_out is optional (HOST,
+ * [1 + n_auto][2 (b, a)][2L][N], the coefficient-form keys in the layout of fhe_ckks_ksk_upload). */
+fhe_status fhe_ckks_keygen(fhe_ctx* ctx, fhe_ckks_ctx* ck, uint64_t seed, size_t n_auto, const int64_t* auto_ts, int64_t* sk_out,
+                           fhe_ckks_ksk** keys_out, uint64_t* export_out);
+/* Serialised key-switching key: header {magic "FHEB200K", version 1, kind 3, log_n, L, bytes} | the evaluation-form device image;
+ * rejected with FHE_EINVAL when it does not match the context it is loaded into. */
+size_t fhe_ckks_ksk_serialized_size(const fhe_ckks_ksk* ksk);
+fhe_status fhe_ckks_ksk_serialize(fhe_ctx* ctx, const fhe_ckks_ctx* ck, const fhe_ckks_ksk* ksk, void* buf, size_t cap);
+fhe_status fhe_ckks_ksk_deserialize(fhe_ctx* ctx, const fhe_ckks_ctx* ck, const void* buf, size_t len, fhe_ckks_ksk** out);
 fhe_status fhe_ckks_ksk_broadcast(fhe_ctx* ctx, fhe_ckks_ksk* ksk, void* nccl_comm, int root);
 /* Ckks::mul = tensor product + relinearize + rescale (ckks.rs:255-272) on `count` pairs at level l (l limbs):
  * ct layout [count][2 (b, a)][l][N] coefficient form (ckks.rs:112-121); out [count][2][l-1][N] */

@@ -178,6 +178,11 @@ def lib():
         L.fhe_ckks_ksk_bytes.argtypes = [vp]
         L.fhe_ckks_ksk_bytes.restype = sz
         L.fhe_ckks_ksk_broadcast.argtypes = [vp, vp, vp, C.c_int]
+        L.fhe_ckks_keygen.argtypes = [vp, vp, u64, sz, vp, vp, vp, vp]
+        L.fhe_ckks_ksk_serialized_size.argtypes = [vp]
+        L.fhe_ckks_ksk_serialized_size.restype = sz
+        L.fhe_ckks_ksk_serialize.argtypes = [vp, vp, vp, vp, sz]
+        L.fhe_ckks_ksk_deserialize.argtypes = [vp, vp, vp, sz, C.POINTER(vp)]
         L.fhe_ckks_mul_relin_rescale_batch.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
         L.fhe_ckks_mul_relin_rescale_batch_host.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
         L.fhe_ckks_key_switch.argtypes = [vp, vp, vp, i64, sz, sz, vp, vp]

@@ -81,6 +81,25 @@ class CkksKeySwitchingKey:
         param.ctx.call("fhe_ckks_ksk_upload", param.h, hptr(ksk), C.byref(h))
         self.h = h
 
+    @classmethod
+    def _adopt(cls, param, h):
+        self = cls.__new__(cls)
+        self.param, self.h = param, C.c_void_p(h) if not isinstance(h, C.c_void_p) else h
+        return self
+
+    def serialize(self):
+        size = int(self.param.ctx.L.fhe_ckks_ksk_serialized_size(self.h))
+        buf = np.zeros(size, dtype=np.uint8)
+        self.param.ctx.call("fhe_ckks_ksk_serialize", self.param.h, self.h, hptr(buf), size)
+        return buf
+
+    @classmethod
+    def deserialize(cls, param, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        h = C.c_void_p()
+        param.ctx.call("fhe_ckks_ksk_deserialize", param.h, hptr(blob), blob.size, C.byref(h))
+        return cls._adopt(param, h)
+
     def free(self):
         if getattr(self, "h", None):
             self.param.ctx.L.fhe_ckks_ksk_free(self.param.ctx.h, self.h)
@@ -101,6 +120,19 @@ class CkksKeySwitchingKey:
             self.free()
         except Exception:
             pass
+
+
+def key_gen(param, seed, auto_ts=(), export=False):
+    """Ckks::sk_gen + rlk_gen + one automorphism key per exponent (ckks.rs:139-184) on the device from the counter stream of `seed`:
+    returns (sk [N] int64, rlk, [automorphism keys]) and, with export=True, the coefficient-form keys [1 + n][2][2L][N] too."""
+    ts = np.ascontiguousarray(list(auto_ts), dtype=np.int64)
+    sk = np.zeros(param.n, dtype=np.int64)
+    handles = (C.c_void_p * (1 + len(ts)))()
+    ex = np.zeros((1 + len(ts), 2, 2 * param.big_l, param.n), dtype=np.uint64) if export else None
+    param.ctx.call("fhe_ckks_keygen", param.h, seed, len(ts), hptr(ts) if len(ts) else None, hptr(sk), C.cast(handles, C.c_void_p),
+                   hptr(ex) if export else None)
+    keys = [CkksKeySwitchingKey._adopt(param, handles[i]) for i in range(1 + len(ts))]
+    return (sk, keys[0], keys[1:], ex) if export else (sk, keys[0], keys[1:])
 
 
 class Ckks:

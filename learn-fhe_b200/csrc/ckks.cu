@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "ctx.cuh"
+#include "keygen_stream.cuh"
 #include "rns_core.cuh"
 #include "rns_tables.hpp"
 
@@ -207,6 +208,51 @@ __global__ void __launch_bounds__(256) rns_automorphism_kernel(const Mod64* __re
         if (it >= n) v = mods[p % l].neg(v);
         out[(p << log_n) + (it & (n - 1))] = v;
     }
+}
+
+// ---- key generation on the device (ckks.rs:154-162 ksk_gen, 215-225 sk_encrypt) --------------------------------
+// key buffer [2 (b, a)][2L][n], coefficient form: a_i[c] uniform mod (q|p)_i from the counter stream; b_i[c] = e[c] + P sk'[c] mod
+// (q|p)_i (P = prod ps; the same small e for every limb, RnsRq::sample_i64); the - a * sk term is subtracted afterwards
+__global__ void __launch_bounds__(256) ckks_kg_rows_kernel(uint64_t seed, uint32_t da, uint32_t de, const Mod64* __restrict__ mods,
+                                                           const uint64_t* __restrict__ pmod_all /* [2L]: P mod modulus */, int limbs, int log_n,
+                                                           const int64_t* __restrict__ skp, uint64_t* __restrict__ key) {
+    const size_t n = (size_t)1 << log_n;
+    const unsigned long long total = (unsigned long long)limbs << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int i = (int)(idx >> log_n);
+        const size_t c = (size_t)(idx & (n - 1));
+        const Mod64 m = mods[i];
+        auto res = [&](int64_t v) { return v < 0 ? m.q - (uint64_t)(-v) % m.q : (uint64_t)v % m.q; };
+        uint64_t sp = res(skp[c]);
+        if (sp == m.q) sp = 0;
+        uint64_t e = res(ks_gauss(seed, de, c));
+        if (e == m.q) e = 0;
+        key[idx] = m.add(e, m.mul(pmod_all[i], sp));
+        key[total + idx] = ks_uniform(seed, da, idx, m.q);
+    }
+}
+// dst[i][c] = residue of the small integer v[c] modulo limb i
+__global__ void __launch_bounds__(256) ckks_kg_residues_kernel(const Mod64* __restrict__ mods, int limbs, int log_n, const int64_t* __restrict__ v,
+                                                               uint64_t* __restrict__ dst) {
+    const size_t n = (size_t)1 << log_n;
+    const unsigned long long total = (unsigned long long)limbs << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const Mod64 m = mods[idx >> log_n];
+        const int64_t x = v[idx & (n - 1)];
+        const uint64_t r = x < 0 ? m.q - (uint64_t)(-x) % m.q : (uint64_t)x % m.q;
+        dst[idx] = r == m.q ? 0 : r;
+    }
+}
+// t <- t o s (evaluation domain, per-limb modulus); then, after the inverse transform, b <- b - t
+__global__ void __launch_bounds__(256) ckks_kg_mul_kernel(const Mod64* __restrict__ mods, int log_n, unsigned long long total, uint64_t* __restrict__ t,
+                                                          const uint64_t* __restrict__ s) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) t[idx] = mods[idx >> log_n].mul(t[idx], s[idx]);
+}
+__global__ void __launch_bounds__(256) ckks_kg_sub_kernel(const Mod64* __restrict__ mods, int log_n, unsigned long long total, uint64_t* __restrict__ b,
+                                                          const uint64_t* __restrict__ t) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) b[idx] = mods[idx >> log_n].sub(b[idx], t[idx]);
 }
 
 static unsigned stream_grid(fhe_ctx* ctx, unsigned long long work) {
@@ -448,6 +494,155 @@ void fhe_ckks_ksk_free(fhe_ctx* ctx, fhe_ckks_ksk* ksk) {
     if (ctx) cudaStreamSynchronize(ctx->stream);
     if (ksk->d_eval) cudaFree(ksk->d_eval);
     delete ksk;
+}
+
+// Key generation on the device: Ckks::sk_gen (ckks.rs:139-141, zo(0.5)), rlk_gen (164-167: ksk_gen(sk, sk^2)) and
+// one automorphism key per exponent in auto_ts (cjk_gen / rtk_gen, 169-184: ksk_gen(sk, sk(X^t))), every key generated on the GPU
+// from the counter-based stream of csrc/keygen_stream.cuh and left there in evaluation form.  keys_out receives 1 + n_auto
+// handles (rlk first); sk_out [N] the secret; export_out (optional, HOST, [1 + n_auto][2 (b, a)][2L][N]) the coefficient-form keys
+// in the layout of fhe_ckks_ksk_upload for parity checks.
+fhe_status fhe_ckks_keygen(fhe_ctx* ctx, fhe_ckks_ctx* ck, uint64_t seed, size_t n_auto, const int64_t* auto_ts, int64_t* sk_out,
+                           fhe_ckks_ksk** keys_out, uint64_t* export_out) {
+    if (!ctx || !ck || !keys_out || (n_auto && !auto_ts)) return FHE_EINVAL;
+    const unsigned log_n = ck->log_n;
+    const size_t n = (size_t)1 << log_n, L2 = 2 * ck->big_l, plane = L2 * n;
+    for (size_t i = 0; i <= n_auto; ++i) keys_out[i] = nullptr;
+    std::vector<int64_t> sk(n);
+    for (size_t c = 0; c < n; ++c) sk[c] = ks_ternary(seed, KS_CKKS_SK, c);
+    const std::vector<uint64_t> qps = level_qps(ck, ck->big_l);
+    std::vector<uint64_t> pmod_all(L2, 0);
+    for (size_t i = 0; i < ck->big_l; ++i) {
+        uint64_t v = 1 % qps[i];
+        for (uint64_t p : ck->ps) v = host_mulmod(v, p % qps[i], qps[i]);
+        pmod_all[i] = v;  // P mod p_j = 0 for the special primes themselves
+    }
+    int64_t *d_sk = nullptr, *d_skp = nullptr;
+    uint64_t *d_sk_eval = nullptr, *d_tmp = nullptr, *d_pmod = nullptr;
+    fhe_status st = FHE_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && st == FHE_OK) st = fail(ctx, FHE_ECUDA, "ckks keygen %s: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaMalloc(&d_sk, n * 8), "alloc");
+    cu(cudaMalloc(&d_skp, n * 8), "alloc");
+    cu(cudaMalloc(&d_sk_eval, plane * 8), "alloc");
+    cu(cudaMalloc(&d_tmp, plane * 8), "alloc");
+    cu(cudaMalloc(&d_pmod, L2 * 8), "alloc");
+    if (st == FHE_OK) {
+        cu(cudaMemcpyAsync(d_sk, sk.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream), "copy");
+        cu(cudaMemcpyAsync(d_pmod, pmod_all.data(), L2 * 8, cudaMemcpyHostToDevice, ctx->stream), "copy");
+    }
+    const unsigned grid = stream_grid(ctx, plane);
+    if (st == FHE_OK) {
+        ckks_kg_residues_kernel<<<grid, 256, 0, ctx->stream>>>(ck->d_mods, (int)L2, (int)log_n, d_sk, d_sk_eval);
+        st = after_launch(ctx, "ckks_kg_residues_kernel");
+    }
+    if (st == FHE_OK) st = launch_ntt_rns_u64(ctx, qps.data(), L2, log_n, L2, d_sk_eval, true);
+    // sk^2 as small integers: exact through the first prime (|coefficient| <= N << q_0 / 2), the reference's i64 Karatsuba gives the same
+    std::vector<int64_t> sk_sq(n);
+    if (st == FHE_OK) {
+        const uint64_t q0 = ck->qs[0];
+        cu(cudaMemcpyAsync(d_tmp, d_sk_eval, n * 8, cudaMemcpyDeviceToDevice, ctx->stream), "copy");  // limb 0 of sk in evaluation form
+        if (st == FHE_OK) st = fhe_pointwise_mul_u64(ctx, q0, n, d_tmp, d_tmp, d_tmp);
+        if (st == FHE_OK) st = launch_ntt_u64(ctx, q0, log_n, 1, d_tmp, false);
+        std::vector<uint64_t> h(n);
+        cu(cudaMemcpyAsync(h.data(), d_tmp, n * 8, cudaMemcpyDeviceToHost, ctx->stream), "copy");
+        cu(cudaStreamSynchronize(ctx->stream), "sync");
+        for (size_t c = 0; c < n; ++c) sk_sq[c] = h[c] < (q0 >> 1) ? (int64_t)h[c] : (int64_t)h[c] - (int64_t)q0;
+    }
+    for (size_t key = 0; key <= n_auto && st == FHE_OK; ++key) {
+        std::vector<int64_t> skp = sk_sq;
+        if (key > 0) {  // sk(X^t) on the i64 secret (avec.rs:34-50)
+            const int64_t m2 = 2 * (int64_t)n, t = ((auto_ts[key - 1] % m2) + m2) % m2;
+            for (size_t i = 0; i < n; ++i) {
+                const size_t it = (size_t)(((unsigned long long)i * (unsigned long long)t) % (unsigned long long)m2);
+                if (it < n)
+                    skp[it] = sk[i];
+                else
+                    skp[it - n] = -sk[i];
+            }
+        }
+        fhe_ckks_ksk* k = new fhe_ckks_ksk();
+        k->bytes = 2 * plane * 8;
+        if (cudaMalloc((void**)&k->d_eval, k->bytes) != cudaSuccess) {
+            delete k;
+            st = fail(ctx, FHE_ENOMEM, "key alloc");
+            break;
+        }
+        keys_out[key] = k;
+        cu(cudaMemcpyAsync(d_skp, skp.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream), "copy");
+        ckks_kg_rows_kernel<<<grid, 256, 0, ctx->stream>>>(seed, ks_ckks_a((uint32_t)key), ks_ckks_e((uint32_t)key), ck->d_mods, d_pmod, (int)L2, (int)log_n,
+                                                           d_skp, k->d_eval);
+        if (st == FHE_OK) st = after_launch(ctx, "ckks_kg_rows_kernel");
+        cu(cudaMemcpyAsync(d_tmp, k->d_eval + plane, plane * 8, cudaMemcpyDeviceToDevice, ctx->stream), "copy");
+        if (st == FHE_OK) st = launch_ntt_rns_u64(ctx, qps.data(), L2, log_n, L2, d_tmp, true);
+        ckks_kg_mul_kernel<<<grid, 256, 0, ctx->stream>>>(ck->d_mods, (int)log_n, plane, d_tmp, d_sk_eval);
+        if (st == FHE_OK) st = after_launch(ctx, "ckks_kg_mul_kernel");
+        if (st == FHE_OK) st = launch_ntt_rns_u64(ctx, qps.data(), L2, log_n, L2, d_tmp, false);
+        ckks_kg_sub_kernel<<<grid, 256, 0, ctx->stream>>>(ck->d_mods, (int)log_n, plane, k->d_eval, d_tmp);  // b = -(a sk) + e + P sk'
+        if (st == FHE_OK) st = after_launch(ctx, "ckks_kg_sub_kernel");
+        if (export_out) {
+            cu(cudaMemcpyAsync(export_out + key * 2 * plane, k->d_eval, 2 * plane * 8, cudaMemcpyDeviceToHost, ctx->stream), "export");
+            cu(cudaStreamSynchronize(ctx->stream), "sync");
+        }
+        if (st == FHE_OK) st = launch_ntt_rns_u64(ctx, qps.data(), L2, log_n, 2 * L2, k->d_eval, true);
+        cu(cudaStreamSynchronize(ctx->stream), "sync");  // skp (host vector) is re-used by the next key
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : {(void*)d_sk, (void*)d_skp, (void*)d_sk_eval, (void*)d_tmp, (void*)d_pmod})
+        if (p) cudaFree(p);
+    if (st != FHE_OK) {
+        for (size_t i = 0; i <= n_auto; ++i) {
+            fhe_ckks_ksk_free(ctx, keys_out[i]);
+            keys_out[i] = nullptr;
+        }
+        return st;
+    }
+    if (sk_out) std::copy(sk.begin(), sk.end(), sk_out);
+    return FHE_OK;
+}
+// serialised key-switching key: header {magic "FHEB200K", version 1, kind 3, log_n, L, bytes} | the evaluation-form image
+struct CkksBlobHeader {
+    char magic[8];
+    uint32_t version, kind;
+    uint64_t log_n, big_l, bytes;
+};
+size_t fhe_ckks_ksk_serialized_size(const fhe_ckks_ksk* ksk) { return ksk ? sizeof(CkksBlobHeader) + ksk->bytes : 0; }
+fhe_status fhe_ckks_ksk_serialize(fhe_ctx* ctx, const fhe_ckks_ctx* ck, const fhe_ckks_ksk* ksk, void* buf, size_t cap) {
+    if (!ctx || !ck || !ksk || !buf) return FHE_EINVAL;
+    FHE_REQUIRE(ctx, cap >= fhe_ckks_ksk_serialized_size(ksk), "buffer too small for the serialised key");
+    CkksBlobHeader h;
+    memcpy(h.magic, "FHEB200K", 8);
+    h.version = 1;
+    h.kind = 3;
+    h.log_n = ck->log_n;
+    h.big_l = ck->big_l;
+    h.bytes = ksk->bytes;
+    memcpy(buf, &h, sizeof h);
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FHE_CUDA(ctx, cudaMemcpy((unsigned char*)buf + sizeof h, ksk->d_eval, ksk->bytes, cudaMemcpyDeviceToHost));
+    return FHE_OK;
+}
+fhe_status fhe_ckks_ksk_deserialize(fhe_ctx* ctx, const fhe_ckks_ctx* ck, const void* buf, size_t len, fhe_ckks_ksk** out) {
+    if (!ctx || !ck || !buf || !out) return FHE_EINVAL;
+    *out = nullptr;
+    CkksBlobHeader h;
+    FHE_REQUIRE(ctx, len >= sizeof h, "serialised key truncated");
+    memcpy(&h, buf, sizeof h);
+    FHE_REQUIRE(ctx, memcmp(h.magic, "FHEB200K", 8) == 0 && h.kind == 3, "not a serialised CKKS key-switching key");
+    FHE_REQUIRE(ctx, h.version == 1, "serialised key of another format version");
+    const size_t want = 2 * 2 * ck->big_l * (((size_t)1) << ck->log_n) * 8;
+    FHE_REQUIRE(ctx, h.log_n == ck->log_n && h.big_l == ck->big_l && h.bytes == want && len == sizeof h + want,
+                "serialised key does not match this CKKS context (ring degree / modulus chain / length)");
+    fhe_ckks_ksk* k = new fhe_ckks_ksk();
+    k->bytes = want;
+    if (cudaMalloc((void**)&k->d_eval, want) != cudaSuccess ||
+        cudaMemcpy(k->d_eval, (const unsigned char*)buf + sizeof h, want, cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (k->d_eval) cudaFree(k->d_eval);
+        delete k;
+        return fail(ctx, FHE_ECUDA, "key image upload failed");
+    }
+    *out = k;
+    return FHE_OK;
 }
 
 fhe_status fhe_ckks_mul_relin_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* rlk, size_t level, size_t count,

@@ -57,6 +57,10 @@ HD int64_t ks_ternary(uint64_t seed, uint32_t domain, uint64_t index) {
 // binary secret (distribution.rs:6-8): 0 / 1 with probability 1/2
 HD int64_t ks_binary(uint64_t seed, uint32_t domain, uint64_t index) { return (int64_t)(ks_u64(seed, domain, index) >> 63); }
 
+// stream domains of the CKKS key generation: secret, then (mask, error) per key: key 0 = relinearisation key, 1.. = automorphism keys
+enum : uint32_t { KS_CKKS_SK = 16, KS_CKKS_KEY0 = 17 };
+HD uint32_t ks_ckks_a(uint32_t key) { return KS_CKKS_KEY0 + 2 * key; }
+HD uint32_t ks_ckks_e(uint32_t key) { return KS_CKKS_KEY0 + 2 * key + 1; }
 // stream domains of the FHEW key generation
 enum : uint32_t { KS_FHEW_Z = 1, KS_FHEW_S = 2, KS_FHEW_KSK_A = 3, KS_FHEW_KSK_E = 4, KS_FHEW_BRK_A = 5, KS_FHEW_BRK_E = 6, KS_FHEW_AK_A = 7, KS_FHEW_AK_E = 8 };
 

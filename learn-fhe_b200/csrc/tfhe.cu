@@ -27,6 +27,7 @@ struct fhe_tfhe_key {
     fhe::DecompT64 ks_dec;
     void* d_brk = nullptr;  // Cx [n][(k+1)d][(k+1)][N/2]
     void* d_ksk = nullptr;  // u64 [(kN) d_ks][n+1]
+    void* d_ksk_colsum = nullptr;  // u64 [n+1]: 2^(ks_log_b - 1) * (sum over rows of ksk[row][j])  (digit-offset correction)
     size_t brk_bytes = 0, ksk_bytes = 0;
     // bounded-error fast path (tfhe_fast.cuh): second image of the bsk in that path's transform and layout, its tables
     fhe::TfheFastDev F;
@@ -262,15 +263,17 @@ __global__ void __launch_bounds__(256) tlwe_digits_kernel(DecompT64 dp, uint32_t
             v >>= dp.log_b;
             const uint64_t carry = (((limb - 1) | v) & limb) >> (dp.log_b - 1);
             v += carry;
-            dig[((grp * dp.d + k) * len + coef) * KS_G + g] = (int32_t)(int64_t)(limb - (carry << dp.log_b));
+            // stored with the offset B/2 so that the GEMM multiplies by a small UNSIGNED factor (two 32-bit multiplies per term
+            // instead of three for a sign-extended one); the epilogue takes (B/2) * column sum of the key off again
+            dig[((grp * dp.d + k) * len + coef) * KS_G + g] = (int32_t)(int64_t)(limb - (carry << dp.log_b)) + (int32_t)(1u << (dp.log_b - 1));
         }
     }
 }
 // out[c][j] = sum_idx ksk[idx][j] * dig[c][idx] (+ b_in for the body column j == n_out), wrapping mod 2^64
 __global__ void __launch_bounds__(KS_COLS) tlwe_key_switch_kernel(uint32_t rows /* len * d */, uint32_t n_out, uint32_t len,
                                                                    unsigned long long count, const int32_t* __restrict__ dig,
-                                                                   const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ ct_in,
-                                                                   uint64_t* __restrict__ out) {
+                                                                   const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ colsum_half,
+                                                                   const uint64_t* __restrict__ ct_in, uint64_t* __restrict__ out) {
     __shared__ __align__(16) int32_t sd[KS_CH * KS_G];
     const uint32_t j = blockIdx.x * KS_COLS + threadIdx.x, ld = n_out + 1;
     const unsigned long long grp = blockIdx.y;
@@ -291,10 +294,10 @@ __global__ void __launch_bounds__(KS_COLS) tlwe_key_switch_kernel(uint32_t rows 
 #pragma unroll
                 for (int q4 = 0; q4 < KS_G / 4; ++q4) {
                     const int4 dv = row[q4];
-                    acc[4 * q4 + 0] += kv * (uint64_t)(int64_t)dv.x;
-                    acc[4 * q4 + 1] += kv * (uint64_t)(int64_t)dv.y;
-                    acc[4 * q4 + 2] += kv * (uint64_t)(int64_t)dv.z;
-                    acc[4 * q4 + 3] += kv * (uint64_t)(int64_t)dv.w;
+                    acc[4 * q4 + 0] += kv * (uint64_t)(uint32_t)dv.x;
+                    acc[4 * q4 + 1] += kv * (uint64_t)(uint32_t)dv.y;
+                    acc[4 * q4 + 2] += kv * (uint64_t)(uint32_t)dv.z;
+                    acc[4 * q4 + 3] += kv * (uint64_t)(uint32_t)dv.w;
                 }
             }
         }
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(KS_COLS) tlwe_key_switch_kernel(uint32_t rows 
         for (int g = 0; g < KS_G; ++g) {
             const unsigned long long c = grp * KS_G + g;
             if (c < count) {
-                uint64_t v = acc[g];
+                uint64_t v = acc[g] - colsum_half[j];  // undo the digit offset: sum (d + B/2) k = sum d k + (B/2) sum k
                 if (j == n_out) v += ct_in[c * (len + 1) + len];
                 out[c * ld + j] = v;
             }
@@ -335,8 +338,8 @@ static fhe_status run_key_switch(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t c
     FHE_CHECK(after_launch(ctx, "tlwe_digits_kernel"));
     FHE_REQUIRE(ctx, groups <= 65535, "key-switch batch too large for one launch (max %d ciphertexts)", 65535 * KS_G);
     dim3 grid((pp.n + 1 + KS_COLS - 1) / KS_COLS, (unsigned)groups);
-    tlwe_key_switch_kernel<<<grid, KS_COLS, 0, ctx->stream>>>(rows, pp.n, len, count, (const int32_t*)scratch, (const uint64_t*)key->d_ksk, d_in,
-                                                              d_out);
+    tlwe_key_switch_kernel<<<grid, KS_COLS, 0, ctx->stream>>>(rows, pp.n, len, count, (const int32_t*)scratch, (const uint64_t*)key->d_ksk,
+                                                              (const uint64_t*)key->d_ksk_colsum, d_in, d_out);
     return after_launch(ctx, "tlwe_key_switch_kernel");
 }
 
@@ -505,8 +508,13 @@ fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uin
             h[r * ld + pp->n] = ksk_b[r];
         }
         key->ksk_bytes = h.size() * 8;
-        if (cudaMalloc(&key->d_ksk, key->ksk_bytes) != cudaSuccess ||
-            cudaMemcpy(key->d_ksk, h.data(), key->ksk_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+        std::vector<uint64_t> cs(ld, 0);
+        for (size_t r = 0; r < rows; ++r)
+            for (size_t j = 0; j < ld; ++j) cs[j] += h[r * ld + j];
+        for (size_t j = 0; j < ld; ++j) cs[j] <<= (pp->ks_log_b - 1);
+        if (cudaMalloc(&key->d_ksk, key->ksk_bytes) != cudaSuccess || cudaMalloc(&key->d_ksk_colsum, ld * 8) != cudaSuccess ||
+            cudaMemcpy(key->d_ksk, h.data(), key->ksk_bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(key->d_ksk_colsum, cs.data(), ld * 8, cudaMemcpyHostToDevice) != cudaSuccess)
             st = fail(ctx, FHE_ECUDA, "ksk upload failed");
     }
     if (st != FHE_OK) {
@@ -523,6 +531,7 @@ void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key) {
     if (ctx) cudaStreamSynchronize(ctx->stream);
     if (key->d_brk) cudaFree(key->d_brk);
     if (key->d_ksk) cudaFree(key->d_ksk);
+    if (key->d_ksk_colsum) cudaFree(key->d_ksk_colsum);
     if (key->d_brk_fast) cudaFree(key->d_brk_fast);
     if (key->d_fast_tab) cudaFree(key->d_fast_tab);
     delete key;
@@ -543,6 +552,7 @@ fhe_status fhe_tfhe_key_broadcast(fhe_ctx* ctx, fhe_tfhe_key* key, void* nccl_co
     if (!ctx || !key) return FHE_EINVAL;
     FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_brk, key->brk_bytes));
     FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ksk, key->ksk_bytes));
+    FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_ksk_colsum, ((size_t)key->param.n + 1) * 8));
     if (key->fast_ok) FHE_CHECK(fhe_keys_broadcast(ctx, nccl_comm, root, key->d_brk_fast, key->brk_fast_bytes));
     FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FHE_OK;

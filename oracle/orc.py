@@ -122,6 +122,7 @@ def lib():
         L.orc_tfhe_key_import.restype = C.c_void_p
         L.orc_tfhe_key_import.argtypes = [C.c_void_p, u64p, u64p, u64p]
         L.orc_ckks_key_import.restype = C.c_void_p
+        L.orc_ckks_keygen_ctr.restype = C.c_void_p
         L.orc_ckks_key_import.argtypes = [C.c_uint, u64p, u64p, C.c_size_t, u64p, i64p, u64p, C.c_size_t]
         L.orc_tfhe_key_free.argtypes = [C.c_void_p]
         L.orc_tfhe_key_free.restype = None
@@ -547,12 +548,14 @@ class CkksKey:
             _ck(-1)
         return self
 
-    def __init__(self, log_n, log_qi, big_l, seed, auto_ts=()):
+    def __init__(self, log_n, log_qi, big_l, seed, auto_ts=(), ctr=False):
+        """ctr=True: the key generation fed by the counter stream of the device keygen (oracle/orc_keygen.hpp)."""
         self.log_n, self.big_l = log_n, big_l
         self.n = 1 << log_n
         ts = np.ascontiguousarray(list(auto_ts), dtype=np.int64)
         self.auto_ts = [int(t) for t in ts]
-        self.h = lib().orc_ckks_keygen(log_n, log_qi, big_l, seed, ts, len(ts))
+        gen = lib().orc_ckks_keygen_ctr if ctr else lib().orc_ckks_keygen
+        self.h = gen(log_n, log_qi, big_l, seed, ts if len(ts) else np.zeros(1, dtype=np.int64), len(ts))
         if not self.h:
             _ck(-1)
         qs = np.zeros(big_l, dtype=np.uint64)

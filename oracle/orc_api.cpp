@@ -689,6 +689,16 @@ void* orc_ckks_key_import(unsigned log_n, const u64* qs, const u64* ps, size_t b
         return nullptr;
     }
 }
+void* orc_ckks_keygen_ctr(unsigned log_n, unsigned log_qi, unsigned big_l, u64 seed, const int64_t* auto_ts, size_t n_ts) {
+    try {
+        CkksParam P = ckks_param_new(log_n, log_qi, big_l);
+        for (u64 q : P.qps()) twiddle(q);
+        return new CkksKey(ckks_key_gen_ctr(P, seed, std::vector<i64>(auto_ts, auto_ts + n_ts)));
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 void orc_ckks_key_free(void* h) { delete (CkksKey*)h; }
 int orc_ckks_moduli(void* h, u64* qs, u64* ps) {
     ORC_TRY({

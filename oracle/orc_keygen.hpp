@@ -6,6 +6,7 @@
 // fhe_fhew_keygen: same seed -> the same key, word for word.
 #pragma once
 #include "../learn-fhe_b200/csrc/keygen_stream.cuh"
+#include "orc_ckks.hpp"
 #include "orc_fhew.hpp"
 
 namespace orc {
@@ -83,6 +84,38 @@ static inline FhewKey fhew_key_gen_ctr(const FhewParam& P, u64 seed) {
         }
         K.ak.push_back(std::move(rows));
     }
+    return K;
+}
+
+// Ckks::sk_gen / rlk_gen / cjk_gen / rtk_gen (scheme/ckks/src/ckks.rs:139-184, 215-225) as ckks_key_gen states them, fed by the counter
+// stream of the device key generation (fhe_ckks_keygen): key 0 = relinearisation key, key 1 + i = automorphism key of auto_ts[i]
+static inline CkksCt ckks_ksk_gen_ctr(const CkksParam& P, const std::vector<i64>& sk, const std::vector<i64>& sk_prime, u64 seed, uint32_t key) {
+    using namespace fhe;
+    Vec qps = P.qps();
+    const size_t n = P.n();
+    RnsPoly pt = rns_from_i64(qps, sk_prime);
+    for (size_t i = 0; i < qps.size(); ++i) {
+        u64 pm = prod_mod(P.ps, qps[i]);
+        for (auto& v : pt.limbs[i]) v = zq_mul(qps[i], v, pm);
+    }
+    CkksCt ct;
+    ct.a = rns_zero(qps, n);
+    for (size_t i = 0; i < qps.size(); ++i)
+        for (size_t c = 0; c < n; ++c) ct.a.limbs[i][c] = ks_uniform(seed, ks_ckks_a(key), (u64)i * n + c, qps[i]);
+    std::vector<i64> e(n);
+    for (size_t c = 0; c < n; ++c) e[c] = ks_gauss(seed, ks_ckks_e(key), c);
+    ct.b = rns_add(rns_add(rns_neg(rns_mul_i64(ct.a, sk)), rns_from_i64(qps, e)), pt);
+    return ct;
+}
+static inline CkksKey ckks_key_gen_ctr(const CkksParam& P, u64 seed, const std::vector<i64>& auto_ts) {
+    using namespace fhe;
+    CkksKey K;
+    K.param = P;
+    K.sk.resize(P.n());
+    for (size_t c = 0; c < P.n(); ++c) K.sk[c] = ks_ternary(seed, KS_CKKS_SK, c);
+    K.rlk = ckks_ksk_gen_ctr(P, K.sk, small_negacyclic_mul(P.qs[0], K.sk, K.sk), seed, 0);
+    for (size_t i = 0; i < auto_ts.size(); ++i)
+        K.autk.push_back({auto_ts[i], ckks_ksk_gen_ctr(P, K.sk, automorphism_i64(K.sk, auto_ts[i]), seed, (uint32_t)(1 + i))});
     return K;
 }
 

@@ -62,3 +62,35 @@ def test_device_keygen_equals_host_keygen_on_the_same_stream(pkg, ctx, orc, shap
         with pytest.raises(pkg.FheError):
             fhew.BootstrappingKey.deserialize(ctx, bad)
     bk.free()
+
+
+@pytest.mark.parametrize("log_n,big_l", [(4, 3), (10, 4), (13, 8)])
+def test_ckks_device_keygen_equals_host_keygen_on_the_same_stream(pkg, ctx, orc, log_n, big_l):
+    """fhe_ckks_keygen (ckks.rs:139-184 on the GPU) == oracle/orc_keygen.hpp on the same counter stream: secret, relinearisation key
+    and two automorphism keys word for word; products / rotations under the device keys equal the oracle's; serialise round trip."""
+    from learn_fhe_b200 import ckks
+    n = 1 << log_n
+    ts = (5, 2 * n - 1)
+    seed = 0x5EED0800 + log_n
+    K = orc.CkksKey(log_n, 55, big_l, seed, auto_ts=ts, ctr=True)
+    P = ckks.CkksParam(ctx, log_n, K.qs, K.ps)
+    sk, rlk, autk, ex = ckks.key_gen(P, seed, ts, export=True)
+    assert (sk == K.sk()).all()
+    assert (ex[0] == K.ksk(-1)).all()
+    for i in range(len(ts)):
+        assert (ex[1 + i] == K.ksk(i)).all(), i
+    rng = np.random.default_rng(log_n)
+    ct0 = K.encrypt(rng.integers(-99, 99, size=n, dtype=np.int64), big_l, 1)[None]
+    ct1 = K.encrypt(rng.integers(-99, 99, size=n, dtype=np.int64), big_l, 2)[None]
+    assert (ckks.Ckks.mul(P, rlk, ct0, ct1) == K.mul(ct0, ct1)).all()
+    assert (ckks.Ckks.key_switch(P, autk[0], ct0, ts[0])[0] == K.key_switch(0, ct0[0], apply_auto=True)).all()
+    blob = rlk.serialize()
+    again = ckks.CkksKeySwitchingKey.deserialize(P, blob)
+    assert (ckks.Ckks.mul(P, again, ct0, ct1) == K.mul(ct0, ct1)).all() and (again.serialize() == blob).all()
+    bad = blob.copy()
+    bad[16] ^= 1  # log_n of the header
+    with pytest.raises(pkg.FheError):
+        ckks.CkksKeySwitchingKey.deserialize(P, bad)
+    for k in [rlk, again] + autk:
+        k.free()
+    P.free()

@@ -36,4 +36,10 @@ if "ntt" in args:
                 ctx.call("fhe_ntt_fwd_u%d" % bits, q, log_n, b, pkg.dptr(t))
                 ctx.call("fhe_ntt_inv_u%d" % bits, q, log_n, b, pkg.dptr(t))
             ctx.sync()
+if "ntt16" in args:  # BASELINE configs[1]'s largest case, for the DRAM-traffic sum: 3 forward transforms of 4096 x 2^16 u64
+    q = pkg.first_two_adic_prime(55, 17)
+    t = torch.zeros(4096 << 16, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        ctx.call("fhe_ntt_fwd_u64", q, 16, 4096, pkg.dptr(t))
+    ctx.sync()
 print("prof_cmd done, launches:", ctx.launches)

@@ -27,6 +27,15 @@ for w in $WHAT; do
         tfhe) TRAFFIC=tfhe_blind_rotate_fast_kernel=16384 KEEP=1 run tfhe tfhe_blind_rotate_fast 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 2 ;;
         tfhe_exact) TRAFFIC=tfhe_blind_rotate_kernel=16384 KEEP=1 run tfhe_exact 'tfhe_blind_rotate_kernel' 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 0 ;;
         ckks) TRAFFIC= run ckks 'rns_|ckks_' 8 python tools/tfhe_bench.py ckks --count 128 ;;
+        traffic)  # DRAM bytes of whole multi-kernel operations (one metric pass): Ckks::mul on 512 pairs, NTT fwd 4096 x 2^16 u64
+            M="--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv"
+            python tools/tfhe_bench.py ckks --count 512 > $OUT/plain_traffic_ckks.log 2>&1 &&
+            ncu $M --log-file $OUT/traffic_ckks_${TAG}.csv python tools/tfhe_bench.py ckks --count 512 > $OUT/ncu_traffic_ckks.log 2>&1 &&
+            python tools/ncu_traffic_sum.py $OUT/traffic_ckks_${TAG}.csv ckks_mul_whole_op 512 3 'ckks_|rns_|ntt_fast' && cp profiles/ncu_traffic.json $OUT/ncu_traffic_merged.json
+            python tools/prof_cmd.py ntt16 > $OUT/plain_traffic_ntt.log 2>&1 &&
+            ncu $M --log-file $OUT/traffic_ntt_${TAG}.csv python tools/prof_cmd.py ntt16 > $OUT/ncu_traffic_ntt.log 2>&1 &&
+            python tools/ncu_traffic_sum.py $OUT/traffic_ntt_${TAG}.csv 'ntt_fwd_u64_2^16' 4096 3 'ntt_fast' && cp profiles/ncu_traffic.json $OUT/ncu_traffic_merged.json
+            echo "traffic: ok" ;;
         launches)
             python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/plain_bench.log 2>&1 || { echo "plain bench failed"; continue; }
             ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $OUT/launches_bench_${TAG}.csv \
