@@ -123,6 +123,7 @@ def lib():
         L.orc_tfhe_key_import.argtypes = [C.c_void_p, u64p, u64p, u64p]
         L.orc_ckks_key_import.restype = C.c_void_p
         L.orc_ckks_keygen_ctr.restype = C.c_void_p
+        L.orc_ckks_keygen_ctr.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint64, i64p, C.c_size_t]
         L.orc_ckks_key_import.argtypes = [C.c_uint, u64p, u64p, C.c_size_t, u64p, i64p, u64p, C.c_size_t]
         L.orc_tfhe_key_free.argtypes = [C.c_void_p]
         L.orc_tfhe_key_free.restype = None
