@@ -221,6 +221,14 @@ typedef struct fhe_tfhe_key fhe_tfhe_key;
  * brk polynomials are converted once to the twisted Fourier domain (c64.rs:20-28 + forward FFT). */
 fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* param, const uint64_t* brk, const uint64_t* ksk_a,
                                const uint64_t* ksk_b, fhe_tfhe_key** out);
+/* Key generation ON THE DEVICE: Bootstrapping::key_gen (scheme/tfhe/src/bootstrapping.rs:59-76; tggsw.rs:73-89,
+ * tglwe.rs:92-103, tlwe.rs:96-111,122-132) for the whole key - n TGGSW encryptions of the TLWE secret bits and the TLWE
+ * key-switching key - from the counter-based stream of csrc/keygen_stream.cuh (uniform torus masks; torus noise = an
+ * integer-only Irwin-Hall variate of standard deviation std * 2^64; the mask-secret products go through the same f64 FFT
+ * product as the reference's `&a * sk`).  z_out [n] / s_out [kN]: the binary secrets (int64, host).  brk_out / ksk_a_out /
+ * ksk_b_out (optional, HOST) export the key in the layout of fhe_tfhe_key_upload. */
+fhe_status fhe_tfhe_keygen(fhe_ctx* ctx, const fhe_tfhe_param* param, double tlwe_std, double tglwe_std, uint64_t seed, int64_t* z_out, int64_t* s_out,
+                           uint64_t* brk_out, uint64_t* ksk_a_out, uint64_t* ksk_b_out, fhe_tfhe_key** out);
 void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key);
 /* Evaluation mode of every product made with this key.  0 (default): the reference's dataflow - each row * limb product is
  * inverse-transformed and rounded on its own (misc.rs:59-61), raw torus words bit-identical to the reference.  1: products

@@ -156,6 +156,7 @@ def lib():
     if hasattr(L, "fhe_tfhe_key_upload"):
         L.fhe_tfhe_key_upload.argtypes = [vp, C.POINTER(TfheParam), vp, vp, vp, C.POINTER(vp)]
         L.fhe_tfhe_key_free.argtypes = [vp, vp]
+        L.fhe_tfhe_keygen.argtypes = [vp, C.POINTER(TfheParam), C.c_double, C.c_double, u64, vp, vp, vp, vp, vp, C.POINTER(vp)]
         L.fhe_tfhe_key_free.restype = None
         L.fhe_tfhe_key_set_mode.argtypes = [vp, vp, C.c_int]
         L.fhe_tfhe_key_bytes.argtypes = [vp]

@@ -54,6 +54,22 @@ HD int64_t ks_ternary(uint64_t seed, uint32_t domain, uint64_t index) {
     const uint64_t u = ks_u64(seed, domain, index) >> 62;
     return u == 0 ? -1 : (u == 1 ? 1 : 0);
 }
+// Torus noise (distribution.rs:49-54 `tdg(sigma)`: the fractional part of a normal variate scaled by 2^64) without floating point:
+// an Irwin-Hall variate - the sum of twelve 32-bit uniforms, mean 6 * 2^32, standard deviation exactly 2^32 - scaled by
+// sigma_q = round(sigma * 2^64) / 2^32.  Approximately Gaussian (support +-6 sigma, like the cut of `dg`), integer-only and
+// therefore identical on host and device; needs sigma < 2^-8 so that the 128-bit product fits the shifts below.
+HD uint64_t ks_tgauss(uint64_t seed, uint32_t domain, uint64_t index, uint64_t sigma_q) {
+    uint64_t sum = 0;
+    for (int j = 0; j < 6; ++j) {
+        const uint64_t w = ks_u64(seed, domain, index * 8 + j);
+        sum += (w >> 32) + (w & 0xFFFFFFFFull);
+    }
+    const int64_t sc = (int64_t)sum - (6ll << 32);
+    const uint64_t mag = (uint64_t)(sc < 0 ? -sc : sc);
+    const uint64_t hi = mulhi_u64(mag, sigma_q), lo = mag * sigma_q;
+    const uint64_t e = (hi << 32) | (lo >> 32);
+    return sc < 0 ? (uint64_t)(0 - e) : e;
+}
 // binary secret (distribution.rs:6-8): 0 / 1 with probability 1/2
 HD int64_t ks_binary(uint64_t seed, uint32_t domain, uint64_t index) { return (int64_t)(ks_u64(seed, domain, index) >> 63); }
 
@@ -61,6 +77,8 @@ HD int64_t ks_binary(uint64_t seed, uint32_t domain, uint64_t index) { return (i
 enum : uint32_t { KS_CKKS_SK = 16, KS_CKKS_KEY0 = 17 };
 HD uint32_t ks_ckks_a(uint32_t key) { return KS_CKKS_KEY0 + 2 * key; }
 HD uint32_t ks_ckks_e(uint32_t key) { return KS_CKKS_KEY0 + 2 * key + 1; }
+// stream domains of the TFHE key generation
+enum : uint32_t { KS_TFHE_Z = 40, KS_TFHE_S = 41, KS_TFHE_BRK_A = 42, KS_TFHE_BRK_E = 43, KS_TFHE_KSK_A = 44, KS_TFHE_KSK_E = 45 };
 // stream domains of the FHEW key generation
 enum : uint32_t { KS_FHEW_Z = 1, KS_FHEW_S = 2, KS_FHEW_KSK_A = 3, KS_FHEW_KSK_E = 4, KS_FHEW_BRK_A = 5, KS_FHEW_BRK_E = 6, KS_FHEW_AK_A = 7, KS_FHEW_AK_E = 8 };
 

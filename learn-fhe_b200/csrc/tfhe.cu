@@ -14,9 +14,11 @@
 // error bound of c64.rs:186-208.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "ctx.cuh"
+#include "keygen_stream.cuh"
 #include "tfhe_core.cuh"
 #include "tfhe_fast.cuh"
 #include "tfhe_tables.hpp"
@@ -454,11 +456,23 @@ fhe_status fhe_fft64_negacyclic_mul_host(fhe_ctx* ctx, uint64_t* a, const uint64
     return FHE_OK;
 }
 
-fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uint64_t* brk, const uint64_t* ksk_a, const uint64_t* ksk_b,
-                               fhe_tfhe_key** out) {
+}  // extern "C"
+
+// column sums of the merged ksk [rows][ld], scaled by B/2 (the digit-offset correction of tlwe_key_switch_kernel)
+__global__ void tfhe_ksk_colsum_kernel(const uint64_t* __restrict__ ksk, size_t rows, uint32_t ld, uint32_t shift, uint64_t* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ld) return;
+    uint64_t s = 0;
+    for (size_t r = 0; r < rows; ++r) s += ksk[r * ld + j];
+    out[j] = s << shift;
+}
+// Key object from either the reference layout on the HOST (brk, ksk_a, ksk_b: fhe_tfhe_key_upload) or buffers already on the DEVICE
+// (d_brk_raw [polys][N] torus words in the same order, d_ksk_merged [(kN) d_ks][n+1]: fhe_tfhe_keygen; d_ksk_merged is adopted).
+static fhe_status tfhe_key_build(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uint64_t* brk, const uint64_t* ksk_a, const uint64_t* ksk_b,
+                                 uint64_t* d_brk_raw, uint64_t* d_ksk_merged, fhe_tfhe_key** out) {
     if (!ctx || !pp || !out) return FHE_EINVAL;
     *out = nullptr;
-    FHE_REQUIRE(ctx, brk && ksk_a && ksk_b, "null key pointer");
+    FHE_REQUIRE(ctx, (brk && ksk_a && ksk_b) || (d_brk_raw && d_ksk_merged), "null key pointer");
     FHE_REQUIRE(ctx, pp->log_big_n >= 1 && pp->log_big_n <= 12, "TFHE ring degree 2^%u out of range (2..4096)", pp->log_big_n);
     FHE_REQUIRE(ctx, pp->k >= 1 && pp->k <= 4, "GLWE dimension k must be in [1, 4]");
     FHE_REQUIRE(ctx, pp->n >= 1 && pp->n <= 65535, "TLWE dimension out of range");
@@ -482,11 +496,11 @@ fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uin
     fhe_status st = get_fft_tab(ctx, pp->log_big_n, &P.fft);
     // brk: [n][(k+1)d][(k+1)][N] torus words -> Fourier domain
     const size_t polys = (size_t)pp->n * (pp->k + 1) * pp->bs_d * (pp->k + 1);
-    uint64_t* d_tmp = nullptr;
-    if (st == FHE_OK && cudaMalloc((void**)&d_tmp, polys * n * 8) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "bsk staging alloc");
+    uint64_t* d_tmp = d_brk_raw;
+    if (st == FHE_OK && !d_tmp && cudaMalloc((void**)&d_tmp, polys * n * 8) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "bsk staging alloc");
     key->brk_bytes = polys * m * sizeof(Cx);
     if (st == FHE_OK && cudaMalloc(&key->d_brk, key->brk_bytes) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "bsk alloc");
-    if (st == FHE_OK && cudaMemcpyAsync(d_tmp, brk, polys * n * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    if (st == FHE_OK && brk && cudaMemcpyAsync(d_tmp, brk, polys * n * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         st = fail(ctx, FHE_ECUDA, "bsk upload");
     if (st == FHE_OK) {
         unsigned grid;
@@ -498,9 +512,21 @@ fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uin
     }
     if (st == FHE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, FHE_ECUDA, "bsk transform failed");
     if (st == FHE_OK) st = build_fast_key(ctx, key, d_tmp, polys);
-    if (d_tmp) cudaFree(d_tmp);
+    if (d_tmp && !d_brk_raw) cudaFree(d_tmp);
+    if (st == FHE_OK && d_ksk_merged) {  // already merged on the device: adopt, compute the correction sums there
+        const size_t rows = (size_t)pp->k * n * pp->ks_d, ld = pp->n + 1;
+        key->ksk_bytes = rows * ld * 8;
+        key->d_ksk = d_ksk_merged;
+        if (cudaMalloc(&key->d_ksk_colsum, ld * 8) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "ksk alloc");
+        if (st == FHE_OK) {
+            tfhe_ksk_colsum_kernel<<<(unsigned)((ld + 127) / 128), 128, 0, ctx->stream>>>((const uint64_t*)key->d_ksk, rows, (uint32_t)ld, pp->ks_log_b - 1,
+                                                                                          (uint64_t*)key->d_ksk_colsum);
+            st = after_launch(ctx, "tfhe_ksk_colsum_kernel");
+            if (st == FHE_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = fail(ctx, FHE_ECUDA, "ksk column sums failed");
+        }
+    }
     // ksk: [(kN) d_ks][n] + [(kN) d_ks] -> [(kN) d_ks][n+1]
-    if (st == FHE_OK) {
+    if (st == FHE_OK && !d_ksk_merged) {
         const size_t rows = (size_t)pp->k * n * pp->ks_d, ld = pp->n + 1;
         std::vector<uint64_t> h(rows * ld);
         for (size_t r = 0; r < rows; ++r) {
@@ -518,12 +544,145 @@ fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uin
             st = fail(ctx, FHE_ECUDA, "ksk upload failed");
     }
     if (st != FHE_OK) {
+        if (d_ksk_merged) key->d_ksk = nullptr;  // stays with the caller on failure
         fhe_tfhe_key_free(ctx, key);
         return st;
     }
     P.brk = (const Cx*)key->d_brk;
     *out = key;
     return FHE_OK;
+}
+
+// ---- key generation on the device (tfhe/bootstrapping.rs:59-76) ------------------------------------------------
+// masks of the TGGSW rows: A [rows][k][N] uniform torus words; Srep [rows][k][N] = the TGLWE secret polynomials repeated per row
+__global__ void __launch_bounds__(256) tfhe_kg_masks_kernel(uint64_t seed, uint32_t log_n, uint32_t k, unsigned long long rows, const int64_t* __restrict__ s,
+                                                            uint64_t* __restrict__ a, uint64_t* __restrict__ srep) {
+    const unsigned long long total = (rows * k) << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint32_t n = 1u << log_n;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        a[i] = ks_u64(seed, KS_TFHE_BRK_A, i);
+        srep[i] = (uint64_t)s[(((i >> log_n) % k) << log_n) + (i & (n - 1))];
+    }
+}
+// out [rows][(k+1)][N] in the upload order (a_0 .. a_{k-1}, b): b = sum_j (a_j s_j) + e (+ the plaintext z_i B^d at coefficient 0 of the
+// component the row's index selects, tggsw.rs:84-87)
+__global__ void __launch_bounds__(256) tfhe_kg_rows_kernel(uint64_t seed, uint64_t sigma_q, uint32_t log_n, uint32_t k, uint32_t d, uint32_t log_b,
+                                                           uint32_t rounding_bits, unsigned long long rows, const int64_t* __restrict__ z,
+                                                           const uint64_t* __restrict__ a, const uint64_t* __restrict__ as, uint64_t* __restrict__ out) {
+    const unsigned long long total = rows << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint32_t n = 1u << log_n, rows_per = (k + 1) * d;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const unsigned long long R = i >> log_n;
+        const uint32_t c = (uint32_t)(i & (n - 1)), r = (uint32_t)(R % rows_per), comp = r / d, dig = r % d;
+        const uint64_t pt = c == 0 ? (uint64_t)z[R / rows_per] << (rounding_bits + dig * log_b) : 0;
+        uint64_t b = ks_tgauss(seed, KS_TFHE_BRK_E, i, sigma_q);
+        for (uint32_t j = 0; j < k; ++j) {
+            const unsigned long long src = ((R * k + j) << log_n) + c;
+            b += as[src];
+            out[((R * (k + 1) + j) << log_n) + c] = a[src] + (j == comp ? pt : 0);
+        }
+        out[((R * (k + 1) + k) << log_n) + c] = b + (comp == k ? pt : 0);
+    }
+}
+// TLWE key-switching key (tlwe.rs:100-111, 122-132) in the merged layout [(kN) d_ks][n + 1]
+__global__ void __launch_bounds__(128) tfhe_kg_ksk_kernel(uint64_t seed, uint64_t sigma_q, uint32_t n_lwe, uint32_t kn, uint32_t d_ks, uint32_t log_b,
+                                                          uint32_t rounding_bits, const int64_t* __restrict__ z, const int64_t* __restrict__ s,
+                                                          uint64_t* __restrict__ ksk) {
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (unsigned long long)kn * d_ks;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t dig = (uint32_t)(idx / kn), i = (uint32_t)(idx % kn);
+        uint64_t* row = ksk + idx * (n_lwe + 1);
+        uint64_t dot = 0;
+        for (uint32_t j = 0; j < n_lwe; ++j) {
+            const uint64_t a = ks_u64(seed, KS_TFHE_KSK_A, idx * n_lwe + j);
+            row[j] = a;
+            dot += a * (uint64_t)z[j];
+        }
+        row[n_lwe] = dot + ks_tgauss(seed, KS_TFHE_KSK_E, idx, sigma_q) + ((uint64_t)(-s[i]) << (rounding_bits + dig * log_b));
+    }
+}
+
+extern "C" {
+
+fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uint64_t* brk, const uint64_t* ksk_a, const uint64_t* ksk_b,
+                               fhe_tfhe_key** out) {
+    if (!ctx || !pp || !out) return FHE_EINVAL;
+    *out = nullptr;
+    FHE_REQUIRE(ctx, brk && ksk_a && ksk_b, "null key pointer");
+    return tfhe_key_build(ctx, pp, brk, ksk_a, ksk_b, nullptr, nullptr, out);
+}
+
+fhe_status fhe_tfhe_keygen(fhe_ctx* ctx, const fhe_tfhe_param* pp, double tlwe_std, double tglwe_std, uint64_t seed, int64_t* z_out, int64_t* s_out,
+                           uint64_t* brk_out, uint64_t* ksk_a_out, uint64_t* ksk_b_out, fhe_tfhe_key** out) {
+    if (!ctx || !pp || !out) return FHE_EINVAL;
+    *out = nullptr;
+    FHE_REQUIRE(ctx, pp->log_big_n >= 1 && pp->log_big_n <= 12 && pp->k >= 1 && pp->k <= 4 && pp->n >= 1 && pp->n <= 65535, "TFHE parameters out of range");
+    FHE_REQUIRE(ctx, tlwe_std > 0 && tlwe_std < 0.00390625 && tglwe_std > 0 && tglwe_std < 0.00390625, "noise standard deviations must be in (0, 2^-8)");
+    FHE_REQUIRE(ctx, pp->bs_log_b * pp->bs_d <= 64 && pp->ks_log_b * pp->ks_d <= 64, "decomposor log_b * d <= 64");
+    const uint32_t log_n = pp->log_big_n, N = 1u << log_n, k = pp->k, kn = k * N;
+    const size_t rows = (size_t)pp->n * (k + 1) * pp->bs_d, ksk_rows = (size_t)kn * pp->ks_d, ld = pp->n + 1;
+    const uint64_t sq_tlwe = (uint64_t)llround(tlwe_std * 18446744073709551616.0), sq_tglwe = (uint64_t)llround(tglwe_std * 18446744073709551616.0);
+    const DecompT64 bsd = make_decomp_t64(pp->bs_log_b, pp->bs_d), ksd = make_decomp_t64(pp->ks_log_b, pp->ks_d);
+    std::vector<int64_t> z(pp->n), s(kn);
+    for (uint32_t i = 0; i < pp->n; ++i) z[i] = ks_binary(seed, KS_TFHE_Z, i);
+    for (uint32_t i = 0; i < kn; ++i) s[i] = ks_binary(seed, KS_TFHE_S, i);
+    int64_t *d_z = nullptr, *d_s = nullptr;
+    uint64_t *d_a = nullptr, *d_as = nullptr, *d_srep = nullptr, *d_raw = nullptr, *d_ksk = nullptr;
+    fhe_status st = FHE_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && st == FHE_OK) st = fail(ctx, FHE_ECUDA, "tfhe keygen %s: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaMalloc(&d_z, pp->n * 8), "alloc");
+    cu(cudaMalloc(&d_s, (size_t)kn * 8), "alloc");
+    cu(cudaMalloc(&d_a, rows * kn * 8), "alloc");
+    cu(cudaMalloc(&d_as, rows * kn * 8), "alloc");
+    cu(cudaMalloc(&d_srep, rows * kn * 8), "alloc");
+    cu(cudaMalloc(&d_raw, rows * (k + 1) * N * 8), "alloc");
+    cu(cudaMalloc(&d_ksk, ksk_rows * ld * 8), "alloc");
+    if (st == FHE_OK) {
+        cu(cudaMemcpyAsync(d_z, z.data(), pp->n * 8, cudaMemcpyHostToDevice, ctx->stream), "copy");
+        cu(cudaMemcpyAsync(d_s, s.data(), (size_t)kn * 8, cudaMemcpyHostToDevice, ctx->stream), "copy");
+    }
+    auto grid = [&](unsigned long long total) { return (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)ctx->sm_count * 16); };
+    if (st == FHE_OK) {
+        tfhe_kg_masks_kernel<<<grid((unsigned long long)rows * kn), 256, 0, ctx->stream>>>(seed, log_n, k, rows, d_s, d_a, d_srep);
+        st = after_launch(ctx, "tfhe_kg_masks_kernel");
+    }
+    cu(cudaMemcpyAsync(d_as, d_a, rows * kn * 8, cudaMemcpyDeviceToDevice, ctx->stream), "copy");
+    // a_j * s_j: the reference's own f64 FFT product (`&a * sk`, tglwe.rs:97-100 -> ring/fft/c64.rs), bit-identical kernel
+    if (st == FHE_OK) st = fhe_fft64_negacyclic_mul(ctx, log_n, rows * k, d_as, d_srep);
+    if (st == FHE_OK) {
+        tfhe_kg_rows_kernel<<<grid((unsigned long long)rows << log_n), 256, 0, ctx->stream>>>(seed, sq_tglwe, log_n, k, pp->bs_d, pp->bs_log_b, bsd.rounding_bits,
+                                                                                              rows, d_z, d_a, d_as, d_raw);
+        st = after_launch(ctx, "tfhe_kg_rows_kernel");
+    }
+    if (st == FHE_OK) {
+        tfhe_kg_ksk_kernel<<<(unsigned)std::min<size_t>((ksk_rows + 127) / 128, (size_t)ctx->sm_count * 16), 128, 0, ctx->stream>>>(
+            seed, sq_tlwe, pp->n, kn, pp->ks_d, pp->ks_log_b, ksd.rounding_bits, d_z, d_s, d_ksk);
+        st = after_launch(ctx, "tfhe_kg_ksk_kernel");
+    }
+    if (st == FHE_OK) cu(cudaStreamSynchronize(ctx->stream), "sync");
+    if (st == FHE_OK && brk_out) cu(cudaMemcpy(brk_out, d_raw, rows * (k + 1) * N * 8, cudaMemcpyDeviceToHost), "export");
+    if (st == FHE_OK && (ksk_a_out || ksk_b_out)) {
+        std::vector<uint64_t> h(ksk_rows * ld);
+        cu(cudaMemcpy(h.data(), d_ksk, h.size() * 8, cudaMemcpyDeviceToHost), "export");
+        for (size_t r = 0; r < ksk_rows; ++r) {
+            if (ksk_a_out) memcpy(ksk_a_out + r * pp->n, h.data() + r * ld, (size_t)pp->n * 8);
+            if (ksk_b_out) ksk_b_out[r] = h[r * ld + pp->n];
+        }
+    }
+    if (st == FHE_OK) {
+        st = tfhe_key_build(ctx, pp, nullptr, nullptr, nullptr, d_raw, d_ksk, out);
+        if (st == FHE_OK) d_ksk = nullptr;  // adopted by the key
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : {(void*)d_z, (void*)d_s, (void*)d_a, (void*)d_as, (void*)d_srep, (void*)d_raw, (void*)d_ksk})
+        if (p) cudaFree(p);
+    if (st == FHE_OK) {
+        if (z_out) std::copy(z.begin(), z.end(), z_out);
+        if (s_out) std::copy(s.begin(), s.end(), s_out);
+    }
+    return st;
 }
 
 void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key) {

@@ -41,6 +41,23 @@ class BootstrappingKey:
         ctx.call("fhe_tfhe_key_upload", C.byref(param), hptr(brk), hptr(ksk_a), hptr(ksk_b), C.byref(h))
         self.h = h
 
+    @classmethod
+    def key_gen(cls, ctx, param, tlwe_std, tglwe_std, seed, export=False):
+        """Bootstrapping::key_gen (tfhe/bootstrapping.rs:59-76) on the device from the counter stream of `seed`: returns
+        (key, z [n], s [kN]) and, with export=True, the key in the upload layout (brk, ksk_a, ksk_b) too."""
+        kn = param.k * param.big_n
+        z, s = np.zeros(param.n, dtype=np.int64), np.zeros(kn, dtype=np.int64)
+        ex = None
+        if export:
+            ex = dict(brk=np.zeros((param.n, (param.k + 1) * param.bs_d, param.k + 1, param.big_n), dtype=np.uint64),
+                      ksk_a=np.zeros((kn * param.ks_d, param.n), dtype=np.uint64), ksk_b=np.zeros(kn * param.ks_d, dtype=np.uint64))
+        P = lambda k: hptr(ex[k]) if ex else None
+        h = C.c_void_p()
+        ctx.call("fhe_tfhe_keygen", C.byref(param), tlwe_std, tglwe_std, seed, hptr(z), hptr(s), P("brk"), P("ksk_a"), P("ksk_b"), C.byref(h))
+        self = cls.__new__(cls)
+        self.ctx, self.param, self.h = ctx, param, h
+        return (self, z, s, ex) if export else (self, z, s)
+
     def free(self):
         if getattr(self, "h", None):
             self.ctx.L.fhe_tfhe_key_free(self.ctx.h, self.h)

@@ -120,6 +120,8 @@ def lib():
         L.orc_tfhe_keygen.restype = C.c_void_p
         L.orc_rgsw_internal_product.argtypes = [C.c_uint64, C.c_uint, C.c_uint, C.c_uint, u64p, u64p, u64p]
         L.orc_tfhe_key_import.restype = C.c_void_p
+        L.orc_tfhe_keygen_ctr.restype = C.c_void_p
+        L.orc_tfhe_keygen_ctr.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_tfhe_key_import.argtypes = [C.c_void_p, u64p, u64p, u64p]
         L.orc_ckks_key_import.restype = C.c_void_p
         L.orc_ckks_keygen_ctr.restype = C.c_void_p
@@ -470,6 +472,11 @@ class TfheKey:
         self.h = _handle if _handle is not None else lib().orc_tfhe_keygen(C.byref(param), seed)
         if not self.h:
             _ck(-1)
+
+    @classmethod
+    def ctr(cls, param, seed):
+        """Key generation fed by the counter stream of the device keygen (oracle/orc_keygen.hpp): the checker of fhe_tfhe_keygen."""
+        return cls(param, seed, _handle=lib().orc_tfhe_keygen_ctr(C.byref(param), seed))
 
     @classmethod
     def from_arrays(cls, param, brk, ksk_a, ksk_b):

@@ -547,6 +547,14 @@ void* orc_tfhe_key_import(const orc_tfhe_param_c* c, const u64* brk, const u64* 
         return nullptr;
     }
 }
+void* orc_tfhe_keygen_ctr(const orc_tfhe_param_c* c, u64 seed) {
+    try {
+        return new TfheKey(tfhe_key_gen_ctr(to_tparam(*c), seed));
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 void orc_tfhe_key_free(void* h) { delete (TfheKey*)h; }
 // export: brk [n][(k+1)*d][(k+1) polys: a_0..a_{k-1}, b][N];  ksk_a [(kN)*d_ks][n], ksk_b [(kN)*d_ks]; z [n]; s [kN]
 int orc_tfhe_key_export(void* h, u64* brk, u64* ksk_a, u64* ksk_b, int64_t* z, int64_t* s) {

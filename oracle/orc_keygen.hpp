@@ -8,6 +8,7 @@
 #include "../learn-fhe_b200/csrc/keygen_stream.cuh"
 #include "orc_ckks.hpp"
 #include "orc_fhew.hpp"
+#include "orc_tfhe.hpp"
 
 namespace orc {
 
@@ -116,6 +117,60 @@ static inline CkksKey ckks_key_gen_ctr(const CkksParam& P, u64 seed, const std::
     K.rlk = ckks_ksk_gen_ctr(P, K.sk, small_negacyclic_mul(P.qs[0], K.sk, K.sk), seed, 0);
     for (size_t i = 0; i < auto_ts.size(); ++i)
         K.autk.push_back({auto_ts[i], ckks_ksk_gen_ctr(P, K.sk, automorphism_i64(K.sk, auto_ts[i]), seed, (uint32_t)(1 + i))});
+    return K;
+}
+
+// tfhe/bootstrapping.rs:59-76 key_gen (tlwe.rs:96-111, 122-132; tglwe.rs:92-103; tggsw.rs:73-89) as tfhe_key_gen states it, fed by
+// the counter stream of fhe_tfhe_keygen; the torus noise is ks_tgauss (integer-only, see keygen_stream.cuh) with
+// sigma_q = round(sigma * 2^64)
+static inline TfheKey tfhe_key_gen_ctr(const TfheParam& P, u64 seed) {
+    using namespace fhe;
+    TfheKey K;
+    K.param = P;
+    const size_t N = P.big_n, kn = (size_t)P.k * N;
+    const u64 sq_tlwe = (u64)std::llround(P.tlwe_std * 18446744073709551616.0), sq_tglwe = (u64)std::llround(P.tglwe_std * 18446744073709551616.0);
+    K.z.resize(P.n);
+    for (size_t i = 0; i < P.n; ++i) K.z[i] = ks_binary(seed, KS_TFHE_Z, i);
+    K.s.resize(kn);
+    for (size_t i = 0; i < kn; ++i) K.s[i] = ks_binary(seed, KS_TFHE_S, i);
+    DecomposorT64 dec = P.bs_dec();
+    const size_t rows_per = (size_t)(P.k + 1) * dec.d;
+    for (unsigned i = 0; i < P.n; ++i) {
+        std::vector<TglweCt> rows;
+        for (size_t r = 0; r < rows_per; ++r) {  // TGLWE encryption of zero (tglwe.rs:92-103)
+            const u64 R = (u64)i * rows_per + r;
+            TglweCt ct;
+            ct.b.assign(N, 0);
+            for (unsigned j = 0; j < P.k; ++j) {
+                Vec a(N);
+                for (size_t c = 0; c < N; ++c) a[c] = ks_u64(seed, KS_TFHE_BRK_A, (R * P.k + j) * N + c);
+                Vec as = rt_mul(a, rt_from_i64(K.s.data() + (size_t)j * N, N));
+                for (size_t c = 0; c < N; ++c) ct.b[c] += as[c];
+                ct.a.push_back(std::move(a));
+            }
+            for (size_t c = 0; c < N; ++c) ct.b[c] += ks_tgauss(seed, KS_TFHE_BRK_E, R * N + c, sq_tglwe);
+            rows.push_back(std::move(ct));
+        }
+        const u64 zi = (u64)K.z[i];  // plaintext: the constant polynomial z_i (tggsw.rs:84-87)
+        for (unsigned j = 0; j < P.k; ++j)
+            for (unsigned d = 0; d < dec.d; ++d) rows[j * dec.d + d].a[j][0] += zi * dec.base(d);
+        for (unsigned d = 0; d < dec.d; ++d) rows[P.k * dec.d + d].b[0] += zi * dec.base(d);
+        K.brk.push_back(std::move(rows));
+    }
+    DecomposorT64 kd = P.ks_dec();
+    for (unsigned d = 0; d < kd.d; ++d)
+        for (size_t i = 0; i < kn; ++i) {  // tlwe.rs:100-111: pt = power_up(-s).flatten(), encrypted under z
+            const u64 idx = (u64)d * kn + i;
+            TlweCt ct;
+            ct.a.resize(P.n);
+            u64 dot = 0;
+            for (size_t j = 0; j < P.n; ++j) {
+                ct.a[j] = ks_u64(seed, KS_TFHE_KSK_A, idx * P.n + j);
+                dot += ct.a[j] * (u64)K.z[j];
+            }
+            ct.b = dot + ks_tgauss(seed, KS_TFHE_KSK_E, idx, sq_tlwe) + (u64)(-K.s[i]) * kd.base(d);
+            K.ksk.push_back(std::move(ct));
+        }
     return K;
 }
 

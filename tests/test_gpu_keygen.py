@@ -94,3 +94,30 @@ def test_ckks_device_keygen_equals_host_keygen_on_the_same_stream(pkg, ctx, orc,
     for k in [rlk, again] + autk:
         k.free()
     P.free()
+
+
+@pytest.mark.parametrize("n,big_n,k,bs,ks", [(6, 64, 2, (8, 3), (4, 5)), (12, 512, 1, (10, 2), (4, 5)), (16, 2048, 1, (23, 1), (4, 5))])
+def test_tfhe_device_keygen_equals_host_keygen_on_the_same_stream(pkg, ctx, orc, n, big_n, k, bs, ks):
+    """fhe_tfhe_keygen (tfhe/bootstrapping.rs:59-76 on the GPU) == oracle/orc_keygen.hpp on the same counter stream: secrets, every
+    TGGSW row (the mask-secret products are the reference's f64 FFT products, bit-identical) and the TLWE key-switching key
+    word for word; programmable bootstraps under the device key equal the oracle's under the same key and decrypt."""
+    from learn_fhe_b200 import tfhe
+    P = orc.tfhe_testing_param()
+    P.n, P.big_n, P.k, P.bs_log_b, P.bs_d, P.ks_log_b, P.ks_d = n, big_n, k, bs[0], bs[1], ks[0], ks[1]
+    param = pkg.TfheParam(log_p=P.log_p, padding=P.padding, n=n, ks_log_b=ks[0], ks_d=ks[1], log_big_n=big_n.bit_length() - 1, k=k, bs_log_b=bs[0],
+                          bs_d=bs[1])
+    seed = 0x5EED0900 + n
+    bk, z, s, ex = tfhe.BootstrappingKey.key_gen(ctx, param, P.tlwe_std, P.tglwe_std, seed, export=True)
+    K = orc.TfheKey.ctr(P, seed)
+    ref = K.export()
+    assert (z == ref["z"]).all() and (s == ref["s"]).all()
+    for key in ("brk", "ksk_a", "ksk_b"):
+        assert (ex[key] == ref[key]).all(), key
+    msgs = np.arange(8, dtype=np.uint64) % np.uint64(1 << P.log_p)
+    cts = K.encrypt(msgs, 4)
+    v = K.lut_poly(np.arange(1 << P.log_p, dtype=np.uint64))
+    got = tfhe.Bootstrapping.bootstrap(bk, tfhe.encode_lut(param, v), cts)
+    assert (got == K.bootstrap(v, cts, threads=4)).all()
+    if big_n >= 512:  # the tiny ring has no noise margin for a look-up
+        assert (K.decrypt(got)[0] == msgs).all()
+    bk.free()
