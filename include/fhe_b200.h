@@ -64,6 +64,9 @@ fhe_status fhe_prof_end(fhe_ctx* ctx, char* json_buf, size_t cap);
 fhe_status fhe_diag_int32_peak(fhe_ctx* ctx, double* imad_tops, double* imad_hi_tops, double* imad_wide_tops);
 /* measured FP64 pipe rates (10^12 thread-instructions per second): DADD, DMUL, DFMA - the denominators of the TFHE roofline */
 fhe_status fhe_diag_fp64_peak(fhe_ctx* ctx, double* dadd_tops, double* dmul_tops, double* dfma_tops);
+/* measured rate (10^12 butterflies per second) of the u32 lazy radix-16 register pass with the Shoup quotient formed by IMAD.HI on
+ * the multiply pipe and by one DFMA (rounded down) on the FP64 pipe; *same_out = 1 when both variants produced identical words */
+fhe_status fhe_diag_butterfly_rate(fhe_ctx* ctx, double* imad_hi_tbf, double* dfma_tbf, int* same_out);
 
 fhe_status fhe_malloc(fhe_ctx* ctx, size_t bytes, void** d_ptr);
 fhe_status fhe_free(fhe_ctx* ctx, void* d_ptr);

@@ -98,6 +98,7 @@ def lib():
     L.fhe_two_adic_primes.argtypes = [ui, ui, sz, vp]
     L.fhe_diag_int32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.fhe_diag_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.fhe_diag_butterfly_rate.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.fhe_keys_broadcast.argtypes = [vp, vp, C.c_int, vp, sz]
     L.fhe_fhew_key_bytes.argtypes = [vp]
     L.fhe_fhew_key_bytes.restype = sz
@@ -260,6 +261,12 @@ class Context:
             self.ck(self.L.fhe_diag_fp64_peak(self.h, C.byref(a), C.byref(b), C.byref(c)))
             self._fp64_peak = {"dadd": a.value, "dmul": b.value, "dfma": c.value}
         return dict(self._fp64_peak)
+
+    def butterfly_rate(self):
+        """u32 radix-16 register pass, 10^12 butterflies/s: Shoup quotient by IMAD.HI vs by DFMA (FP64 pipe); `same` = identical words."""
+        a, b, c = C.c_double(), C.c_double(), C.c_int()
+        self.ck(self.L.fhe_diag_butterfly_rate(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"imad_hi": a.value, "dfma": b.value, "same": bool(c.value)}
 
     @property
     def launches(self):

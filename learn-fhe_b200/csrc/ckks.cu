@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(256) rns_copy_limbs_kernel(int log_n, unsigned
         out[b * out_limbs * n + r] = in[b * in_limbs * n + r];
     }
 }
-// rescale_k: in [B][l+k][n] (+ pre [B][l+k][n]) -> out [B][l][n] (+ post [B][l][n]; if post_even_only only for even b)
+// rescale_k: in [B][l+k][n] -> out [B][l][n] (+ post [B][l][n]; if post_even_only only for even b)
 __global__ void __launch_bounds__(256, 3) rns_rescale_kernel(const __grid_constant__ RescaleTabV R, int log_n, unsigned long long batch, const uint64_t* __restrict__ in,
-                                                          const uint64_t* __restrict__ pre, const uint64_t* __restrict__ post, int post_even_only,
+                                                          const uint64_t* __restrict__ post, int post_even_only,
                                                           uint64_t* __restrict__ out) {
     const unsigned long long total = batch << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
     const size_t n = (size_t)1 << log_n;
@@ -116,11 +116,7 @@ __global__ void __launch_bounds__(256, 3) rns_rescale_kernel(const __grid_consta
         const unsigned long long b = idx >> log_n;
         const size_t c = (size_t)(idx & (n - 1));
         const size_t ibase = b * (size_t)(l + k) * n + c, obase = b * (size_t)l * n + c;
-        auto load = [&](int i) {
-            uint64_t v = in[ibase + (size_t)i * n];
-            if (pre) v = R.m_all[i].add(v, pre[ibase + (size_t)i * n]);
-            return v;
-        };
+        auto load = [&](int i) { return in[ibase + (size_t)i * n]; };
         rns_rescale_coeff(R, load, [&](int i, uint64_t v) {
             if (post && (!post_even_only || (b & 1ull) == 0)) v = R.m_all[i].add(v, post[obase + (size_t)i * n]);
             out[obase + (size_t)i * n] = v;
@@ -128,52 +124,80 @@ __global__ void __launch_bounds__(256, 3) rns_rescale_kernel(const __grid_consta
     }
 }
 
+// Row-wise elementwise kernels: blockIdx.y walks the rows (one limb of one polynomial: the modulus and every base offset are uniform,
+// so no per-element division), blockIdx.x / threadIdx.x walk the row in coefficient pairs (16-byte accesses).
+static constexpr int CKKS_ROW_THREADS = 256;
+struct U64x2 {
+    uint64_t x, y;
+};
+DEV U64x2 ld2(const uint64_t* p) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    return U64x2{v.x, v.y};
+}
+DEV void st2(uint64_t* p, uint64_t x, uint64_t y) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(x, y); }
+static dim3 row_grid(fhe_ctx* ctx, unsigned log_n, unsigned long long rows) {
+    const unsigned long long pairs = ((unsigned long long)1 << log_n) / 2;
+    const unsigned gx = (unsigned)std::max<unsigned long long>(1, pairs / (CKKS_ROW_THREADS * 4));  // ~4 pairs per thread and row
+    const unsigned long long want = std::max<unsigned long long>(1, (unsigned long long)ctx->sm_count * 16 / gx);
+    return dim3(gx, (unsigned)std::min<unsigned long long>(std::min<unsigned long long>(rows, want), 65535), 1);
+}
+
 // tensor product in the evaluation domain: e0, e1 [C][2 (b,a)][l][n] -> d01 [C][2 (d0,d1)][l][n], d2 [C][l][n]  (ckks.rs:262-266)
-__global__ void __launch_bounds__(256) ckks_tensor_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long count,
-                                                          const uint64_t* __restrict__ e0, const uint64_t* __restrict__ e1,
-                                                          uint64_t* __restrict__ d01, uint64_t* __restrict__ d2) {
+__global__ void __launch_bounds__(CKKS_ROW_THREADS) ckks_tensor_kernel(const Mod64* __restrict__ mods, int l, int log_n, unsigned long long count,
+                                                                       const uint64_t* __restrict__ e0, const uint64_t* __restrict__ e1,
+                                                                       uint64_t* __restrict__ d01, uint64_t* __restrict__ d2) {
     const size_t n = (size_t)1 << log_n, ln = (size_t)l * n;
-    const unsigned long long total = count * ln, stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const unsigned long long c = idx / ln;
-        const size_t r = (size_t)(idx - c * ln);
-        const Mod64 m = mods[r >> log_n];
-        const size_t o = c * 2 * ln + r;
-        const uint64_t b0 = e0[o], a0 = e0[o + ln], b1 = e1[o], a1 = e1[o + ln];
-        d01[o] = m.mul(b0, b1);
-        d01[o + ln] = m.add(m.mul(b0, a1), m.mul(a0, b1));
-        d2[c * ln + r] = m.mul(a0, a1);
+    const uint32_t rows = (uint32_t)(count * l);
+    for (uint32_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const uint32_t c = row / (uint32_t)l, j = row - c * (uint32_t)l;
+        const Mod64 m = mods[j];
+        const size_t o = (size_t)c * 2 * ln + (size_t)j * n;
+        const uint64_t *pb0 = e0 + o, *pa0 = pb0 + ln, *pb1 = e1 + o, *pa1 = pb1 + ln;
+        uint64_t *q0 = d01 + o, *q1 = q0 + ln, *q2 = d2 + (size_t)c * ln + (size_t)j * n;
+        for (size_t x = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); x < n; x += 2 * (size_t)gridDim.x * blockDim.x) {
+            const U64x2 b0 = ld2(pb0 + x), a0 = ld2(pa0 + x), b1 = ld2(pb1 + x), a1 = ld2(pa1 + x);
+            st2(q0 + x, m.mul(b0.x, b1.x), m.mul(b0.y, b1.y));
+            st2(q1 + x, m.add(m.mul(b0.x, a1.x), m.mul(a0.x, b1.x)), m.add(m.mul(b0.y, a1.y), m.mul(a0.y, b1.y)));
+            st2(q2 + x, m.mul(a0.x, a1.x), m.mul(a0.y, a1.y));
+        }
     }
 }
 // key products: x = [xq (l limbs, eval) ; xp (L limbs, eval)] against ksk [2 (b,a)][2L][n] eval -> out [C][2][l+L][n]  (ckks.rs:289-291)
-__global__ void __launch_bounds__(256) ckks_keymul_kernel(const Mod64* __restrict__ mods /* [2L]: qs then ps */, int l, int big_l, int log_n,
-                                                          unsigned long long count, const uint64_t* __restrict__ xq, const uint64_t* __restrict__ xp,
-                                                          const uint64_t* __restrict__ ksk, const uint64_t* __restrict__ addend /* [C][2][l][n] or null */,
-                                                          const uint64_t* __restrict__ pmod /* [L]: P mod q_j */, uint64_t* __restrict__ out) {
+__global__ void __launch_bounds__(CKKS_ROW_THREADS) ckks_keymul_kernel(const Mod64* __restrict__ mods /* [2L]: qs then ps */, int l, int big_l,
+                                                                       int log_n, unsigned long long count, const uint64_t* __restrict__ xq,
+                                                                       const uint64_t* __restrict__ xp, const uint64_t* __restrict__ ksk,
+                                                                       const uint64_t* __restrict__ addend /* [C][2][l][n] or null */,
+                                                                       const uint64_t* __restrict__ pmod /* [L]: P mod q_j */,
+                                                                       uint64_t* __restrict__ out) {
     const size_t n = (size_t)1 << log_n;
-    const int le = l + big_l;
-    const unsigned long long total = count * le * n, stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const unsigned long long c = idx / ((unsigned long long)le * n);
-        const size_t r = (size_t)(idx - c * le * n);
-        const int j = (int)(r >> log_n);
-        const size_t x = r & (n - 1);
-        const int kl = j < l ? j : big_l + (j - l);
+    const uint32_t le = (uint32_t)(l + big_l), rows = (uint32_t)(count * le);
+    for (uint32_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const uint32_t c = row / le, j = row - c * le;
+        const uint32_t kl = j < (uint32_t)l ? j : (uint32_t)big_l + (j - (uint32_t)l);
         const Mod64 m = mods[kl];
-        const uint64_t v = j < l ? xq[(c * l + j) * n + x] : xp[(c * big_l + (j - l)) * n + x];
-        const size_t o = c * 2 * le * n + r;
-        uint64_t kb = m.mul(ksk[(size_t)kl * n + x], v);
-        uint64_t ka = m.mul(ksk[((size_t)2 * big_l + kl) * n + x], v);
-        if (addend && j < l) {
-            // Ckks::mul adds (d0, d1) to the relinearised pair after the division by P (ckks.rs:266, rns.rs:127-132).  On the
-            // kept limbs rescale_k is (x_i + P/2 - ext_i) * P^-1, so adding P * d_i to x_i here - in the evaluation domain, before
-            // the inverse transform - yields exactly d_i + rescale_k(x)_i and saves the inverse transforms of d0 and d1.
-            const size_t a0 = (c * 2 * l + j) * n + x;
-            kb = m.add(kb, m.mul(pmod[j], addend[a0]));
-            ka = m.add(ka, m.mul(pmod[j], addend[a0 + (size_t)l * n]));
+        const uint64_t* pv = j < (uint32_t)l ? xq + ((size_t)c * l + j) * n : xp + ((size_t)c * big_l + (j - l)) * n;
+        const uint64_t *pkb = ksk + (size_t)kl * n, *pka = ksk + ((size_t)2 * big_l + kl) * n;
+        uint64_t *ob = out + ((size_t)c * 2 * le + j) * n, *oa = ob + (size_t)le * n;
+        // Ckks::mul adds (d0, d1) to the relinearised pair after the division by P (ckks.rs:266, rns.rs:127-132).  On the kept
+        // limbs rescale_k is (x_i + P/2 - ext_i) * P^-1, so adding P * d_i to x_i here - in the evaluation domain, before the
+        // inverse transform - yields exactly d_i + rescale_k(x)_i and saves the inverse transforms of d0 and d1.
+        const bool add = addend && j < (uint32_t)l;
+        const uint64_t* pd0 = add ? addend + ((size_t)c * 2 * l + j) * n : nullptr;
+        const uint64_t* pd1 = add ? pd0 + (size_t)l * n : nullptr;
+        const uint64_t pm = add ? pmod[j] : 0;
+        for (size_t x = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); x < n; x += 2 * (size_t)gridDim.x * blockDim.x) {
+            const U64x2 v = ld2(pv + x), wb = ld2(pkb + x), wa = ld2(pka + x);
+            uint64_t b0 = m.mul(wb.x, v.x), b1 = m.mul(wb.y, v.y), a0 = m.mul(wa.x, v.x), a1 = m.mul(wa.y, v.y);
+            if (add) {
+                const U64x2 d0 = ld2(pd0 + x), d1 = ld2(pd1 + x);
+                b0 = m.add(b0, m.mul(pm, d0.x));
+                b1 = m.add(b1, m.mul(pm, d0.y));
+                a0 = m.add(a0, m.mul(pm, d1.x));
+                a1 = m.add(a1, m.mul(pm, d1.y));
+            }
+            st2(ob + x, b0, b1);
+            st2(oa + x, a0, a1);
         }
-        out[o] = kb;
-        out[o + (size_t)le * n] = ka;
     }
 }
 // plaintext x ciphertext in the evaluation domain: e [C][2][l][n] *= pe [1 or C][l][n] (limb-wise)   (ckks.rs:250-253)
@@ -313,13 +337,13 @@ static fhe_status run_extend(fhe_ctx* ctx, const std::vector<uint64_t>& qs, cons
     return after_launch(ctx, "rns_extend_kernel");
 }
 static fhe_status run_rescale(fhe_ctx* ctx, const std::vector<uint64_t>& all, size_t k, unsigned log_n, size_t batch, const uint64_t* d_in,
-                              const uint64_t* d_pre, const uint64_t* d_post, bool post_even_only, uint64_t* d_out) {
+                              const uint64_t* d_post, bool post_even_only, uint64_t* d_out) {
     FHE_REQUIRE(ctx, k >= 1 && k < all.size(), "rescale_k needs 0 < k < number of limbs (rns.rs:104)");
     FHE_REQUIRE(ctx, k <= (size_t)RNS_MAXL, "rescale_k supports dropping at most %d limbs", RNS_MAXL);
     const RescaleOwned* t;
     FHE_CHECK(get_rescale(ctx, all, k, &t));
-    rns_rescale_kernel<<<stream_grid(ctx, (unsigned long long)batch << log_n), 256, 0, ctx->stream>>>(t->tab, (int)log_n, batch, d_in, d_pre,
-                                                                                                     d_post, post_even_only ? 1 : 0, d_out);
+    rns_rescale_kernel<<<stream_grid(ctx, (unsigned long long)batch << log_n), 256, 0, ctx->stream>>>(t->tab, (int)log_n, batch, d_in, d_post,
+                                                                                                     post_even_only ? 1 : 0, d_out);
     return after_launch(ctx, "rns_rescale_kernel");
 }
 
@@ -376,11 +400,11 @@ static fhe_status key_switch_core(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks
     const std::vector<uint64_t> qs = level_qs(ck, l), qps = level_qps(ck, l);
     FHE_CHECK(run_extend(ctx, qs, ck->ps, log_n, count, a_coeff, (int)l, 0, xp, (int)L, 0));
     FHE_CHECK(launch_ntt_rns_u64(ctx, ck->ps.data(), L, log_n, count * L, xp, true));
-    ckks_keymul_kernel<<<stream_grid(ctx, (unsigned long long)count * (l + L) << log_n), 256, 0, ctx->stream>>>(
+    ckks_keymul_kernel<<<row_grid(ctx, log_n, (unsigned long long)count * (l + L)), CKKS_ROW_THREADS, 0, ctx->stream>>>(
         ck->d_mods, (int)l, (int)L, (int)log_n, count, a_eval, xp, ksk->d_eval, d01_eval, ck->d_pmod, kk);
     FHE_CHECK(after_launch(ctx, "ckks_keymul_kernel"));
     FHE_CHECK(launch_ntt_rns_u64(ctx, qps.data(), l + L, log_n, count * 2 * (l + L), kk, false));
-    return run_rescale(ctx, qps, L, log_n, count * 2, kk, nullptr, post, true, r);
+    return run_rescale(ctx, qps, L, log_n, count * 2, kk, post, true, r);
 }
 }  // namespace fhe
 
@@ -407,7 +431,7 @@ fhe_status fhe_rns_rescale_k(fhe_ctx* ctx, const uint64_t* qs, size_t nq, size_t
     FHE_REQUIRE(ctx, d_in && d_out && log_n <= 20, "bad arguments");
     std::vector<uint64_t> all(qs, qs + nq);
     FHE_CHECK(check_moduli(ctx, all));
-    return run_rescale(ctx, all, k, log_n, batch, d_in, nullptr, nullptr, false, d_out);
+    return run_rescale(ctx, all, k, log_n, batch, d_in, nullptr, false, d_out);
 }
 
 // ---- CKKS ----------------------------------------------------------------------------------------------------------------
@@ -673,13 +697,13 @@ fhe_status fhe_ckks_mul_relin_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, cons
         const uint64_t* in1 = d_ct1 + base * 2 * l * n;
         FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * 2 * l, in0, e0, true));
         FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * 2 * l, in1, e1, true));
-        ckks_tensor_kernel<<<stream_grid(ctx, (unsigned long long)c * l << log_n), 256, 0, ctx->stream>>>(ck->d_mods, (int)l, (int)log_n, c, e0, e1,
+        ckks_tensor_kernel<<<row_grid(ctx, log_n, (unsigned long long)c * l), CKKS_ROW_THREADS, 0, ctx->stream>>>(ck->d_mods, (int)l, (int)log_n, c, e0, e1,
                                                                                                          d01, d2e);
         FHE_CHECK(after_launch(ctx, "ckks_tensor_kernel"));
         FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * l, d2e, d2c, false));
         // relinearize(d2) with ct_b = 0, plus (d0, d1) folded in before the inverse transforms; then rescale (ckks.rs:266, 123-125)
         FHE_CHECK(key_switch_core(ctx, ck, rlk, l, c, d2c, d2e, xp, kk, nullptr, r, d01));
-        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, r, nullptr, nullptr, false, d_out + base * 2 * (l - 1) * n));
+        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, r, nullptr, false, d_out + base * 2 * (l - 1) * n));
     }
     return FHE_OK;
 }
@@ -769,7 +793,7 @@ fhe_status fhe_ckks_mul_plain_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, size
             ck->d_mods, (int)l, (int)log_n, c, pt_count == 1 ? 0 : 1, pe + (pt_count == 1 ? 0 : base * l * n), e, e);
         FHE_CHECK(after_launch(ctx, "ckks_ptmul_kernel"));
         FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, c * 2 * l, e, false));
-        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, e, nullptr, nullptr, false, d_out + base * 2 * (l - 1) * n));
+        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, e, nullptr, false, d_out + base * 2 * (l - 1) * n));
     }
     return FHE_OK;
 }
@@ -838,7 +862,7 @@ fhe_status fhe_ckks_mul_mat(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t
                                                                                                     rot + j * ct_in, prod);
             FHE_CHECK(after_launch(ctx, "ckks_ptmul_kernel"));
             FHE_CHECK(launch_ntt_rns_u64(ctx, qs.data(), l, log_n, count * 2 * l, prod, false));
-            FHE_CHECK(run_rescale(ctx, qs, 1, log_n, count * 2, prod, nullptr, nullptr, false, first ? inner : tmp));
+            FHE_CHECK(run_rescale(ctx, qs, 1, log_n, count * 2, prod, nullptr, false, first ? inner : tmp));
             if (!first) FHE_CHECK(add(inner, tmp, inner));
             first = false;
         }
@@ -860,7 +884,7 @@ fhe_status fhe_ckks_rescale(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t level, size_t
     if (count == 0) return FHE_OK;
     FHE_REQUIRE(ctx, d_ct && d_out, "null pointer");
     FHE_REQUIRE(ctx, level >= 2 && level <= ck->big_l, "level must be in [2, L]");
-    return run_rescale(ctx, level_qs(ck, level), 1, ck->log_n, count * 2, d_ct, nullptr, nullptr, false, d_out);
+    return run_rescale(ctx, level_qs(ck, level), 1, ck->log_n, count * 2, d_ct, nullptr, false, d_out);
 }
 
 }  // extern "C"

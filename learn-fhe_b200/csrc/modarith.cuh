@@ -51,6 +51,30 @@ HD uint64_t mulhi_u64_approx(uint64_t a, uint64_t b) {
     // only the high words of the cross terms are needed: IMAD.HI (2 issue slots) instead of IMAD.WIDE (2.4)
     return (uint64_t)ah * bh + (uint64_t)mulhi_u32(al, bh) + (uint64_t)mulhi_u32(ah, bl);
 }
+// floor(wp * y / 2^32) on the FP64 pipe.  c = wp 2^-32 and K = 2^52 - wp 2^20 are exact doubles; with Y = 2^52 + y (y placed in the
+// low word of the double 2^52) the product-sum Y c + K equals y wp 2^-32 + 2^52 exactly, and one DFMA rounded towards minus
+// infinity lands on 2^52 + floor(y wp / 2^32): the low word of the result IS mulhi_u32(wp, y), for every y and wp.
+struct F64Quot {
+    double c, k;
+};
+HD F64Quot make_f64_quot(uint32_t wp) {
+    F64Quot f;
+#if defined(__CUDA_ARCH__)
+    f.c = __dadd_rn(__hiloint2double(0x41300000, (int)wp), -0x1p20);  // (2^20 + wp 2^-32) - 2^20
+    f.k = __fma_rn(f.c, -0x1p52, 0x1p52);
+#else
+    f.c = (double)wp * 0x1p-32;
+    f.k = 0x1p52 - (double)wp * 0x1p20;
+#endif
+    return f;
+}
+HD uint32_t mulhi_u32_f64(const F64Quot& f, uint32_t y) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(__fma_rd(__hiloint2double(0x43300000, (int)y), f.c, f.k));
+#else
+    return (uint32_t)(((uint64_t)(uint32_t)(f.c * 0x1p32) * y) >> 32);
+#endif
+}
 HD uint32_t umin_(uint32_t a, uint32_t b) { return a < b ? a : b; }
 // a + b for sums that cannot wrap (a + b < 2^32), forced onto the ALU pipe (VIADDMNMX).  ptxas otherwise places many
 // two-operand integer adds on the IMAD pipe as IMAD.IADD, and that pipe is the measured bottleneck of every modular kernel

@@ -88,9 +88,10 @@ HD double u64_to_f64(uint64_t v) {
 }
 
 // Rns::extend_bases for one coefficient (rns.rs:331-345): x[i] = residue mod q_i (i < nq) -> y[k] = residue mod p_k.
-// `emit(k, y)` receives the outputs.
-template <typename Tab, typename Emit>
-HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq valid */, Emit emit) {
+// `emit(k, y)` receives the outputs; `begin(k)` runs before the products of target k (rescale_k requests the kept limb there, so its
+// global-memory latency hides behind them).
+template <typename Tab, typename Emit, typename Begin>
+HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq valid */, Emit emit, Begin begin) {
     uint64_t v[RNS_MAXL];
     double acc = 0.0;
 #pragma unroll
@@ -105,6 +106,7 @@ HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq
     }
     const uint32_t u = (uint32_t)f64_round_half_away(acc);
     for (int k = 0; k < T.np; ++k) {
+        begin(k);
         const Mod64 m = T.mp[k];
         const uint64_t* qh = T.qhat_ps + (size_t)k * RNS_MAXL;
         uint64_t s = 0;
@@ -148,6 +150,11 @@ HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq
     }
 }
 
+template <typename Tab, typename Emit>
+HD void rns_extend_coeff(const Tab& T, const uint64_t* x, Emit emit) {
+    rns_extend_coeff(T, x, emit, [](int) {});
+}
+
 // rescale_k for one coefficient: x(i) reads limb i of the input (already including any pre-addend, canonical);
 // emit(i, y) receives the kept limbs before any post-addend.
 template <typename Tab, typename Load, typename Emit>
@@ -155,11 +162,6 @@ HD void rns_rescale_coeff(const Tab& R, Load x, Emit emit) {
     const int l = R.l, k = R.k;
     // round(): s_i = x_i + (P >> 1) mod q_i, for every limb (rns.rs:120-125)
     auto rounded = [&](int i) { return R.m_all[i].add(x(i), R.ph[i]); };
-    auto finish = [&](int i, uint64_t sub) {
-        const Mod64 m = R.m_all[i];
-        const uint64_t v = m.sub(rounded(i), sub);
-        emit(i, m.redq(m.shoup_lazy(v, R.pinv[i], R.pinv_sh[i])));  // div(): * P^-1 (rns.rs:127-132)
-    };
     if (k == 1) {
         const uint64_t vp = rounded(l);  // non-centred value of the dropped limb (rns.rs:109-111)
         // this path is bound by global-memory latency: issue every load before the first use (static register indices)
@@ -177,8 +179,17 @@ HD void rns_rescale_coeff(const Tab& R, Load x, Emit emit) {
         uint64_t xs[RNS_MAXL];
 #pragma unroll
         for (int j = 0; j < RNS_MAXL; ++j) xs[j] = j < k ? rounded(l + j) : 0;
-        // (loading the kept limbs up front and unrolling the target loop was measured: more registers, lower occupancy, slower)
-        rns_extend_coeff(R.ext, xs, [&](int i, uint64_t y) { finish(i, y); });
+        // (loading the kept limbs up front and unrolling the target loop was measured: more registers, lower occupancy, slower;
+        // one limb ahead of its use costs two registers)
+        uint64_t kept = 0;
+        rns_extend_coeff(
+            R.ext, xs,
+            [&](int i, uint64_t y) {
+                const Mod64 m = R.m_all[i];
+                const uint64_t v = m.sub(m.add(kept, R.ph[i]), y);
+                emit(i, m.redq(m.shoup_lazy(v, R.pinv[i], R.pinv_sh[i])));  // div(): * P^-1 (rns.rs:127-132)
+            },
+            [&](int i) { kept = x(i); });
     }
 }
 

@@ -161,6 +161,14 @@ __global__ void __launch_bounds__(TFHE_THREADS, 2) tfhe_blind_rotate_kernel(Tfhe
 
 // ---- bounded-error fast path (tfhe_fast.cuh) ------------------------------------------------------------------------------------------
 static constexpr int TFHE_FAST_THREADS = 128;
+// tuning knobs (A/B builds): CTAs per SM the fused kernel is compiled for (3: 168 registers; 2: 255) and the number of spectral
+// positions whose limb-0 key rows are requested before P2 (0: none)
+#ifndef TFHE_FAST_MINB
+#define TFHE_FAST_MINB 3
+#endif
+#ifndef TFHE_PRE
+#define TFHE_PRE 0
+#endif
 // key polynomial (step, r, o) [N] torus words -> forward spectrum in the coalesced P3 layout; one CTA per polynomial
 template <typename C>
 __global__ void __launch_bounds__(256) tfhe_fast_key_kernel(TfheFastDev P, unsigned long long polys, const uint64_t* __restrict__ src,
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(256) tfhe_fast_key_kernel(TfheFastDev P, unsig
 // blind_rotate + sample_extract(0) for k = 1: ct_in [count][n_lwe+1] -> out [count][N+1]; persistent CTA per ciphertext,
 // accumulator (2 N torus words) and the exchange buffer (2 d N/2 complex) resident in shared memory across all n CMUX steps
 template <typename C>
-__global__ void __launch_bounds__(TFHE_FAST_THREADS, 3) tfhe_blind_rotate_fast_kernel(TfheFastDev P, const uint64_t* __restrict__ lut,
+__global__ void __launch_bounds__(TFHE_FAST_THREADS, TFHE_FAST_MINB) tfhe_blind_rotate_fast_kernel(TfheFastDev P, const uint64_t* __restrict__ lut,
                                                                                    const uint64_t* __restrict__ ct_in, unsigned long long count,
                                                                                    uint64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,7 +217,30 @@ __global__ void __launch_bounds__(TFHE_FAST_THREADS, 3) tfhe_blind_rotate_fast_k
         for (uint32_t i = 0; i < P.n_lwe; ++i) {
             const uint32_t e = ex[i];
             if (e == 0) continue;  // rotate(0) - acc = 0: the external product of zero is exactly zero
-            tfhe_fast_cmux<C>(P, acc, X, i, e, run);
+            constexpr int NPRE = TFHE_PRE < (1 << C::R3) ? TFHE_PRE : (1 << C::R3);
+            if constexpr (NPRE > 0 && C::U1 == TFHE_FAST_THREADS && C::U2 == 2 * TFHE_FAST_THREADS && C::U3 == TFHE_FAST_THREADS &&
+                          C::U4 == 2 * TFHE_FAST_THREADS) {
+                // the five phases of tfhe_fast_cmux with one P1 / P3 / P5 unit and two P2 / P4 units per thread; limb 0's key rows are
+                // requested from L2 before P2
+                const uint32_t t = threadIdx.x;
+                const Cx* key = P.key + (size_t)i * C::KEY_STRIDE;
+                tfhe_fast_p1<C>(P, acc, X, t, e);
+                __syncthreads();
+                Cx kq[2 * NPRE];
+                tfhe_fast_p3_keys<C, 0, NPRE>(key, t, 0, kq);
+                tfhe_fast_mid<C, true>(P, X, t);
+                tfhe_fast_mid<C, true>(P, X, t + TFHE_FAST_THREADS);
+                __syncthreads();
+                tfhe_fast_p3<C, NPRE>(P, X, key, t, kq);
+                __syncthreads();
+                tfhe_fast_mid<C, false>(P, X, t);
+                tfhe_fast_mid<C, false>(P, X, t + TFHE_FAST_THREADS);
+                __syncthreads();
+                tfhe_fast_p5<C>(P, acc, X, t);
+                __syncthreads();
+            } else {
+                tfhe_fast_cmux<C>(P, acc, X, i, e, run);
+            }
         }
         uint64_t* o = out + ct * ((unsigned long long)N + 1);
         for (uint32_t x = threadIdx.x; x < N; x += TFHE_FAST_THREADS) o[x] = x == 0 ? acc[0] : (uint64_t)(0 - acc[N - x]);

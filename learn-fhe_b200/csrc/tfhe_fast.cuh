@@ -271,8 +271,19 @@ HD void tfhe_fast_mid(const TfheFastDev& P, Cx* __restrict__ X, uint32_t unit) {
     for (int i = 0; i < NE; ++i) f[p0 ^ swz_cx((uint32_t)i << L)] = x[i];
 }
 // ---- P3: last forward pass of every limb, multiply-accumulate with the key, first inverse pass ----------------------------------------
-template <typename C>
-HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restrict__ key, uint32_t g) {
+// key rows of limb r at the unit's spectral positions I0 .. I1-1: k[2 i + o]
+template <typename C, int I0 = 0, int I1 = (1 << C::R3)>
+HD void tfhe_fast_p3_keys(const Cx* __restrict__ key, uint32_t g, uint32_t r, Cx* k) {
+#pragma unroll
+    for (int i = I0; i < I1; ++i) {
+        k[2 * i] = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 0) * C::U3 + g));
+        k[2 * i + 1] = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 1) * C::U3 + g));
+    }
+}
+// NPRE > 0: kpre holds the rows of limb 0 at the unit's first NPRE spectral positions, requested by the kernel before P2 so that
+// their L2 latency hides behind that pass (r02 ncu: half of P3's stall samples are long_scoreboard on these loads)
+template <typename C, int NPRE = 0>
+HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restrict__ key, uint32_t g, const Cx* kpre) {
     constexpr int NE = 1 << C::R3;
     constexpr uint32_t G = C::U3;
     Cx o0[NE], o1[NE];
@@ -288,8 +299,14 @@ HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restr
         fast_fwd_regs<C::R3>(x, [&](int u, int top) { return ld_cx(P.fft.W3 + (size_t)((1 << u) - 1 + top) * G + g); });
 #pragma unroll
         for (int i = 0; i < NE; ++i) {
-            const Cx k0 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 0) * G + g));
-            const Cx k1 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 1) * G + g));
+            Cx k0, k1;
+            if (NPRE > 0 && i < NPRE && r == 0) {
+                k0 = kpre[2 * i];
+                k1 = kpre[2 * i + 1];
+            } else {
+                k0 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 0) * G + g));
+                k1 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 1) * G + g));
+            }
             o0[i] = Cx{f64_fma_rn(-x[i].im, k0.im, f64_fma_rn(x[i].re, k0.re, o0[i].re)), f64_fma_rn(x[i].im, k0.re, f64_fma_rn(x[i].re, k0.im, o0[i].im))};
             o1[i] = Cx{f64_fma_rn(-x[i].im, k1.im, f64_fma_rn(x[i].re, k1.re, o1[i].re)), f64_fma_rn(x[i].im, k1.re, f64_fma_rn(x[i].re, k1.im, o1[i].im))};
         }
@@ -340,7 +357,7 @@ HD void tfhe_fast_cmux(const TfheFastDev& P, uint64_t* acc, Cx* X, uint32_t step
     const Cx* key = P.key + (size_t)step * C::KEY_STRIDE;
     run(C::U1, [&](uint32_t u) { tfhe_fast_p1<C>(P, acc, X, u, e); });
     run(C::U2, [&](uint32_t u) { tfhe_fast_mid<C, true>(P, X, u); });
-    run(C::U3, [&](uint32_t u) { tfhe_fast_p3<C>(P, X, key, u); });
+    run(C::U3, [&](uint32_t u) { tfhe_fast_p3<C>(P, X, key, u, nullptr); });
     run(C::U4, [&](uint32_t u) { tfhe_fast_mid<C, false>(P, X, u); });
     run(C::U1, [&](uint32_t u) { tfhe_fast_p5<C>(P, acc, X, u); });
 }

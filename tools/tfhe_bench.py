@@ -31,6 +31,8 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+if "bf" in args:
+    print("u32 butterfly rate (T bf/s):", ctx.butterfly_rate())
 if "peaks" in args:
     print("fp64 peaks (T instr/s):", ctx.fp64_peak(), "int32:", ctx.int32_peak())
 if "tfhe" in args or not args:
