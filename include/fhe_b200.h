@@ -240,7 +240,10 @@ void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key);
  * 2: the fused bounded-error blind rotation (k = 1; N = 512, 1024, 2048): same digits and the same exact sums as mode 1, FMA
  * butterflies, twist merged into the forward twiddles, one rounding per output coefficient; each CMUX output is within
  * (k+1) d 2^(64 + log_b + log_n - 53) of the reference's, decryptions are identical (FHE_EUNSUPPORTED for other shapes).
- * The stand-alone external product / CMUX entry points evaluate modes 1 and 2 alike. */
+ * 3: mode 2 with the accumulator held as the top 32 bits of every torus word (each CMUX increment is a sum of f64 products of
+ * magnitude ~2^90 with nothing but rounding noise below 2^35 - in the reference's own dataflow too - so the extra rounding of
+ * at most 2^31 per step is invisible next to it; the low halves of the output words are zero).
+ * The stand-alone external product / CMUX entry points evaluate modes 1, 2 and 3 alike. */
 fhe_status fhe_tfhe_key_set_mode(fhe_ctx* ctx, fhe_tfhe_key* key, int mode);
 /* device bytes held by the key (Fourier-domain bsk + ksk) and its one-time NCCL broadcast from `root` */
 size_t fhe_tfhe_key_bytes(const fhe_tfhe_key* key);

@@ -123,6 +123,20 @@ __global__ void __launch_bounds__(256, 3) rns_rescale_kernel(const __grid_consta
         });
     }
 }
+// rescale_k(k) then rescale_k(1) in one pass: in [B][l+k][n] -> out [B][l-1][n]   (Ckks::mul: key_switch's division by P followed by
+// rescale, ckks.rs:266 + 123-125)
+__global__ void __launch_bounds__(256, 3) rns_rescale2_kernel(const __grid_constant__ RescaleTabV R, const __grid_constant__ Rescale1TabV R1, int log_n,
+                                                           unsigned long long batch, const uint64_t* __restrict__ in, uint64_t* __restrict__ out) {
+    const unsigned long long total = batch << log_n, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const size_t n = (size_t)1 << log_n;
+    const int l = R.l, k = R.k;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const unsigned long long b = idx >> log_n;
+        const size_t c = (size_t)(idx & (n - 1));
+        const size_t ibase = b * (size_t)(l + k) * n + c, obase = b * (size_t)(l - 1) * n + c;
+        rns_rescale2_coeff(R, R1, [&](int i) { return in[ibase + (size_t)i * n]; }, [&](int i, uint64_t v) { out[obase + (size_t)i * n] = v; });
+    }
+}
 
 // Row-wise elementwise kernels: blockIdx.y walks the rows (one limb of one polynomial: the modulus and every base offset are uniform,
 // so no per-element division), blockIdx.x / threadIdx.x walk the row in coefficient pairs (16-byte accesses).
@@ -347,6 +361,32 @@ static fhe_status run_rescale(fhe_ctx* ctx, const std::vector<uint64_t>& all, si
     return after_launch(ctx, "rns_rescale_kernel");
 }
 
+// rescale_k(all, k) followed by rescale_k(kept, 1), fused (kept = all[0 .. all.size() - k), at least two limbs)
+static fhe_status run_rescale2(fhe_ctx* ctx, const std::vector<uint64_t>& all, size_t k, unsigned log_n, size_t batch, const uint64_t* d_in,
+                               uint64_t* d_out) {
+    FHE_REQUIRE(ctx, k >= 2 && k + 2 <= all.size() && k <= (size_t)RNS_MAXL, "fused rescale needs k >= 2 dropped and >= 2 kept limbs");
+    const std::vector<uint64_t> kept(all.begin(), all.end() - k);
+    const RescaleOwned *t, *t1;
+    FHE_CHECK(get_rescale(ctx, all, k, &t));
+    FHE_CHECK(get_rescale(ctx, kept, 1, &t1));
+    Rescale1TabV r1;
+    memset(&r1, 0, sizeof r1);
+    r1.l = t1->tab.l;
+    r1.fast = 1;
+    for (size_t i = 0; i < kept.size(); ++i)
+        if (all[i] >= (1ull << 61) || kept.back() > 2 * kept[i]) r1.fast = 0;
+    for (size_t i = 0; i < kept.size(); ++i) {
+        r1.m_all[i] = t1->tab.m_all[i];
+        r1.ph[i] = t1->tab.ph[i];
+    }
+    for (size_t i = 0; i + 1 < kept.size(); ++i) {
+        r1.pinv[i] = t1->tab.pinv[i];
+        r1.pinv_sh[i] = t1->tab.pinv_sh[i];
+    }
+    rns_rescale2_kernel<<<stream_grid(ctx, (unsigned long long)batch << log_n), 256, 0, ctx->stream>>>(t->tab, r1, (int)log_n, batch, d_in, d_out);
+    return after_launch(ctx, "rns_rescale2_kernel");
+}
+
 }  // namespace fhe
 
 using namespace fhe;
@@ -381,6 +421,15 @@ static fhe_status ckks_ws(fhe_ctx* ctx, fhe_ckks_ctx* ck, size_t bytes, uint64_t
     *out = (uint64_t*)ck->ws;
     return FHE_OK;
 }
+// bytes of workspace one chunk of a batched operation may use (FHE_B200_CKKS_WS_MB overrides; tuning knob)
+static size_t ckks_ws_budget() {
+    static const size_t v = [] {
+        const char* e = getenv("FHE_B200_CKKS_WS_MB");
+        const long mb = e ? atol(e) : 0;
+        return mb > 0 ? (size_t)mb << 20 : (size_t)6 << 30;
+    }();
+    return v;
+}
 static std::vector<uint64_t> level_qs(const fhe_ckks_ctx* ck, size_t l) { return std::vector<uint64_t>(ck->qs.begin(), ck->qs.begin() + l); }
 static std::vector<uint64_t> level_qps(const fhe_ckks_ctx* ck, size_t l) {
     std::vector<uint64_t> v = level_qs(ck, l);
@@ -394,7 +443,7 @@ static std::vector<uint64_t> level_qps(const fhe_ckks_ctx* ck, size_t l) {
 // d01_eval (optional, [count][2][l][n] evaluation form): added to the result (see ckks_keymul_kernel)
 static fhe_status key_switch_core(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* ksk, size_t l, size_t count, const uint64_t* a_coeff,
                                   const uint64_t* a_eval, uint64_t* xp, uint64_t* kk, const uint64_t* post, uint64_t* r,
-                                  const uint64_t* d01_eval = nullptr) {
+                                  const uint64_t* d01_eval = nullptr, uint64_t* rescaled_out = nullptr) {
     const unsigned log_n = ck->log_n;
     const size_t L = ck->big_l;
     const std::vector<uint64_t> qs = level_qs(ck, l), qps = level_qps(ck, l);
@@ -404,7 +453,11 @@ static fhe_status key_switch_core(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks
         ck->d_mods, (int)l, (int)L, (int)log_n, count, a_eval, xp, ksk->d_eval, d01_eval, ck->d_pmod, kk);
     FHE_CHECK(after_launch(ctx, "ckks_keymul_kernel"));
     FHE_CHECK(launch_ntt_rns_u64(ctx, qps.data(), l + L, log_n, count * 2 * (l + L), kk, false));
-    return run_rescale(ctx, qps, L, log_n, count * 2, kk, post, true, r);
+    // rescaled_out: the caller wants rescale(r) (one more limb dropped) and not r itself
+    if (rescaled_out && !post && L >= 2 && l >= 2) return run_rescale2(ctx, qps, L, log_n, count * 2, kk, rescaled_out);
+    FHE_CHECK(run_rescale(ctx, qps, L, log_n, count * 2, kk, post, true, r));
+    if (rescaled_out) return run_rescale(ctx, qs, 1, log_n, count * 2, r, nullptr, false, rescaled_out);
+    return FHE_OK;
 }
 }  // namespace fhe
 
@@ -680,7 +733,7 @@ fhe_status fhe_ckks_mul_relin_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, cons
     const std::vector<uint64_t> qs = level_qs(ck, l);
     // per-pair workspace (words): e0, e1 (2l each) | d01 (2l) | d2 eval (l) | d2 coeff (l) | xp (L) | kk (2(l+L)) | r (2l)
     const size_t per = (2 * l + 2 * l + 2 * l + l + l + L + 2 * le + 2 * l) * n;
-    const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ((size_t)6 << 30) / (per * 8)));
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ckks_ws_budget() / (per * 8)));
     uint64_t* ws;
     FHE_CHECK(ckks_ws(ctx, ck, chunk * per * 8, &ws));
     uint64_t* e0 = ws;
@@ -702,8 +755,7 @@ fhe_status fhe_ckks_mul_relin_rescale_batch(fhe_ctx* ctx, fhe_ckks_ctx* ck, cons
         FHE_CHECK(after_launch(ctx, "ckks_tensor_kernel"));
         FHE_CHECK(launch_ntt_rns_u64_oop(ctx, qs.data(), l, log_n, c * l, d2e, d2c, false));
         // relinearize(d2) with ct_b = 0, plus (d0, d1) folded in before the inverse transforms; then rescale (ckks.rs:266, 123-125)
-        FHE_CHECK(key_switch_core(ctx, ck, rlk, l, c, d2c, d2e, xp, kk, nullptr, r, d01));
-        FHE_CHECK(run_rescale(ctx, qs, 1, log_n, c * 2, r, nullptr, false, d_out + base * 2 * (l - 1) * n));
+        FHE_CHECK(key_switch_core(ctx, ck, rlk, l, c, d2c, d2e, xp, kk, nullptr, r, d01, d_out + base * 2 * (l - 1) * n));
     }
     return FHE_OK;
 }
@@ -739,7 +791,7 @@ fhe_status fhe_ckks_key_switch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ks
     const std::vector<uint64_t> qs = level_qs(ck, l);
     // per-ciphertext workspace (words): ct' (2l) | a coeff (l) | a eval (l) | xp (L) | kk (2(l+L))
     const size_t per = (2 * l + l + l + L + 2 * le) * n;
-    const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ((size_t)6 << 30) / (per * 8)));
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ckks_ws_budget() / (per * 8)));
     uint64_t* ws;
     FHE_CHECK(ckks_ws(ctx, ck, chunk * per * 8, &ws));
     uint64_t* cta = ws;

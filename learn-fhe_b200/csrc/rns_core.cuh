@@ -90,8 +90,9 @@ HD double u64_to_f64(uint64_t v) {
 // Rns::extend_bases for one coefficient (rns.rs:331-345): x[i] = residue mod q_i (i < nq) -> y[k] = residue mod p_k.
 // `emit(k, y)` receives the outputs; `begin(k)` runs before the products of target k (rescale_k requests the kept limb there, so its
 // global-memory latency hides behind them).
+// Targets are visited in the order first, 0, 1, ... (skipping first).
 template <typename Tab, typename Emit, typename Begin>
-HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq valid */, Emit emit, Begin begin) {
+HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq valid */, Emit emit, Begin begin, int first = 0) {
     uint64_t v[RNS_MAXL];
     double acc = 0.0;
 #pragma unroll
@@ -105,7 +106,8 @@ HD void rns_extend_coeff(const Tab& T, const uint64_t* x /* [RNS_MAXL], first nq
         }
     }
     const uint32_t u = (uint32_t)f64_round_half_away(acc);
-    for (int k = 0; k < T.np; ++k) {
+    for (int kk = 0; kk < T.np; ++kk) {
+        const int k = kk == 0 ? first : (kk <= first ? kk - 1 : kk);
         begin(k);
         const Mod64 m = T.mp[k];
         const uint64_t* qh = T.qhat_ps + (size_t)k * RNS_MAXL;
@@ -191,6 +193,46 @@ HD void rns_rescale_coeff(const Tab& R, Load x, Emit emit) {
             },
             [&](int i) { kept = x(i); });
     }
+}
+
+// rescale_k by the k dropped limbs of R followed by rescale_k(1) of the result's last limb (tables of the second step in R1:
+// R1.l = R.l - 1, R1.k = 1) for one coefficient, without materialising the intermediate: exactly rns_rescale_coeff(R1, .)
+// applied to the limbs rns_rescale_coeff(R, .) emits.  The last kept limb is converted first because every other output needs it.
+struct Rescale1TabV {
+    int l;
+    int fast;  // 1: every modulus < 2^61 and the dropped limb of the second step < 2 q_i for every kept q_i (lazy finishing, see below)
+    Mod64 m_all[RNS_MAXL + 1];
+    uint64_t ph[RNS_MAXL + 1];
+    uint64_t pinv[RNS_MAXL], pinv_sh[RNS_MAXL];
+};
+template <typename Tab, typename Tab1, typename Load, typename Emit>
+HD void rns_rescale2_coeff(const Tab& R, const Tab1& R1, Load x, Emit emit) {
+    const int l = R.l, k = R.k;
+    uint64_t xs[RNS_MAXL];
+#pragma unroll
+    for (int j = 0; j < RNS_MAXL; ++j) xs[j] = j < k ? R.m_all[l + j].add(x(l + j), R.ph[l + j]) : 0;
+    uint64_t kept = 0, vp = 0;
+    rns_extend_coeff(
+        R.ext, xs,
+        [&](int i, uint64_t y) {
+            const Mod64 m = R.m_all[i];
+            const uint64_t v = m.sub(m.add(kept, R.ph[i]), y);
+            const uint64_t r = m.redq(m.shoup_lazy(v, R.pinv[i], R.pinv_sh[i]));  // limb i of rescale_k(x, k)
+            if (i == l - 1) {
+                vp = m.add(r, R1.ph[l - 1]);  // rounded dropped limb of the second step (rns.rs:109-111)
+            } else if (R1.fast) {
+                // same canonical result with lazy intermediates: u = kept + P/2 + q - y < 3q, t = u P^-1 in [0, 4q) (3-multiply high
+                // word), w = t + q_last/2 + q - (vp mod q) < 6q < 2^64, and one canonical reduction at the very end
+                const uint64_t u = kept + R.ph[i] + m.q - y;
+                const uint64_t t = R.pinv[i] * u - mulhi_u64_approx(R.pinv_sh[i], u) * m.q;
+                const uint64_t w = t + R1.ph[i] + m.q - umin_(vp, vp - m.q);
+                emit(i, m.canon4(R1.pinv[i] * w - mulhi_u64_approx(R1.pinv_sh[i], w) * m.q));
+            } else {
+                const uint64_t w = m.sub(m.add(r, R1.ph[i]), rns_reduce_u64(m, vp));
+                emit(i, m.redq(m.shoup_lazy(w, R1.pinv[i], R1.pinv_sh[i])));
+            }
+        },
+        [&](int i) { kept = x(i); }, l - 1);
 }
 
 }  // namespace fhe

@@ -190,15 +190,16 @@ __global__ void __launch_bounds__(256) tfhe_fast_key_kernel(TfheFastDev P, unsig
 }
 // blind_rotate + sample_extract(0) for k = 1: ct_in [count][n_lwe+1] -> out [count][N+1]; persistent CTA per ciphertext,
 // accumulator (2 N torus words) and the exchange buffer (2 d N/2 complex) resident in shared memory across all n CMUX steps
-template <typename C>
+// A = uint64_t: accumulator in full torus words (mode 2); uint32_t: its top half only (mode 3)
+template <typename C, typename A>
 __global__ void __launch_bounds__(TFHE_FAST_THREADS, TFHE_FAST_MINB) tfhe_blind_rotate_fast_kernel(TfheFastDev P, const uint64_t* __restrict__ lut,
                                                                                    const uint64_t* __restrict__ ct_in, unsigned long long count,
                                                                                    uint64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr uint32_t N = C::N;
-    uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);
-    Cx* X = reinterpret_cast<Cx*>(acc + 2 * N);
-    uint16_t* ex = reinterpret_cast<uint16_t*>(X + (size_t)C::NL * C::M);
+    Cx* X = reinterpret_cast<Cx*>(smem_raw);  // 16-byte aligned entries first
+    A* acc = reinterpret_cast<A*>(X + (size_t)C::NL * C::M);
+    uint16_t* ex = reinterpret_cast<uint16_t*>(acc + 2 * N);
     const uint32_t rb = 64 - (C::LG + 2);  // tfhe/bootstrapping.rs:99-104: switch to Z_{2N}
     auto run = [&](uint32_t units, auto f) {
         for (uint32_t u = threadIdx.x; u < units; u += TFHE_FAST_THREADS) f(u);
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(TFHE_FAST_THREADS, TFHE_FAST_MINB) tfhe_blind_
         const uint32_t e0 = (2 * N - bt) & (2 * N - 1);  // rotate(-b~)
         for (uint32_t c = threadIdx.x; c < N; c += TFHE_FAST_THREADS) {
             acc[c] = 0;
-            acc[N + c] = t64_rot_coef(lut, N, e0, c);
+            acc[N + c] = t64_to_acc<A>(t64_rot_coef(lut, N, e0, c));
         }
         __syncthreads();
         for (uint32_t i = 0; i < P.n_lwe; ++i) {
@@ -243,8 +244,8 @@ __global__ void __launch_bounds__(TFHE_FAST_THREADS, TFHE_FAST_MINB) tfhe_blind_
             }
         }
         uint64_t* o = out + ct * ((unsigned long long)N + 1);
-        for (uint32_t x = threadIdx.x; x < N; x += TFHE_FAST_THREADS) o[x] = x == 0 ? acc[0] : (uint64_t)(0 - acc[N - x]);
-        if (threadIdx.x == 0) o[N] = acc[N];
+        for (uint32_t x = threadIdx.x; x < N; x += TFHE_FAST_THREADS) o[x] = acc_to_t64(x == 0 ? acc[0] : (A)(0 - acc[N - x]));
+        if (threadIdx.x == 0) o[N] = acc_to_t64(acc[N]);
         __syncthreads();
     }
 }
@@ -378,21 +379,25 @@ static fhe_status run_key_switch(fhe_ctx* ctx, const fhe_tfhe_key* key, size_t c
 
 static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_tfhe_key* key, const uint64_t* d_lut, size_t count, const uint64_t* d_in,
                                    uint64_t* d_out) {
-    if (key->mode == 2) {
+    if (key->mode >= 2) {
         fhe_status st = FHE_OK;
         tfhe_fast_dispatch(key->P.log_n - 1, key->P.bs_dec.d, [&](auto cfg) {
             typedef decltype(cfg) C;
-            const size_t smem = tfhe_fast_smem_bytes<C>(key->F.n_lwe);
-            auto kern = tfhe_blind_rotate_fast_kernel<C>;
-            int occ = 0;
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TFHE_FAST_THREADS, smem) != cudaSuccess || occ < 1) {
-                st = fail(ctx, FHE_ECUDA, "tfhe_blind_rotate_fast_kernel does not fit (%zu bytes of shared memory)", smem);
-                return;
-            }
-            const unsigned grid = (unsigned)std::min<unsigned long long>(count, (unsigned long long)ctx->sm_count * occ);
-            kern<<<grid, TFHE_FAST_THREADS, smem, ctx->stream>>>(key->F, d_lut, d_in, count, d_out);
-            st = after_launch(ctx, "tfhe_blind_rotate_fast_kernel");
+            auto launch = [&](auto kern, size_t smem) {
+                int occ = 0;
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TFHE_FAST_THREADS, smem) != cudaSuccess || occ < 1) {
+                    st = fail(ctx, FHE_ECUDA, "tfhe_blind_rotate_fast_kernel does not fit (%zu bytes of shared memory)", smem);
+                    return;
+                }
+                const unsigned grid = (unsigned)std::min<unsigned long long>(count, (unsigned long long)ctx->sm_count * occ);
+                kern<<<grid, TFHE_FAST_THREADS, smem, ctx->stream>>>(key->F, d_lut, d_in, count, d_out);
+                st = after_launch(ctx, "tfhe_blind_rotate_fast_kernel");
+            };
+            if (key->mode == 3)
+                launch(tfhe_blind_rotate_fast_kernel<C, uint32_t>, tfhe_fast_smem_bytes<C, uint32_t>(key->F.n_lwe));
+            else
+                launch(tfhe_blind_rotate_fast_kernel<C, uint64_t>, tfhe_fast_smem_bytes<C, uint64_t>(key->F.n_lwe));
         });
         return st;
     }
@@ -728,9 +733,10 @@ void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key) {
 }
 fhe_status fhe_tfhe_key_set_mode(fhe_ctx* ctx, fhe_tfhe_key* key, int mode) {
     if (!ctx || !key) return FHE_EINVAL;
-    FHE_REQUIRE(ctx, mode >= 0 && mode <= 2,
-                "mode must be 0 (reference dataflow, bit-identical), 1 (Fourier-domain accumulation) or 2 (bounded-error fused path)");
-    if (mode == 2 && !key->fast_ok)
+    FHE_REQUIRE(ctx, mode >= 0 && mode <= 3,
+                "mode must be 0 (reference dataflow, bit-identical), 1 (Fourier-domain accumulation), 2 (bounded-error fused path) or 3 "
+                "(fused path with 32-bit accumulator words)");
+    if (mode >= 2 && !key->fast_ok)
         return fail(ctx, FHE_EUNSUPPORTED, "the fused bounded-error path needs k = 1, log_b d <= 31, d <= 3 (2 at N = 2048) and N in {512, 1024, 2048}");
     FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     key->mode = mode;

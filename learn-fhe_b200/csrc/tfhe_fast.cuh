@@ -67,6 +67,44 @@ HD uint64_t f64_to_torus(double x) {
     return (uint64_t)(long long)__builtin_rint(y);
 #endif
 }
+// the top 32 bits of x mod 2^64, rounded to nearest: y = x - 2^64 rint(x 2^-64) as above (|y| <= 2^63), then rint(y 2^-32) sits
+// in the low word of y 2^-32 + 1.5 * 2^52
+HD uint32_t f64_to_torus32(double x) {
+    const double t = f64_mul_rn(x, 0x1p-64);
+    const double r = f64_sub_rn(f64_add_rn(t, 0x1.8p52), 0x1.8p52);
+    const double y = f64_fma_rn(-r, 0x1p64, x);
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(__fma_rn(y, 0x1p-32, 0x1.8p52));
+#else
+    return (uint32_t)(int64_t)__builtin_rint(y * 0x1p-32);
+#endif
+}
+// Accumulator word of the fused path: uint64_t (the full torus word) or uint32_t (its top half; every increment is a sum of f64
+// products of magnitude ~2^90 and carries no information below bit 35, see DESIGN.md "TFHE fused kernel")
+template <typename A>
+HD A f64_to_acc(double x);
+template <>
+HD uint64_t f64_to_acc<uint64_t>(double x) {
+    return f64_to_torus(x);
+}
+template <>
+HD uint32_t f64_to_acc<uint32_t>(double x) {
+    return f64_to_torus32(x);
+}
+HD uint32_t acc_hi_word(uint64_t v) { return (uint32_t)(v >> 32); }
+HD uint32_t acc_hi_word(uint32_t v) { return v; }
+HD uint64_t acc_to_t64(uint64_t v) { return v; }
+HD uint64_t acc_to_t64(uint32_t v) { return (uint64_t)v << 32; }
+template <typename A>
+HD A t64_to_acc(uint64_t v);
+template <>
+HD uint64_t t64_to_acc<uint64_t>(uint64_t v) {
+    return v;
+}
+template <>
+HD uint32_t t64_to_acc<uint32_t>(uint64_t v) {
+    return (uint32_t)((v + 0x80000000ull) >> 32);
+}
 HD double i32_to_f64(int32_t v) {
 #if defined(__CUDA_ARCH__)
     return __int2double_rn(v);
@@ -113,8 +151,8 @@ struct TfheFastDev {
 };
 
 template <int D>
-HD void t64_digits(const FastDigits& fd, uint64_t v64, int32_t* dig) {
-    uint32_t v = ((uint32_t)(v64 >> 32) + fd.rnd) >> fd.sh;
+HD void t64_digits(const FastDigits& fd, uint32_t hi /* high word of the torus value */, int32_t* dig) {
+    uint32_t v = (hi + fd.rnd) >> fd.sh;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         const uint32_t limb = v & fd.mask;
@@ -212,18 +250,18 @@ struct TfheFastCfg {
     static constexpr uint32_t U4 = 2u << (LG - R2);       // P4 units: (output, group)
     static constexpr size_t KEY_STRIDE = (size_t)2 * NL * M;  // complex words per CMUX step
 };
-template <typename C>
+template <typename C, typename A = uint64_t>
 HD size_t tfhe_fast_smem_bytes(uint32_t n_lwe) {
-    return (size_t)2 * C::N * 8 + (size_t)C::NL * C::M * sizeof(Cx) + (((size_t)n_lwe * 2 + 15) & ~(size_t)15);
+    return (size_t)2 * C::N * sizeof(A) + (size_t)C::NL * C::M * sizeof(Cx) + (((size_t)n_lwe * 2 + 15) & ~(size_t)15);
 }
 
 // ---- P1: rotate-subtract, decompose, first forward pass -----------------------------------------------------------------------
-template <typename C>
-HD void tfhe_fast_p1(const TfheFastDev& P, const uint64_t* __restrict__ acc, Cx* __restrict__ X, uint32_t unit, uint32_t e) {
+template <typename C, typename A>
+HD void tfhe_fast_p1(const TfheFastDev& P, const A* __restrict__ acc, Cx* __restrict__ X, uint32_t unit, uint32_t e) {
     constexpr int L = C::LG - C::R1, NE = 1 << C::R1;
     constexpr uint32_t N = C::N, M = C::M;
     const uint32_t j = unit >> L, lo = unit & ((1u << L) - 1u);
-    const uint64_t* a = acc + (size_t)j * N;
+    const A* a = acc + (size_t)j * N;
     int32_t dig[C::D][NE][2];
     const uint32_t from0 = (lo + 2 * N - e) & (2 * N - 1);
 #pragma unroll
@@ -232,10 +270,10 @@ HD void tfhe_fast_p1(const TfheFastDev& P, const uint64_t* __restrict__ acc, Cx*
         for (int half = 0; half < 2; ++half) {
             const uint32_t c = lo + ((uint32_t)i << L) + (uint32_t)half * M;
             const uint32_t from = (from0 + ((uint32_t)i << L) + (uint32_t)half * M) & (2 * N - 1);
-            const uint64_t r = a[from & (N - 1)];
-            const uint64_t diff = ((from & N) ? (uint64_t)(0 - r) : r) - a[c];
+            const A r = a[from & (N - 1)];
+            const A diff = (A)(((from & N) ? (A)(0 - r) : r) - a[c]);
             int32_t dd[C::D];
-            t64_digits<C::D>(P.dig, diff, dd);
+            t64_digits<C::D>(P.dig, acc_hi_word(diff), dd);
 #pragma unroll
             for (int k = 0; k < C::D; ++k) dig[k][i][half] = dd[k];
         }
@@ -321,12 +359,12 @@ HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restr
     }
 }
 // ---- P5: last inverse pass, untwist, round, accumulate ---------------------------------------------------------------------------------
-template <typename C>
-HD void tfhe_fast_p5(const TfheFastDev& P, uint64_t* __restrict__ acc, const Cx* __restrict__ X, uint32_t unit) {
+template <typename C, typename A>
+HD void tfhe_fast_p5(const TfheFastDev& P, A* __restrict__ acc, const Cx* __restrict__ X, uint32_t unit) {
     constexpr int L = C::LG - C::R1, NE = 1 << C::R1;
     const uint32_t o = unit >> L, lo = unit & ((1u << L) - 1u);
     const Cx* f = X + ((size_t)o << C::LG);
-    uint64_t* a = acc + (size_t)o * C::N;
+    A* a = acc + (size_t)o * C::N;
     const uint32_t p0 = swz_cx(lo);
     Cx x[NE];
 #pragma unroll
@@ -344,16 +382,16 @@ HD void tfhe_fast_p5(const TfheFastDev& P, uint64_t* __restrict__ acc, const Cx*
         const Cx u = i == 0 ? ul : Cx{f64_fma_rn(-ul.im, P.fft.u0[i].im, f64_mul_rn(ul.re, P.fft.u0[i].re)), f64_fma_rn(ul.im, P.fft.u0[i].re, f64_mul_rn(ul.re, P.fft.u0[i].im))};
         const double re = f64_fma_rn(-x[i].im, u.im, f64_mul_rn(x[i].re, u.re));
         const double im = f64_fma_rn(x[i].im, u.re, f64_mul_rn(x[i].re, u.im));
-        a[p] += f64_to_torus(re);
-        a[p + C::M] += f64_to_torus(im);
+        a[p] += f64_to_acc<A>(re);
+        a[p + C::M] += f64_to_acc<A>(im);
     }
 }
 
 // One CMUX step acc <- acc + external_product(brk_step, acc.rotate(e) - acc) (tggsw.rs:100-121) on the accumulator in `acc`
 // ([2][N] torus words).  run(units, f) calls f(unit) for every unit in [0, units) - spread over the CTA's threads on the
 // device, a plain loop in tests/hostsim - followed by a barrier.
-template <typename C, typename Run>
-HD void tfhe_fast_cmux(const TfheFastDev& P, uint64_t* acc, Cx* X, uint32_t step, uint32_t e, Run run) {
+template <typename C, typename A, typename Run>
+HD void tfhe_fast_cmux(const TfheFastDev& P, A* acc, Cx* X, uint32_t step, uint32_t e, Run run) {
     const Cx* key = P.key + (size_t)step * C::KEY_STRIDE;
     run(C::U1, [&](uint32_t u) { tfhe_fast_p1<C>(P, acc, X, u, e); });
     run(C::U2, [&](uint32_t u) { tfhe_fast_mid<C, true>(P, X, u); });

@@ -72,7 +72,9 @@ class BootstrappingKey:
     def set_mode(self, mode):
         """0 / False (default): the reference's dataflow, bit-identical torus words; 1 / True: Fourier-domain accumulation (one
         rounding per output coefficient; within the reference's error bound, decryptions identical); 2: the fused
-        bounded-error blind rotation (same contract as 1; k = 1, N in {512, 1024, 2048})."""
+        bounded-error blind rotation (same contract as 1; k = 1, N in {512, 1024, 2048}); 3: mode 2 with the accumulator kept as
+        the top 32 bits of every torus word (each increment is a sum of f64 products of magnitude ~2^90 whose bits below 2^35 are
+        rounding noise in every mode, the reference's included; output words have zero low halves)."""
         self.ctx.call("fhe_tfhe_key_set_mode", self.h, int(mode))
 
     @property

@@ -257,6 +257,23 @@ def test_kernel_logic_rns(H, orc):
         out = np.zeros((nq - k, n), dtype=np.uint64)
         assert H.sim_rns_rescale(U(qs), nq, k, x.reshape(-1), out.reshape(-1), n) == 0
         assert (out == orc.rns_rescale_k(qs, k, x)).all(), (nq, k)
+    # Ckks::mul's two consecutive rescales fused into one pass (rns_rescale2_coeff)
+    H.sim_rns_rescale2.argtypes = [u64p, C.c_size_t, C.c_size_t, u64p, u64p, C.c_size_t]
+    for nq, k in ((16, 8), (6, 4), (4, 2), (11, 3)):
+        qs = primes[:nq]
+        x = np.stack([orc.residues(11 * nq + i, n, q) for i, q in enumerate(qs)])
+        x[:, 0] = 0
+        x[:, 1] = [q - 1 for q in qs]
+        out = np.zeros((nq - k - 1, n), dtype=np.uint64)
+        assert H.sim_rns_rescale2(U(qs), nq, k, x.reshape(-1), out.reshape(-1), n) == 0
+        assert (out == orc.rns_rescale_k(qs[:nq - k], 1, orc.rns_rescale_k(qs, k, x))).all(), (nq, k)
+    # a wider last kept limb: the canonical (non-lazy) finishing path
+    qs = primes[:3] + orc.two_adic_primes(58, 10, 1) + primes[3:6]
+    x = np.stack([orc.residues(900 + i, n, q) for i, q in enumerate(qs)])
+    x[:, 1] = [q - 1 for q in qs]
+    out = np.zeros((3, n), dtype=np.uint64)
+    assert H.sim_rns_rescale2(U(qs), 7, 3, x.reshape(-1), out.reshape(-1), n) == 0
+    assert (out == orc.rns_rescale_k(qs[:4], 1, orc.rns_rescale_k(qs, 3, x))).all()
     # the three accumulation modes of rns_extend_coeff at the largest fan-in (16 source limbs, all residues q_i - 1):
     # exact 128-bit sum (targets in [2^33, 2^59), incl. primes just below 2^59), lazy Shoup sum (forced), canonical (61-bit)
     big = orc.two_adic_primes(59, 8, 16)
@@ -424,11 +441,14 @@ def test_kernel_logic_tfhe_fast_mode(H, orc, bs_d, big_n, n, bs_log_b):
     phase = lambda t: (int(t[-1]) - int((t[:-1] * sk).sum(dtype=np.uint64))) % (1 << 64)
     dec = lambda ph: ((ph + (1 << (log_delta - 1))) >> log_delta) % (1 << (P.log_p + P.padding))
     log_delta = 64 - (P.log_p + P.padding)
+    H.sim_tfhe_fast_blind_rotate_extract32.argtypes = [C.c_void_p, u64p, u64p, u64p]
     for ct in cts:
-        out = np.zeros(P.big_n + 1, dtype=np.uint64)
-        assert H.sim_tfhe_fast_blind_rotate_extract(h, lut, ct, out) == 0
         ref = K.blind_rotate_extract(v, ct)
-        d = (phase(out) - phase(ref) + (1 << 63)) % (1 << 64) - (1 << 63)
-        assert abs(d) < 2 ** (log_delta - 4), (d, log_delta)
-        assert dec(phase(out)) == dec(phase(ref))
+        for fn in (H.sim_tfhe_fast_blind_rotate_extract, H.sim_tfhe_fast_blind_rotate_extract32):  # 64- and 32-bit accumulator words
+            out = np.zeros(P.big_n + 1, dtype=np.uint64)
+            assert fn(h, lut, ct, out) == 0
+            d = (phase(out) - phase(ref) + (1 << 63)) % (1 << 64) - (1 << 63)
+            assert abs(d) < 2 ** (log_delta - 4), (d, log_delta)
+            assert dec(phase(out)) == dec(phase(ref))
+        assert (out & u64(0xFFFFFFFF) == 0).all()
     H.sim_tfhe_fast_key_free(h)
