@@ -232,6 +232,12 @@ fhe_status fhe_tfhe_key_upload(fhe_ctx* ctx, const fhe_tfhe_param* param, const 
  * ksk_b_out (optional, HOST) export the key in the layout of fhe_tfhe_key_upload. */
 fhe_status fhe_tfhe_keygen(fhe_ctx* ctx, const fhe_tfhe_param* param, double tlwe_std, double tglwe_std, uint64_t seed, int64_t* z_out, int64_t* s_out,
                            uint64_t* brk_out, uint64_t* ksk_a_out, uint64_t* ksk_b_out, fhe_tfhe_key** out);
+/* Serialised key: header {magic "FHEB200K", version 1, kind 2} | fhe_tfhe_param | the device images (bsk in the twisted Fourier
+ * domain, merged ksk, its digit-offset column sums, and the fused path's bsk image when the parameters have one).  Loading is
+ * four host-to-device copies, no transform; inconsistent or truncated blobs are rejected with FHE_EINVAL. */
+size_t fhe_tfhe_key_serialized_size(const fhe_tfhe_key* key);
+fhe_status fhe_tfhe_key_serialize(fhe_ctx* ctx, const fhe_tfhe_key* key, void* buf, size_t cap);
+fhe_status fhe_tfhe_key_deserialize(fhe_ctx* ctx, const void* buf, size_t len, fhe_tfhe_key** out);
 void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key);
 /* Evaluation mode of every product made with this key.  0 (default): the reference's dataflow - each row * limb product is
  * inverse-transformed and rounded on its own (misc.rs:59-61), raw torus words bit-identical to the reference.  1: products

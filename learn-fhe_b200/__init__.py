@@ -148,6 +148,10 @@ def lib():
     L.fhe_fhew_blind_rotate_batch.argtypes = [vp, vp, vp, sz, vp, vp]
     L.fhe_fhew_key_check_error.argtypes = [vp, vp]
     L.fhe_fhew_keygen.argtypes = [vp, C.POINTER(FhewParam), u64, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.fhe_tfhe_key_serialized_size.argtypes = [vp]
+    L.fhe_tfhe_key_serialized_size.restype = sz
+    L.fhe_tfhe_key_serialize.argtypes = [vp, vp, vp, sz]
+    L.fhe_tfhe_key_deserialize.argtypes = [vp, vp, sz, C.POINTER(vp)]
     L.fhe_fhew_key_serialized_size.argtypes = [vp]
     L.fhe_fhew_key_serialized_size.restype = sz
     L.fhe_fhew_key_serialize.argtypes = [vp, vp, vp, sz]

@@ -254,6 +254,19 @@ class BootstrappingKey:
         self.rtk = {j: _ckks.CkksKeySwitchingKey(bparam.param, ksk_for(j)) for j in bparam.rotation_indices(chains)}
         self._plans, self._dev_plans = {}, {}
 
+    @classmethod
+    def key_gen(cls, bparam, seed, chains=("sfft", "sifft")):
+        """Bootstrapping::key_gen (bootstrapping.rs:56-71) on the device: the secret, the relinearisation key and one rotation key
+        per index of the chains' BSGS plans from the counter stream of `seed` (fhe_ckks_keygen); nothing but the secret leaves the
+        device.  Returns (key, sk [N] int64); the relinearisation key is `key.rlk`."""
+        js = bparam.rotation_indices(chains)
+        sk, rlk, autk = _ckks.key_gen(bparam.param, seed, [bparam.rotation_exponent(j) for j in js])
+        self = cls.__new__(cls)
+        self.bparam, self.rlk = bparam, rlk
+        self.rtk = dict(zip(js, autk))
+        self._plans, self._dev_plans = {}, {}
+        return self, sk
+
     def broadcast_keys(self, dist, root=0):
         for j in sorted(self.rtk):
             self.rtk[j].broadcast(dist, root)
@@ -266,6 +279,9 @@ class BootstrappingKey:
         for k in self.rtk.values():
             k.free()
         self.rtk = {}
+        if getattr(self, "rlk", None) is not None:
+            self.rlk.free()
+            self.rlk = None
 
     def plan(self, which, idx, level):
         key = (which, idx, level)

@@ -409,7 +409,8 @@ static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_tfhe_key* key, const 
 }
 
 // second image of the bsk for the fast path, from the raw torus polynomials still on the device in d_raw ([polys][N])
-static fhe_status build_fast_key(fhe_ctx* ctx, fhe_tfhe_key* key, const uint64_t* d_raw, size_t polys) {
+// (img != nullptr: the image itself, a host copy of d_brk_fast written by fhe_tfhe_key_serialize, is uploaded instead)
+static fhe_status build_fast_key(fhe_ctx* ctx, fhe_tfhe_key* key, const uint64_t* d_raw, size_t polys, const void* img = nullptr, size_t img_bytes = 0) {
     const fhe_tfhe_param& pp = key->param;
     key->fast_ok = false;
     if (pp.k != 1 || pp.bs_log_b * pp.bs_d > 31 || pp.n > 65535) return FHE_OK;
@@ -430,6 +431,12 @@ static fhe_status build_fast_key(fhe_ctx* ctx, fhe_tfhe_key* key, const uint64_t
         key->F.dig = make_fast_digits(key->P.bs_dec);
         key->F.fft = h.view((const Cx*)key->d_fast_tab);
         key->F.key = (const Cx*)key->d_brk_fast;
+        if (img) {
+            if (img_bytes != key->brk_fast_bytes || cudaMemcpyAsync(key->d_brk_fast, img, img_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                st = fail(ctx, FHE_EINVAL, "fast-path bsk image does not match the parameters");
+            return;
+        }
         const size_t smem = C::M * sizeof(Cx);
         auto kern = tfhe_fast_key_kernel<C>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -504,11 +511,16 @@ __global__ void tfhe_ksk_colsum_kernel(const uint64_t* __restrict__ ksk, size_t 
 }
 // Key object from either the reference layout on the HOST (brk, ksk_a, ksk_b: fhe_tfhe_key_upload) or buffers already on the DEVICE
 // (d_brk_raw [polys][N] torus words in the same order, d_ksk_merged [(kN) d_ks][n+1]: fhe_tfhe_keygen; d_ksk_merged is adopted).
+// host copies of a key's device buffers (fhe_tfhe_key_serialize); fast == nullptr when the key had no fused-path image
+struct TfheKeyImages {
+    const void *brk = nullptr, *ksk = nullptr, *colsum = nullptr, *fast = nullptr;
+    size_t brk_bytes = 0, ksk_bytes = 0, colsum_bytes = 0, fast_bytes = 0;
+};
 static fhe_status tfhe_key_build(fhe_ctx* ctx, const fhe_tfhe_param* pp, const uint64_t* brk, const uint64_t* ksk_a, const uint64_t* ksk_b,
-                                 uint64_t* d_brk_raw, uint64_t* d_ksk_merged, fhe_tfhe_key** out) {
+                                 uint64_t* d_brk_raw, uint64_t* d_ksk_merged, fhe_tfhe_key** out, const TfheKeyImages* img = nullptr) {
     if (!ctx || !pp || !out) return FHE_EINVAL;
     *out = nullptr;
-    FHE_REQUIRE(ctx, (brk && ksk_a && ksk_b) || (d_brk_raw && d_ksk_merged), "null key pointer");
+    FHE_REQUIRE(ctx, (brk && ksk_a && ksk_b) || (d_brk_raw && d_ksk_merged) || img, "null key pointer");
     FHE_REQUIRE(ctx, pp->log_big_n >= 1 && pp->log_big_n <= 12, "TFHE ring degree 2^%u out of range (2..4096)", pp->log_big_n);
     FHE_REQUIRE(ctx, pp->k >= 1 && pp->k <= 4, "GLWE dimension k must be in [1, 4]");
     FHE_REQUIRE(ctx, pp->n >= 1 && pp->n <= 65535, "TLWE dimension out of range");
@@ -533,8 +545,30 @@ static fhe_status tfhe_key_build(fhe_ctx* ctx, const fhe_tfhe_param* pp, const u
     // brk: [n][(k+1)d][(k+1)][N] torus words -> Fourier domain
     const size_t polys = (size_t)pp->n * (pp->k + 1) * pp->bs_d * (pp->k + 1);
     uint64_t* d_tmp = d_brk_raw;
-    if (st == FHE_OK && !d_tmp && cudaMalloc((void**)&d_tmp, polys * n * 8) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "bsk staging alloc");
     key->brk_bytes = polys * m * sizeof(Cx);
+    if (st == FHE_OK && img) {  // serialised key: the device images as they were, no transform
+        const size_t rows = (size_t)pp->k * n * pp->ks_d, ld = pp->n + 1;
+        key->ksk_bytes = rows * ld * 8;
+        if (img->brk_bytes != key->brk_bytes || img->ksk_bytes != key->ksk_bytes || img->colsum_bytes != ld * 8)
+            st = fail(ctx, FHE_EINVAL, "serialised key sections do not match its parameters");
+        if (st == FHE_OK && (cudaMalloc(&key->d_brk, key->brk_bytes) != cudaSuccess || cudaMalloc(&key->d_ksk, key->ksk_bytes) != cudaSuccess ||
+                             cudaMalloc(&key->d_ksk_colsum, ld * 8) != cudaSuccess))
+            st = fail(ctx, FHE_ENOMEM, "key alloc");
+        if (st == FHE_OK && (cudaMemcpy(key->d_brk, img->brk, key->brk_bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+                             cudaMemcpy(key->d_ksk, img->ksk, key->ksk_bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+                             cudaMemcpy(key->d_ksk_colsum, img->colsum, ld * 8, cudaMemcpyHostToDevice) != cudaSuccess))
+            st = fail(ctx, FHE_ECUDA, "key image upload failed");
+        if (st == FHE_OK && img->fast) st = build_fast_key(ctx, key, nullptr, polys, img->fast, img->fast_bytes);
+        if (st == FHE_OK && img->fast && !key->fast_ok) st = fail(ctx, FHE_EINVAL, "serialised key carries a fused-path image its parameters do not support");
+        if (st != FHE_OK) {
+            fhe_tfhe_key_free(ctx, key);
+            return st;
+        }
+        P.brk = (const Cx*)key->d_brk;
+        *out = key;
+        return FHE_OK;
+    }
+    if (st == FHE_OK && !d_tmp && cudaMalloc((void**)&d_tmp, polys * n * 8) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "bsk staging alloc");
     if (st == FHE_OK && cudaMalloc(&key->d_brk, key->brk_bytes) != cudaSuccess) st = fail(ctx, FHE_ENOMEM, "bsk alloc");
     if (st == FHE_OK && brk && cudaMemcpyAsync(d_tmp, brk, polys * n * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         st = fail(ctx, FHE_ECUDA, "bsk upload");
@@ -719,6 +753,76 @@ fhe_status fhe_tfhe_keygen(fhe_ctx* ctx, const fhe_tfhe_param* pp, double tlwe_s
         if (s_out) std::copy(s.begin(), s.end(), s_out);
     }
     return st;
+}
+
+// ---- serialised key: header | fhe_tfhe_param | bsk image (Fourier domain) | ksk image | ksk column sums |
+// fused-path bsk image (when the parameters have one).  The images are the device buffers themselves: loading is four copies.
+struct TfheBlobHeader {
+    char magic[8];
+    uint32_t version, kind;
+    uint64_t param_bytes, brk_bytes, ksk_bytes, colsum_bytes, fast_bytes;
+};
+static const char TFHE_BLOB_MAGIC[8] = {'F', 'H', 'E', 'B', '2', '0', '0', 'K'};
+size_t fhe_tfhe_key_serialized_size(const fhe_tfhe_key* key) {
+    if (!key) return 0;
+    return sizeof(TfheBlobHeader) + sizeof(fhe_tfhe_param) + key->brk_bytes + key->ksk_bytes + ((size_t)key->param.n + 1) * 8 +
+           (key->fast_ok ? key->brk_fast_bytes : 0);
+}
+fhe_status fhe_tfhe_key_serialize(fhe_ctx* ctx, const fhe_tfhe_key* key, void* buf, size_t cap) {
+    if (!ctx || !key || !buf) return FHE_EINVAL;
+    FHE_REQUIRE(ctx, cap >= fhe_tfhe_key_serialized_size(key), "buffer too small for the serialised key");
+    TfheBlobHeader h;
+    memcpy(h.magic, TFHE_BLOB_MAGIC, 8);
+    h.version = 1;
+    h.kind = 2;
+    h.param_bytes = sizeof(fhe_tfhe_param);
+    h.brk_bytes = key->brk_bytes;
+    h.ksk_bytes = key->ksk_bytes;
+    h.colsum_bytes = ((size_t)key->param.n + 1) * 8;
+    h.fast_bytes = key->fast_ok ? key->brk_fast_bytes : 0;
+    unsigned char* p = (unsigned char*)buf;
+    memcpy(p, &h, sizeof h);
+    p += sizeof h;
+    memcpy(p, &key->param, sizeof(fhe_tfhe_param));
+    p += sizeof(fhe_tfhe_param);
+    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FHE_CUDA(ctx, cudaMemcpy(p, key->d_brk, h.brk_bytes, cudaMemcpyDeviceToHost));
+    p += h.brk_bytes;
+    FHE_CUDA(ctx, cudaMemcpy(p, key->d_ksk, h.ksk_bytes, cudaMemcpyDeviceToHost));
+    p += h.ksk_bytes;
+    FHE_CUDA(ctx, cudaMemcpy(p, key->d_ksk_colsum, h.colsum_bytes, cudaMemcpyDeviceToHost));
+    p += h.colsum_bytes;
+    if (h.fast_bytes) FHE_CUDA(ctx, cudaMemcpy(p, key->d_brk_fast, h.fast_bytes, cudaMemcpyDeviceToHost));
+    return FHE_OK;
+}
+fhe_status fhe_tfhe_key_deserialize(fhe_ctx* ctx, const void* buf, size_t len, fhe_tfhe_key** out) {
+    if (!ctx || !buf || !out) return FHE_EINVAL;
+    *out = nullptr;
+    TfheBlobHeader h;
+    FHE_REQUIRE(ctx, len >= sizeof h, "serialised key truncated");
+    memcpy(&h, buf, sizeof h);
+    FHE_REQUIRE(ctx, memcmp(h.magic, TFHE_BLOB_MAGIC, 8) == 0 && h.kind == 2, "not a serialised TFHE key");
+    FHE_REQUIRE(ctx, h.version == 1 && h.param_bytes == sizeof(fhe_tfhe_param), "serialised key of another format version");
+    FHE_REQUIRE(ctx, len >= sizeof h + sizeof(fhe_tfhe_param), "serialised key truncated");
+    const unsigned char* p = (const unsigned char*)buf + sizeof h;
+    fhe_tfhe_param pp;
+    memcpy(&pp, p, sizeof pp);
+    p += sizeof pp;
+    FHE_REQUIRE(ctx, h.brk_bytes <= len && h.ksk_bytes <= len && h.colsum_bytes <= len && h.fast_bytes <= len &&
+                         len == sizeof h + sizeof pp + h.brk_bytes + h.ksk_bytes + h.colsum_bytes + h.fast_bytes,
+                "serialised key length mismatch");
+    TfheKeyImages img;
+    img.brk = p;
+    img.brk_bytes = h.brk_bytes;
+    img.ksk = p + h.brk_bytes;
+    img.ksk_bytes = h.ksk_bytes;
+    img.colsum = p + h.brk_bytes + h.ksk_bytes;
+    img.colsum_bytes = h.colsum_bytes;
+    if (h.fast_bytes) {
+        img.fast = p + h.brk_bytes + h.ksk_bytes + h.colsum_bytes;
+        img.fast_bytes = h.fast_bytes;
+    }
+    return tfhe_key_build(ctx, &pp, nullptr, nullptr, nullptr, nullptr, nullptr, out, &img);
 }
 
 void fhe_tfhe_key_free(fhe_ctx* ctx, fhe_tfhe_key* key) {

@@ -58,6 +58,24 @@ class BootstrappingKey:
         self.ctx, self.param, self.h = ctx, param, h
         return (self, z, s, ex) if export else (self, z, s)
 
+    def serialize(self):
+        """The key as bytes: header, parameters and the device images (fhe_tfhe_key_serialize)."""
+        size = int(self.ctx.L.fhe_tfhe_key_serialized_size(self.h))
+        buf = np.zeros(size, dtype=np.uint8)
+        self.ctx.call("fhe_tfhe_key_serialize", self.h, hptr(buf), size)
+        return buf
+
+    @classmethod
+    def deserialize(cls, ctx, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        h = C.c_void_p()
+        ctx.call("fhe_tfhe_key_deserialize", hptr(blob), blob.size, C.byref(h))
+        self = cls.__new__(cls)
+        # the parameters travel in the blob: fhe_tfhe_param follows the 56-byte header
+        self.ctx, self.h = ctx, h
+        self.param = TfheParam.from_buffer_copy(blob[56:56 + C.sizeof(TfheParam)].tobytes())
+        return self
+
     def free(self):
         if getattr(self, "h", None):
             self.ctx.L.fhe_tfhe_key_free(self.ctx.h, self.h)

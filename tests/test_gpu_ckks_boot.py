@@ -49,3 +49,36 @@ def test_slot_to_coeff_and_back_match_the_oracle_chain(pkg, ctx, orc, log_n, bac
             assert np.abs(got - m0[c]).max() < 1e-4
     bk.free()
     P.free()
+
+
+def test_bootstrapping_key_generated_on_the_device(pkg, ctx, orc):
+    """BootstrappingKey.key_gen: the rotation keys of the BSGS plans come from fhe_ckks_keygen (counter stream) and equal the
+    checker's keys for the same seed and exponents, so SlotToCoeff under them is the oracle chain, and it decrypts under the
+    returned secret."""
+    from learn_fhe_b200 import ckks, ckks_bootstrapping as cb
+    log_n, big_l, seed = 6, 8, 0x5EED0B00
+    K0 = orc.CkksKey(log_n, 55, big_l, 1)
+    P = ckks.CkksParam(ctx, log_n, K0.qs, K0.ps)
+    bp = cb.BootstrappingParam(P, 3, "mp")
+    js = bp.rotation_indices()
+    bk, sk = cb.BootstrappingKey.key_gen(bp, seed)
+    K = orc.CkksKey(log_n, 55, big_l, seed, auto_ts=tuple(bp.rotation_exponent(j) for j in js), ctr=True)
+    assert (sk == K.sk()).all() and sorted(bk.rtk) == sorted(js)
+    key_index = {j: i for i, j in enumerate(js)}
+    rng = np.random.default_rng(3)
+    m0 = rng.uniform(-1, 1, bp.l) + 1j * rng.uniform(-1, 1, bp.l)
+    z = cb.sifft(bp.B, [bp.B.mp.mpc(complex(x)) for x in m0])
+    re, im = bp.B.re_im(z)
+    ints = bp.B.trunc_scaled(np.concatenate([re, im]), P.qs[big_l - 1])
+    ct0 = K.encrypt(np.array(ints, dtype=np.int64), big_l, 77)[None]
+    ct1 = cb.Bootstrapping.slot_to_coeff(bk, ct0)
+    assert (ct1[0] == ref.chain(orc, K, key_index, bp, "sfft", ct0[0])).all()
+    got = ref.decode(P, 1, ref.crt_centered(K.qs[:ct1.shape[2]], K.decrypt(ct1[0])))
+    m1 = ref.sfft(ref.bit_reverse(m0))
+    assert np.abs(got - m1).max() < 1e-4 * max(1.0, np.abs(m1).max())
+    # the relinearisation key generated alongside
+    a = K.encrypt(rng.integers(-99, 99, size=P.n, dtype=np.int64), big_l, 1)[None]
+    b = K.encrypt(rng.integers(-99, 99, size=P.n, dtype=np.int64), big_l, 2)[None]
+    assert (ckks.Ckks.mul(P, bk.rlk, a, b) == K.mul(a, b)).all()
+    bk.free()
+    P.free()

@@ -120,4 +120,23 @@ def test_tfhe_device_keygen_equals_host_keygen_on_the_same_stream(pkg, ctx, orc,
     assert (got == K.bootstrap(v, cts, threads=4)).all()
     if big_n >= 512:  # the tiny ring has no noise margin for a look-up
         assert (K.decrypt(got)[0] == msgs).all()
+    # serialised key: round trip, same outputs in every mode the parameters support, corrupted blobs rejected
+    blob = bk.serialize()
+    again = tfhe.BootstrappingKey.deserialize(ctx, blob)
+    assert (again.param.n, again.param.log_big_n, again.param.bs_d) == (param.n, param.log_big_n, param.bs_d)
+    assert (tfhe.Bootstrapping.bootstrap(again, tfhe.encode_lut(param, v), cts) == got).all()
+    assert (again.serialize() == blob).all()
+    if k == 1 and big_n >= 512 and bs[0] * bs[1] <= 31:
+        for mode in (2, 3):
+            bk.set_mode(mode)
+            again.set_mode(mode)
+            assert (tfhe.Bootstrapping.bootstrap(again, tfhe.encode_lut(param, v), cts) == tfhe.Bootstrapping.bootstrap(bk, tfhe.encode_lut(param, v), cts)).all()
+    for bad in (blob[:-8], np.concatenate([blob, np.zeros(8, dtype=np.uint8)]), np.concatenate([np.zeros(8, dtype=np.uint8), blob[8:]])):
+        with pytest.raises(pkg.FheError):
+            tfhe.BootstrappingKey.deserialize(ctx, bad)
+    wrong = blob.copy()
+    wrong[8] = 9  # version
+    with pytest.raises(pkg.FheError):
+        tfhe.BootstrappingKey.deserialize(ctx, wrong)
+    again.free()
     bk.free()

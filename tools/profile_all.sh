@@ -24,7 +24,7 @@ for w in $WHAT; do
     case $w in
         fhew) TRAFFIC=fhew_blind_rotate_fast_kernel=16384 KEEP=1 run fhew fhew_blind_rotate_fast 1 python tools/prof_cmd.py fhew --batch 16384 ;;
         ntt) TRAFFIC= run ntt ntt_fast 12 python tools/prof_cmd.py ntt ;;
-        tfhe) TRAFFIC=tfhe_blind_rotate_fast_kernel=16384 KEEP=1 run tfhe tfhe_blind_rotate_fast 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 2 ;;
+        tfhe) TRAFFIC=tfhe_blind_rotate_fast_kernel=16384 KEEP=1 run tfhe tfhe_blind_rotate_fast 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 3 ;;
         tfhe_exact) TRAFFIC=tfhe_blind_rotate_kernel=16384 KEEP=1 run tfhe_exact 'tfhe_blind_rotate_kernel' 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 0 ;;
         bf) TRAFFIC= KEEP=1 run bf bf_rate 8 python tools/tfhe_bench.py bf ;;
         ckks) TRAFFIC= run ckks 'rns_|ckks_' 8 python tools/tfhe_bench.py ckks --count 128 ;;
