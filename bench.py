@@ -356,8 +356,8 @@ def tfhe_leg(pkg, ctx, torch, dist, world, rank, local, batch, steps, synthetic_
                           "unit": "Tflop/s f64 (algorithmic; peak = measured %s rate of this device, csrc/diag.cu)" % ("DFMA x 2" if mode >= 2 else "DADD/DMUL"),
                           "frac": ach / peak if ach else None, "traffic": ncu_traffic(kname, mine) if mode != 2 else None, "flops_per_pbs": flops,
                           "fp64_peaks_tinstr": pk,
-                          "ncu": "profiles/r02_ncu_full_tfhe_fused_b16384.csv: the busiest unit is the shared-memory / L1 data path "
-                                 "(LSU wavefronts 74 %), FP64 pipe 43 % of issue slots" if mode >= 2 else "profiles/r01_ncu_full_tfhe_b16384.csv"}}
+                          "ncu": ("profiles/r02_ncu_full_tfhe_fused_mode%d_b16384.csv: the busiest unit is the shared-memory / L1 data path "
+                                  "(LSU wavefronts %s), FP64 pipe %s of issue slots" % ((3, "60 %", "46 %") if mode == 3 else (2, "74 %", "43 %"))) if mode >= 2 else "profiles/r01_ncu_full_tfhe_b16384.csv"}}
         if mode == 3:
             r["parity"] = ("same digits and exact sums as the reference; one rounding per output; |CMUX output - reference| < (k+1) d 2^(64+log_b+log_n-53) "
                            "+ 2^31 (accumulator words keep their top 32 bits: the f64 increments carry nothing below 2^35); decryptions identical")

@@ -209,23 +209,26 @@ HD void fast_fwd_regs(const L& m, typename L::W* x, const TwPair<typename L::W>*
 template <typename L, int R, bool LAST, bool NC = true>
 HD void fast_inv_regs(const L& m, typename L::W* x, const TwPair<typename L::W>* __restrict__ itw, uint32_t tb,
                       TwPair<typename L::W> ninv, TwPair<typename L::W> wninv) {
+    // every stage is one flat loop over its 2^(R-1) butterflies (constant trip count: nvcc left the nested `low < h` form partly
+    // rolled for R = 4 inside the tile kernel, which put x[] in local memory); butterfly b of stage `stage`: top = b >> stage
 #pragma unroll
-    for (int u = R - 1; u >= 0; --u) {
-        const int h = 1 << (R - 1 - u);
-        const int stage = R - 1 - u;
+    for (int stage = 0; stage < R; ++stage) {
+        const int u = R - 1 - stage;
+        const int h = 1 << stage;
+        TwPair<typename L::W> t[1 << (R - 1)];
+        if (!(LAST && u == 0)) {
 #pragma unroll
-        for (int top = 0; top < (1 << u); ++top) {
-            if (LAST && u == 0) {
+            for (int top = 0; top < (1 << (R - 1)); ++top)
+                if (top < (1 << u)) t[top] = NC ? ld_tw(itw + ((tb << u) + top)) : itw[(tb << u) + top];
+        }
 #pragma unroll
-                for (int low = 0; low < h; ++low) m.bf_inv_last(x[low], x[low + h], ninv, wninv, stage);
-            } else {
-                const TwPair<typename L::W> t = NC ? ld_tw(itw + ((tb << u) + top)) : itw[(tb << u) + top];
-#pragma unroll
-                for (int low = 0; low < h; ++low) {
-                    const int j = (top << (R - u)) | low;
-                    m.bf_inv(x[j], x[j + h], t, stage);
-                }
-            }
+        for (int b = 0; b < (1 << (R - 1)); ++b) {
+            const int top = b >> stage, low = b & (h - 1);
+            const int j = (top << (R - u)) | low;
+            if (LAST && u == 0)
+                m.bf_inv_last(x[j], x[j + h], ninv, wninv, stage);
+            else
+                m.bf_inv(x[j], x[j + h], t[top], stage);
         }
     }
 }
@@ -252,9 +255,9 @@ template <typename L, int R, bool LAST, bool NC = true>
 HD void fast_inv_regs2(const L& m, typename L::W* x, typename L::W* y, const TwPair<typename L::W>* __restrict__ itw, uint32_t tb,
                        TwPair<typename L::W> ninv, TwPair<typename L::W> wninv) {
 #pragma unroll
-    for (int u = R - 1; u >= 0; --u) {
-        const int h = 1 << (R - 1 - u);
-        const int stage = R - 1 - u;
+    for (int stage = 0; stage < R; ++stage) {  // ascending trip variable: nvcc does not always unroll the descending form
+        const int u = R - 1 - stage;
+        const int h = 1 << stage;
 #pragma unroll
         for (int top = 0; top < (1 << u); ++top) {
             if (LAST && u == 0) {
@@ -318,6 +321,35 @@ DEV void st_vec8(uint64_t* s, uint32_t P0, const uint64_t* x) {
 #pragma unroll
     for (int m = 0; m < 4; ++m) *reinterpret_cast<ulonglong2*>(s + (P0 ^ (2u * m))) = make_ulonglong2(x[2 * m], x[2 * m + 1]);
 }
+// 16 consecutive 64-bit words of a tile (the swizzle of a 16-aligned position only touches address bits 1-3)
+DEV void ld_vec16(const uint64_t* s, uint32_t P0, uint64_t* x) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(s + (P0 ^ (2u * m)));
+        x[2 * m] = a.x;
+        x[2 * m + 1] = a.y;
+    }
+}
+DEV void st_vec16(uint64_t* s, uint32_t P0, const uint64_t* x) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) *reinterpret_cast<ulonglong2*>(s + (P0 ^ (2u * m))) = make_ulonglong2(x[2 * m], x[2 * m + 1]);
+}
+DEV void ldg_vec16(const uint64_t* g, uint64_t* x) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const ulonglong2 a = reinterpret_cast<const ulonglong2*>(g)[m];
+        x[2 * m] = a.x;
+        x[2 * m + 1] = a.y;
+    }
+}
+DEV void stg_vec16(uint64_t* g, const uint64_t* x) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) reinterpret_cast<ulonglong2*>(g)[m] = make_ulonglong2(x[2 * m], x[2 * m + 1]);
+}
+DEV void ld_vec16(const uint32_t*, uint32_t, uint32_t*) {}  // radix-16 tile passes exist for 64-bit words only
+DEV void st_vec16(uint32_t*, uint32_t, const uint32_t*) {}
+DEV void ldg_vec16(const uint32_t*, uint32_t*) {}
+DEV void stg_vec16(uint32_t*, const uint32_t*) {}
 // 8 contiguous words in global memory (16-byte aligned)
 DEV void ldg_vec8(const uint32_t* g, uint32_t* x) {
     const uint4 a = reinterpret_cast<const uint4*>(g)[0], b = reinterpret_cast<const uint4*>(g)[1];
@@ -355,6 +387,22 @@ inline void ldg_vec8(const W* g, W* x) {
 template <typename W>
 inline void stg_vec8(W* g, const W* x) {
     for (int j = 0; j < 8; ++j) g[j] = x[j];
+}
+template <typename W>
+inline void ld_vec16(const W* s, uint32_t P0, W* x) {
+    for (uint32_t j = 0; j < 16; ++j) x[j] = s[P0 ^ j];
+}
+template <typename W>
+inline void st_vec16(W* s, uint32_t P0, const W* x) {
+    for (uint32_t j = 0; j < 16; ++j) s[P0 ^ j] = x[j];
+}
+template <typename W>
+inline void ldg_vec16(const W* g, W* x) {
+    for (int j = 0; j < 16; ++j) x[j] = g[j];
+}
+template <typename W>
+inline void stg_vec16(W* g, const W* x) {
+    for (int j = 0; j < 16; ++j) g[j] = x[j];
 }
 #endif
 
@@ -409,26 +457,26 @@ HD void fast_fwd_first2(const FastLimb<L>& d, const uint32_t* g, uint32_t* s, in
         for (int j = 0; j < (1 << R1); ++j) st_pair(s + (P0 ^ swz2<W>((uint32_t)j << LL)), x[j], y[j]);
     }
 }
-// forward middle pass (radix-8, shared -> shared); local stages t0 .. t0+2, LL = LOGT - t0 - 3 >= 3
-template <typename L, int LOGT, int TPP, int t0>
+// forward middle pass (radix 2^RM, shared -> shared); local stages t0 .. t0+RM-1, LL = LOGT - t0 - RM >= 3
+template <typename L, int LOGT, int TPP, int t0, int RM = 3>
 HD void fast_fwd_mid(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {
     typedef typename L::W W;
-    constexpr int LL = LOGT - t0 - 3;
+    constexpr int LL = LOGT - t0 - RM, NE = 1 << RM;
 #pragma unroll 1
-    for (uint32_t grp = tid; grp < (1u << (LOGT - 3)); grp += TPP) {
+    for (uint32_t grp = tid; grp < (1u << (LOGT - RM)); grp += TPP) {
         const uint32_t lo = grp & ((1u << LL) - 1u), hi = grp >> LL;
-        const uint32_t P0 = swz2<W>((hi << (LL + 3)) | lo);
-        W x[8];
+        const uint32_t P0 = swz2<W>((hi << (LL + RM)) | lo);
+        W x[NE];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = s[P0 ^ swz2<W>((uint32_t)j << LL)];
+        for (int j = 0; j < NE; ++j) x[j] = s[P0 ^ swz2<W>((uint32_t)j << LL)];
         if (pre_red) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = d.m.pre_red(x[j]);
+            for (int j = 0; j < NE; ++j) x[j] = d.m.pre_red(x[j]);
         }
         const uint32_t tb = (1u << (s0 + t0)) + (k << t0) + hi;
-        fast_fwd_regs<L, 3>(d.m, x, d.tw, tb);
+        fast_fwd_regs<L, RM>(d.m, x, d.tw, tb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[P0 ^ swz2<W>((uint32_t)j << LL)] = x[j];
+        for (int j = 0; j < NE; ++j) s[P0 ^ swz2<W>((uint32_t)j << LL)] = x[j];
     }
 }
 // forward middle pass for 32-bit words, two adjacent groups (lo even, lo + 1) per iteration: the XOR swizzle leaves word-address
@@ -459,58 +507,72 @@ HD void fast_fwd_mid2(const FastLimb<L>& d, uint32_t* s, int s0, uint32_t k, boo
         for (int j = 0; j < 8; ++j) st_pair(s + (P0 ^ swz2<W>((uint32_t)j << LL)), x[j], y[j]);
     }
 }
-// forward last pass (radix-8, LL = 0): shared -> registers -> global, canonical output
-template <typename L, int LOGT, int TPP>
+// forward last pass (radix 2^RM, LL = 0): shared -> registers -> global, canonical output
+template <typename L, int LOGT, int TPP, int RM = 3>
 HD void fast_fwd_last(const FastLimb<L>& d, const typename L::W* s, typename L::W* __restrict__ g, int s0, uint32_t k, bool pre_red,
                       uint32_t tid) {
     typedef typename L::W W;
-    constexpr int t0 = LOGT - 3;
+    constexpr int t0 = LOGT - RM, NE = 1 << RM;
 #pragma unroll 1
-    for (uint32_t grp = tid; grp < (1u << (LOGT - 3)); grp += TPP) {
-        W x[8];
-        ld_vec8(s, swz2<W>(grp << 3), x);
+    for (uint32_t grp = tid; grp < (1u << (LOGT - RM)); grp += TPP) {
+        W x[NE];
+        if (RM == 4)
+            ld_vec16(s, swz2<W>(grp << RM), x);
+        else
+            ld_vec8(s, swz2<W>(grp << RM), x);
         if (pre_red) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = d.m.pre_red(x[j]);
+            for (int j = 0; j < NE; ++j) x[j] = d.m.pre_red(x[j]);
         }
         const uint32_t tb = (1u << (s0 + t0)) + (k << t0) + grp;
-        fast_fwd_regs<L, 3>(d.m, x, d.tw, tb);
+        fast_fwd_regs<L, RM>(d.m, x, d.tw, tb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = d.m.canon(x[j]);
-        stg_vec8(g + (grp << 3), x);
+        for (int j = 0; j < NE; ++j) x[j] = d.m.canon(x[j]);
+        if (RM == 4)
+            stg_vec16(g + (grp << RM), x);
+        else
+            stg_vec8(g + (grp << RM), x);
     }
 }
-// inverse first pass (radix-8, LL = 0): global -> registers -> shared
-template <typename L, int LOGT, int TPP>
+// inverse first pass (radix 2^RM, LL = 0): global -> registers -> shared
+template <typename L, int LOGT, int TPP, int RM = 3>
 HD void fast_inv_first(const FastLimb<L>& d, const typename L::W* g, typename L::W* s, int s0, uint32_t k, uint32_t tid) {
     typedef typename L::W W;
-    constexpr int t0 = LOGT - 3;
+    constexpr int t0 = LOGT - RM, NE = 1 << RM;
 #pragma unroll 1
-    for (uint32_t grp = tid; grp < (1u << (LOGT - 3)); grp += TPP) {
-        W x[8];
-        ldg_vec8(g + (grp << 3), x);
+    for (uint32_t grp = tid; grp < (1u << (LOGT - RM)); grp += TPP) {
+        W x[NE];
+        if (RM == 4)
+            ldg_vec16(g + (grp << RM), x);
+        else
+            ldg_vec8(g + (grp << RM), x);
         const uint32_t tb = (1u << (s0 + t0)) + (k << t0) + grp;
-        fast_inv_regs<L, 3, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
+        fast_inv_regs<L, RM, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
         x[0] = d.m.inv_pass_fix(x[0]);
-        st_vec8(s, swz2<W>(grp << 3), x);
+        if (RM == 4) x[1] = d.m.inv_pass_fix(x[1]);  // the sum chain of a 4-stage pass reaches 32q on element 1 (see Lz64)
+        if (RM == 4)
+            st_vec16(s, swz2<W>(grp << RM), x);
+        else
+            st_vec8(s, swz2<W>(grp << RM), x);
     }
 }
-template <typename L, int LOGT, int TPP, int t0>
+template <typename L, int LOGT, int TPP, int t0, int RM = 3>
 HD void fast_inv_mid(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, uint32_t tid) {
     typedef typename L::W W;
-    constexpr int LL = LOGT - t0 - 3;
+    constexpr int LL = LOGT - t0 - RM, NE = 1 << RM;
 #pragma unroll 1
-    for (uint32_t grp = tid; grp < (1u << (LOGT - 3)); grp += TPP) {
+    for (uint32_t grp = tid; grp < (1u << (LOGT - RM)); grp += TPP) {
         const uint32_t lo = grp & ((1u << LL) - 1u), hi = grp >> LL;
-        const uint32_t P0 = swz2<W>((hi << (LL + 3)) | lo);
-        W x[8];
+        const uint32_t P0 = swz2<W>((hi << (LL + RM)) | lo);
+        W x[NE];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = s[P0 ^ swz2<W>((uint32_t)j << LL)];
+        for (int j = 0; j < NE; ++j) x[j] = s[P0 ^ swz2<W>((uint32_t)j << LL)];
         const uint32_t tb = (1u << (s0 + t0)) + (k << t0) + hi;
-        fast_inv_regs<L, 3, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
+        fast_inv_regs<L, RM, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
         x[0] = d.m.inv_pass_fix(x[0]);
+        if (RM == 4) x[1] = d.m.inv_pass_fix(x[1]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[P0 ^ swz2<W>((uint32_t)j << LL)] = x[j];
+        for (int j = 0; j < NE; ++j) s[P0 ^ swz2<W>((uint32_t)j << LL)] = x[j];
     }
 }
 template <typename L, int LOGT, int TPP, int t0>
@@ -591,19 +653,27 @@ HD void fast_inv_last2(const FastLimb<L>& d, const uint32_t* s, uint32_t* __rest
 HD constexpr int fast_r1(int logt) { return logt % 3 == 0 ? 3 : (logt % 3 == 1 ? 4 : 2); }
 // ---- tile geometry and pass sequence (shared by the kernel and tests/hostsim) -----------------------------------------------
 // PAIR (32-bit words only): middle passes process two adjacent groups per thread, so half as many threads cover a tile.
+// FAST_R16_64 = 1: the 2^12 tile of 64-bit words runs three radix-16 passes (4 + 4 + 4) instead of four radix-8 ones: two instead
+// of three round trips through shared memory, one group per thread and pass.  Measured (4096 x 2^12 / 2^16, B200): forward 1.82-1.84
+// vs 1.84 TB/s / 1.48-1.50 vs 1.50, inverse 1.59-1.63 vs 1.84 / 1.31-1.32 vs 1.49 at 80 or 64 registers: the tile is bound by the
+// multiply pipe, not by the shared-memory round trips.  Off.
+#ifndef FAST_R16_64
+#define FAST_R16_64 0
+#endif
 template <typename L, int LOGT>
 struct FastGeom {
-    static constexpr int R1 = fast_r1(LOGT);
-    static constexpr int RMAX = R1 > 3 ? R1 : 3;
+    static constexpr int RM = (L::BITS == 64 && FAST_R16_64 && LOGT == 12) ? 4 : 3;  // radix of the passes after the first
+    static constexpr int R1 = RM == 4 ? 4 : fast_r1(LOGT);
+    static constexpr int RMAX = R1 > RM ? R1 : RM;
     static constexpr int PAIR = (L::BITS == 32 && FAST_PAIR32) ? 1 : 0;
     // 64-bit words: no pairing (twice the registers), but for the big tiles half the threads per tile, each walking two groups
     // per pass: 256-thread CTAs (4 per SM) interleave their load / compute / store phases better than 512-thread ones
     // (measured +6-13 % at 2^12, the tile of N = 2^12 and 2^16; smaller tiles already run 256-thread CTAs)
-    static constexpr int HALF = ((L::BITS == 64 && FAST_HALF64 && LOGT >= 12) || (L::BITS == 32 && FAST_HALF32 && LOGT >= 12)) ? 1 : 0;
+    static constexpr int HALF = (RM == 3 && ((L::BITS == 64 && FAST_HALF64 && LOGT >= 12) || (L::BITS == 32 && FAST_HALF32 && LOGT >= 12))) ? 1 : 0;
     static constexpr int TPP = 1 << (LOGT - RMAX - PAIR - HALF);
     static constexpr int PB = TPP >= FAST_MIN_NTHR ? 1 : FAST_MIN_NTHR / TPP;
     static constexpr int NTHR = TPP * PB;
-    static constexpr int NP3 = (LOGT - R1) / 3;
+    static constexpr int NP3 = (LOGT - R1) / RM;  // passes after the first (middle passes + the last one)
 };
 template <typename L, int LOGT, int t0>
 HD void fast_fwd_mid_any(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {
@@ -611,7 +681,7 @@ HD void fast_fwd_mid_any(const FastLimb<L>& d, typename L::W* s, int s0, uint32_
     if constexpr (G::PAIR != 0)
         fast_fwd_mid2<L, LOGT, G::TPP, t0>(d, s, s0, k, pre_red, tid);
     else
-        fast_fwd_mid<L, LOGT, G::TPP, t0>(d, s, s0, k, pre_red, tid);
+        fast_fwd_mid<L, LOGT, G::TPP, t0, G::RM>(d, s, s0, k, pre_red, tid);
 }
 template <typename L, int LOGT, int t0>
 HD void fast_inv_mid_any(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k, uint32_t tid) {
@@ -619,7 +689,7 @@ HD void fast_inv_mid_any(const FastLimb<L>& d, typename L::W* s, int s0, uint32_
     if constexpr (G::PAIR != 0)
         fast_inv_mid2<L, LOGT, G::TPP, t0>(d, s, s0, k, tid);
     else
-        fast_inv_mid<L, LOGT, G::TPP, t0>(d, s, s0, k, tid);
+        fast_inv_mid<L, LOGT, G::TPP, t0, G::RM>(d, s, s0, k, tid);
 }
 template <typename L, int LOGT>
 HD void fast_fwd_first_any(const FastLimb<L>& d, const typename L::W* g, typename L::W* s, int s0, uint32_t k, bool pre_red, uint32_t tid) {

@@ -43,9 +43,13 @@ struct FastArgs {
 #endif
 // measured exceptions for 64-bit words: the forward 2^11 tile (also the tile of N = 2^14, 2^15) is 9-12 % faster at 51 registers,
 // the 2^10 tile 3-5 % faster at 85
+#ifndef FAST_OCC64_R16
+#define FAST_OCC64_R16 768  // the radix-16 plan of the 2^12 tile (FAST_R16_64): 16 values + twiddles per thread
+#endif
 template <typename L, int LOGT, bool FWD>
 struct FastOcc {
-    static constexpr int value = L::BITS == 32 ? FAST_OCC32 : (LOGT == 11 && FWD ? 1280 : (LOGT == 10 ? 768 : FAST_OCC64));
+    static constexpr int value = L::BITS == 32 ? FAST_OCC32
+                                               : (FastGeom<L, LOGT>::RM == 4 ? FAST_OCC64_R16 : (LOGT == 11 && FWD ? 1280 : (LOGT == 10 ? 768 : FAST_OCC64)));
 };
 template <typename L, int LOGT, bool FWD, bool FINAL>
 __global__ void __launch_bounds__(FastGeom<L, LOGT>::NTHR, FastOcc<L, LOGT, FWD>::value / FastGeom<L, LOGT>::NTHR)
@@ -74,16 +78,16 @@ ntt_fast_tile_kernel(FastArgs<L> a) {
             __syncthreads();
         }
         if (G::NP3 > 2) {
-            if (active) fast_fwd_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, s, a.s0, k, ((a.pre_red >> 2) & 1u) != 0, tid);
+            if (active) fast_fwd_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + G::RM : G::R1)>(d, s, a.s0, k, ((a.pre_red >> 2) & 1u) != 0, tid);
             __syncthreads();
         }
         static_assert(G::NP3 <= 3, "at most two middle passes");
-        if (active) fast_fwd_last<L, LOGT, G::TPP>(d, s, g, a.s0, k, ((a.pre_red >> G::NP3) & 1u) != 0, tid);
+        if (active) fast_fwd_last<L, LOGT, G::TPP, G::RM>(d, s, g, a.s0, k, ((a.pre_red >> G::NP3) & 1u) != 0, tid);
     } else {
-        if (active) fast_inv_first<L, LOGT, G::TPP>(d, gin, s, a.s0, k, tid);
+        if (active) fast_inv_first<L, LOGT, G::TPP, G::RM>(d, gin, s, a.s0, k, tid);
         __syncthreads();
         if (G::NP3 > 2) {
-            if (active) fast_inv_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, s, a.s0, k, tid);
+            if (active) fast_inv_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + G::RM : G::R1)>(d, s, a.s0, k, tid);
             __syncthreads();
         }
         if (G::NP3 > 1) {
@@ -172,7 +176,7 @@ ntt_fast_tile_tma_kernel(FastArgs<L> a, unsigned long long n_blocks) {
         if (FWD) {
             if (active) fast_fwd_first_any<L, LOGT>(d, stage, work, a.s0, k, (a.pre_red & 1u) != 0, tid);
         } else {
-            if (active) fast_inv_first<L, LOGT, G::TPP>(d, stage, work, a.s0, k, tid);
+            if (active) fast_inv_first<L, LOGT, G::TPP, G::RM>(d, stage, work, a.s0, k, tid);
         }
         __syncthreads();  // the staged block is consumed: the copy engine may refill the buffer
         if (blk + gridDim.x < n_blocks && threadIdx.x == 0) issue(blk + gridDim.x);
@@ -182,13 +186,13 @@ ntt_fast_tile_tma_kernel(FastArgs<L> a, unsigned long long n_blocks) {
                 __syncthreads();
             }
             if (G::NP3 > 2) {
-                if (active) fast_fwd_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, work, a.s0, k, ((a.pre_red >> 2) & 1u) != 0, tid);
+                if (active) fast_fwd_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + G::RM : G::R1)>(d, work, a.s0, k, ((a.pre_red >> 2) & 1u) != 0, tid);
                 __syncthreads();
             }
-            if (active) fast_fwd_last<L, LOGT, G::TPP>(d, work, g, a.s0, k, ((a.pre_red >> G::NP3) & 1u) != 0, tid);
+            if (active) fast_fwd_last<L, LOGT, G::TPP, G::RM>(d, work, g, a.s0, k, ((a.pre_red >> G::NP3) & 1u) != 0, tid);
         } else {
             if (G::NP3 > 2) {
-                if (active) fast_inv_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + 3 : G::R1)>(d, work, a.s0, k, tid);
+                if (active) fast_inv_mid_any<L, LOGT, (G::NP3 > 2 ? G::R1 + G::RM : G::R1)>(d, work, a.s0, k, tid);
                 __syncthreads();
             }
             if (G::NP3 > 1) {

@@ -328,9 +328,15 @@ HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restr
 #pragma unroll
     for (int i = 0; i < NE; ++i) o0[i] = o1[i] = Cx{0.0, 0.0};
     const uint32_t p0 = swz_cx(g << C::R3);
+#ifndef TFHE_P3K
+#define TFHE_P3K 4  // key rows of this many spectral positions are requested before the forward pass of each limb (mode 3, 16 384 PBS: 0 / 2 / 4 / 8 -> 341 / 339 / 326 / 341 ms)
+#endif
+    constexpr int NPK = TFHE_P3K < NE ? TFHE_P3K : NE;
 #pragma unroll 1
     for (uint32_t r = 0; r < C::NL; ++r) {
         const Cx* f = X + ((size_t)r << C::LG);
+        Cx kq[NPK > 0 ? 2 * NPK : 1];
+        if (NPK > 0) tfhe_fast_p3_keys<C, 0, NPK>(key, g, r, kq);
         Cx x[NE];
 #pragma unroll
         for (int i = 0; i < NE; ++i) x[i] = f[p0 ^ (uint32_t)i];  // swz_cx(i) = i for i < 8
@@ -341,6 +347,9 @@ HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restr
             if (NPRE > 0 && i < NPRE && r == 0) {
                 k0 = kpre[2 * i];
                 k1 = kpre[2 * i + 1];
+            } else if (NPK > 0 && i < NPK) {
+                k0 = kq[2 * i];
+                k1 = kq[2 * i + 1];
             } else {
                 k0 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 0) * G + g));
                 k1 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 1) * G + g));
