@@ -209,8 +209,33 @@ HD void fast_fwd_regs(const L& m, typename L::W* x, const TwPair<typename L::W>*
 template <typename L, int R, bool LAST, bool NC = true>
 HD void fast_inv_regs(const L& m, typename L::W* x, const TwPair<typename L::W>* __restrict__ itw, uint32_t tb,
                       TwPair<typename L::W> ninv, TwPair<typename L::W> wninv) {
-    // every stage is one flat loop over its 2^(R-1) butterflies (constant trip count: nvcc left the nested `low < h` form partly
-    // rolled for R = 4 inside the tile kernel, which put x[] in local memory); butterfly b of stage `stage`: top = b >> stage
+#pragma unroll
+    for (int u = R - 1; u >= 0; --u) {
+        const int h = 1 << (R - 1 - u);
+        const int stage = R - 1 - u;
+#pragma unroll
+        for (int top = 0; top < (1 << u); ++top) {
+            if (LAST && u == 0) {
+#pragma unroll
+                for (int low = 0; low < h; ++low) m.bf_inv_last(x[low], x[low + h], ninv, wninv, stage);
+            } else {
+                const TwPair<typename L::W> t = NC ? ld_tw(itw + ((tb << u) + top)) : itw[(tb << u) + top];
+#pragma unroll
+                for (int low = 0; low < h; ++low) {
+                    const int j = (top << (R - u)) | low;
+                    m.bf_inv(x[j], x[j + h], t, stage);
+                }
+            }
+        }
+    }
+}
+
+template <typename L, int R, bool LAST, bool NC = true>
+HD void fast_inv_regs_flat(const L& m, typename L::W* x, const TwPair<typename L::W>* __restrict__ itw, uint32_t tb,
+                      TwPair<typename L::W> ninv, TwPair<typename L::W> wninv) {
+    // fast_inv_regs with every stage as one flat loop over its 2^(R-1) butterflies (constant trip count: nvcc left the nested `low < h`
+    // form partly rolled for R = 4 inside the tile kernel, which put x[] in local memory); butterfly b of stage `stage`: top = b >> stage.
+    // Only the radix-16 tile plan (FAST_R16_64) uses it: the FHEW kernel measured 1 % slower with this form.
 #pragma unroll
     for (int stage = 0; stage < R; ++stage) {
         const int u = R - 1 - stage;
@@ -255,9 +280,9 @@ template <typename L, int R, bool LAST, bool NC = true>
 HD void fast_inv_regs2(const L& m, typename L::W* x, typename L::W* y, const TwPair<typename L::W>* __restrict__ itw, uint32_t tb,
                        TwPair<typename L::W> ninv, TwPair<typename L::W> wninv) {
 #pragma unroll
-    for (int stage = 0; stage < R; ++stage) {  // ascending trip variable: nvcc does not always unroll the descending form
-        const int u = R - 1 - stage;
-        const int h = 1 << stage;
+    for (int u = R - 1; u >= 0; --u) {
+        const int h = 1 << (R - 1 - u);
+        const int stage = R - 1 - u;
 #pragma unroll
         for (int top = 0; top < (1 << u); ++top) {
             if (LAST && u == 0) {
@@ -547,7 +572,10 @@ HD void fast_inv_first(const FastLimb<L>& d, const typename L::W* g, typename L:
         else
             ldg_vec8(g + (grp << RM), x);
         const uint32_t tb = (1u << (s0 + t0)) + (k << t0) + grp;
-        fast_inv_regs<L, RM, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
+        if (RM == 4)
+            fast_inv_regs_flat<L, RM, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
+        else
+            fast_inv_regs<L, RM, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
         x[0] = d.m.inv_pass_fix(x[0]);
         if (RM == 4) x[1] = d.m.inv_pass_fix(x[1]);  // the sum chain of a 4-stage pass reaches 32q on element 1 (see Lz64)
         if (RM == 4)
@@ -568,7 +596,10 @@ HD void fast_inv_mid(const FastLimb<L>& d, typename L::W* s, int s0, uint32_t k,
 #pragma unroll
         for (int j = 0; j < NE; ++j) x[j] = s[P0 ^ swz2<W>((uint32_t)j << LL)];
         const uint32_t tb = (1u << (s0 + t0)) + (k << t0) + hi;
-        fast_inv_regs<L, RM, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
+        if (RM == 4)
+            fast_inv_regs_flat<L, RM, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
+        else
+            fast_inv_regs<L, RM, false>(d.m, x, d.itw, tb, d.ninv, d.wninv);
         x[0] = d.m.inv_pass_fix(x[0]);
         if (RM == 4) x[1] = d.m.inv_pass_fix(x[1]);
 #pragma unroll
