@@ -308,14 +308,21 @@ HD void tfhe_fast_mid(const TfheFastDev& P, Cx* __restrict__ X, uint32_t unit) {
 #pragma unroll
     for (int i = 0; i < NE; ++i) f[p0 ^ swz_cx((uint32_t)i << L)] = x[i];
 }
+// key rows: every ciphertext reads the same rows at step i, and the CTAs of one SM walk the steps almost in lockstep, so with
+// TFHE_KEY_L1 = 1 the rows go through L1 (one CTA's miss could be the others' hit); 0: L2 only (ld.global.cg).  Measured: 326.0 vs
+// 327.3 ms per 16 384 PBS - 64 KiB of rows per step do not survive in the ~70 KiB of L1 left beside the twiddle tables.
+#ifndef TFHE_KEY_L1
+#define TFHE_KEY_L1 0
+#endif
+HD Cx ld_key(const Cx* p) { return TFHE_KEY_L1 ? ld_cx(p) : ld_cx_stream(p); }
 // ---- P3: last forward pass of every limb, multiply-accumulate with the key, first inverse pass ----------------------------------------
 // key rows of limb r at the unit's spectral positions I0 .. I1-1: k[2 i + o]
 template <typename C, int I0 = 0, int I1 = (1 << C::R3)>
 HD void tfhe_fast_p3_keys(const Cx* __restrict__ key, uint32_t g, uint32_t r, Cx* k) {
 #pragma unroll
     for (int i = I0; i < I1; ++i) {
-        k[2 * i] = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 0) * C::U3 + g));
-        k[2 * i + 1] = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 1) * C::U3 + g));
+        k[2 * i] = ld_key(key + ((size_t)((i * C::NL + r) * 2 + 0) * C::U3 + g));
+        k[2 * i + 1] = ld_key(key + ((size_t)((i * C::NL + r) * 2 + 1) * C::U3 + g));
     }
 }
 // NPRE > 0: kpre holds the rows of limb 0 at the unit's first NPRE spectral positions, requested by the kernel before P2 so that
@@ -351,8 +358,8 @@ HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restr
                 k0 = kq[2 * i];
                 k1 = kq[2 * i + 1];
             } else {
-                k0 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 0) * G + g));
-                k1 = ld_cx_stream(key + ((size_t)((i * C::NL + r) * 2 + 1) * G + g));
+                k0 = ld_key(key + ((size_t)((i * C::NL + r) * 2 + 0) * G + g));
+                k1 = ld_key(key + ((size_t)((i * C::NL + r) * 2 + 1) * G + g));
             }
             o0[i] = Cx{f64_fma_rn(-x[i].im, k0.im, f64_fma_rn(x[i].re, k0.re, o0[i].re)), f64_fma_rn(x[i].im, k0.re, f64_fma_rn(x[i].re, k0.im, o0[i].im))};
             o1[i] = Cx{f64_fma_rn(-x[i].im, k1.im, f64_fma_rn(x[i].re, k1.re, o1[i].re)), f64_fma_rn(x[i].im, k1.re, f64_fma_rn(x[i].re, k1.im, o1[i].im))};
