@@ -313,7 +313,12 @@ static fhe_status launch_fast_tile(fhe_ctx* ctx, FastArgs<L>& a) {
             tattr_done.fetch_or(dev_bit, std::memory_order_relaxed);
         }
         if (occ >= 1) {
-            const unsigned tgrid = (unsigned)std::min<unsigned long long>(grid, (unsigned long long)ctx->sm_count * occ);
+            // blocks per persistent CTA the grid is sized for: with one block each (a batch that fits one wave) nothing is pipelined
+            static const int depth = [] {
+                const char* e = getenv("FHE_B200_NTT_TMA_DEPTH");
+                return e ? std::max(1, atoi(e)) : 1;
+            }();
+            const unsigned tgrid = (unsigned)std::min<unsigned long long>((grid + depth - 1) / depth, (unsigned long long)ctx->sm_count * occ);
             tk<<<tgrid, G::NTHR, tsmem, ctx->stream>>>(a, grid);
             return after_launch(ctx, FWD ? "ntt_fast_tile_tma_kernel<fwd>" : "ntt_fast_tile_tma_kernel<inv>");
         }
