@@ -772,12 +772,45 @@ fhe_status fhe_ckks_mul_relin_rescale_batch_host(fhe_ctx* ctx, fhe_ckks_ctx* ck,
     FHE_CHECK(ensure_stage_d(ctx, 0, in_bytes, &d0));
     FHE_CHECK(ensure_stage_d(ctx, 1, in_bytes, &d1));
     FHE_CHECK(ensure_stage_d(ctx, 2, out_bytes, &dout));
-    FHE_CUDA(ctx, cudaMemcpyAsync(d0, ct0, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    FHE_CUDA(ctx, cudaMemcpyAsync(d1, ct1, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    FHE_CHECK(fhe_ckks_mul_relin_rescale_batch(ctx, ck, rlk, level, count, (const uint64_t*)d0, (const uint64_t*)d1, (uint64_t*)dout));
-    FHE_CUDA(ctx, cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return FHE_OK;
+    // Pipelined over chunks: the H2D copies of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of chunk c (two copy
+    // streams + events; PCIe is full duplex).  The operation moves 4 level + 2 (level - 1) limbs per pair over the bus for ~0.1 ms
+    // of kernels per pair, so the host path is bound by the H2D direction once the three stages overlap.
+    size_t nchunk = count >= 32 ? 8 : (count >= 8 ? 4 : (count >= 2 ? 2 : 1));
+    if (const char* e = getenv("FHE_B200_HOST_CHUNKS")) nchunk = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), count));  // tuning knob
+    const size_t cs = (count + nchunk - 1) / nchunk, in_pair = 2 * level * n, out_pair = 2 * (level - 1) * n;
+    if (!ctx->copy_in) FHE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    if (!ctx->copy_out) FHE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> ev(2 * nchunk + 1);  // per chunk: inputs landed, kernels done; last: fence
+    const size_t fence = 2 * nchunk;
+    for (auto& e : ev) FHE_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    fhe_status st = FHE_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && st == FHE_OK) st = fail(ctx, FHE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaEventRecord(ev[fence], ctx->stream), "event");  // the staging buffers are free once earlier work on the stream is done
+    cu(cudaStreamWaitEvent(ctx->copy_in, ev[fence], 0), "wait");
+    for (size_t c = 0; c < nchunk && st == FHE_OK; ++c) {
+        const size_t off = c * cs;
+        if (off >= count) break;
+        const size_t cnt = std::min(cs, count - off);
+        uint64_t *c0 = (uint64_t*)d0 + off * in_pair, *c1 = (uint64_t*)d1 + off * in_pair, *co = (uint64_t*)dout + off * out_pair;
+        cu(cudaMemcpyAsync(c0, ct0 + off * in_pair, cnt * in_pair * 8, cudaMemcpyHostToDevice, ctx->copy_in), "H2D");
+        cu(cudaMemcpyAsync(c1, ct1 + off * in_pair, cnt * in_pair * 8, cudaMemcpyHostToDevice, ctx->copy_in), "H2D");
+        cu(cudaEventRecord(ev[2 * c], ctx->copy_in), "event");
+        cu(cudaStreamWaitEvent(ctx->stream, ev[2 * c], 0), "wait");
+        if (st == FHE_OK) st = fhe_ckks_mul_relin_rescale_batch(ctx, ck, rlk, level, cnt, c0, c1, co);
+        cu(cudaEventRecord(ev[2 * c + 1], ctx->stream), "event");
+        cu(cudaStreamWaitEvent(ctx->copy_out, ev[2 * c + 1], 0), "wait");
+        cu(cudaMemcpyAsync(out + off * out_pair, co, cnt * out_pair * 8, cudaMemcpyDeviceToHost, ctx->copy_out), "D2H");
+    }
+    cu(cudaEventRecord(ev[fence], ctx->copy_out), "event");
+    cu(cudaStreamWaitEvent(ctx->stream, ev[fence], 0), "wait");
+    if (st == FHE_OK)
+        cu(cudaStreamSynchronize(ctx->stream), "sync");
+    else
+        cudaDeviceSynchronize();
+    for (auto& e : ev) cudaEventDestroy(e);
+    return st;
 }
 
 fhe_status fhe_ckks_key_switch(fhe_ctx* ctx, fhe_ckks_ctx* ck, const fhe_ckks_ksk* ksk, int64_t t, size_t level, size_t count,

@@ -159,11 +159,50 @@ static fhe_status ntt_host(fhe_ctx* ctx, uint64_t q, uint64_t* a, size_t n, size
     size_t bytes = n * batch * sizeof(uint64_t);
     void* d;
     FHE_CHECK(ensure_scratch(ctx, bytes, &d));
-    FHE_CUDA(ctx, cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    FHE_CHECK(launch_ntt_u64(ctx, q, lg, batch, (uint64_t*)d, fwd));
-    FHE_CUDA(ctx, cudaMemcpyAsync(a, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return FHE_OK;
+    // Pipelined over chunks of polynomials (two copy streams + events): the H2D copy of chunk c+1 and the D2H copy of chunk c-1
+    // overlap the transform of chunk c, so a large batch moves at the full-duplex PCIe rate instead of one direction at a time.
+    size_t nchunk = (bytes >= ((size_t)32 << 20) && batch >= 8) ? 8 : 1;
+    if (const char* e = getenv("FHE_B200_HOST_CHUNKS")) nchunk = std::max<size_t>(1, std::min<size_t>((size_t)atoi(e), batch));  // tuning knob
+    if (nchunk == 1) {
+        FHE_CUDA(ctx, cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        FHE_CHECK(launch_ntt_u64(ctx, q, lg, batch, (uint64_t*)d, fwd));
+        FHE_CUDA(ctx, cudaMemcpyAsync(a, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        FHE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return FHE_OK;
+    }
+    const size_t cs = (batch + nchunk - 1) / nchunk;
+    if (!ctx->copy_in) FHE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    if (!ctx->copy_out) FHE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> ev(2 * nchunk + 1);
+    const size_t fence = 2 * nchunk;
+    for (auto& e : ev) FHE_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    fhe_status st = FHE_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && st == FHE_OK) st = fail(ctx, FHE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    cu(cudaEventRecord(ev[fence], ctx->stream), "event");  // the scratch buffer is free once earlier work on the stream is done
+    cu(cudaStreamWaitEvent(ctx->copy_in, ev[fence], 0), "wait");
+    for (size_t c = 0; c < nchunk && st == FHE_OK; ++c) {
+        const size_t off = c * cs;
+        if (off >= batch) break;
+        const size_t cnt = std::min(cs, batch - off);
+        uint64_t* dc = (uint64_t*)d + off * n;
+        cu(cudaMemcpyAsync(dc, a + off * n, cnt * n * 8, cudaMemcpyHostToDevice, ctx->copy_in), "H2D");
+        cu(cudaEventRecord(ev[2 * c], ctx->copy_in), "event");
+        cu(cudaStreamWaitEvent(ctx->stream, ev[2 * c], 0), "wait");
+        if (st == FHE_OK) st = launch_ntt_u64(ctx, q, lg, cnt, dc, fwd);
+        cu(cudaEventRecord(ev[2 * c + 1], ctx->stream), "event");
+        cu(cudaStreamWaitEvent(ctx->copy_out, ev[2 * c + 1], 0), "wait");
+        cu(cudaMemcpyAsync(a + off * n, dc, cnt * n * 8, cudaMemcpyDeviceToHost, ctx->copy_out), "D2H");
+    }
+    cu(cudaEventRecord(ev[fence], ctx->copy_out), "event");
+    cu(cudaStreamWaitEvent(ctx->stream, ev[fence], 0), "wait");
+    if (st == FHE_OK)
+        cu(cudaStreamSynchronize(ctx->stream), "sync");
+    else
+        cudaDeviceSynchronize();
+    for (auto& e : ev) cudaEventDestroy(e);
+    return st;
 }
 
 }  // namespace fhe

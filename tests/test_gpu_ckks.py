@@ -86,6 +86,30 @@ def test_mul_relin_rescale_matches_oracle(pkg, ctx, orc, ckks_setup):
         assert (K.decrypt(got[0]) == K.decrypt(ref[0])).all()
 
 
+def test_host_paths_pipelined_over_ragged_chunks(pkg, ctx, orc, ckks_setup, monkeypatch):
+    """The host-slice entry points overlap H2D / kernels / D2H over chunks of the batch (two copy streams + events): any chunk
+    count, including ones that do not divide the batch, gives the words of the one-chunk path (Ckks::mul and the NTT)."""
+    from learn_fhe_b200 import ckks, util
+    K, P, rlk = ckks_setup
+    level, count = P.big_l, 7
+    ct0 = np.stack([K.encrypt(_small_pt(300 + i, K.n), level, 400 + i) for i in range(count)])
+    ct1 = np.stack([K.encrypt(_small_pt(500 + i, K.n), level, 600 + i) for i in range(count)])
+    ref = K.mul(ct0, ct1, threads=4)
+    q = K.qs[0]
+    a = np.stack([orc.residues(900 + i, K.n, q) for i in range(11)])
+    want = a.copy()
+    monkeypatch.setenv("FHE_B200_HOST_CHUNKS", "1")
+    util.nega_cyclic_ntt_in_place(ctx, q, want)
+    for chunks in ("1", "2", "3", "7", "64"):
+        monkeypatch.setenv("FHE_B200_HOST_CHUNKS", chunks)
+        assert (ckks.Ckks.mul(P, rlk, ct0, ct1) == ref).all(), chunks
+        x = a.copy()
+        util.nega_cyclic_ntt_in_place(ctx, q, x)
+        assert (x == want).all(), chunks
+        util.nega_cyclic_intt_in_place(ctx, q, x)
+        assert (x == a).all(), chunks
+
+
 def test_mul_chain_all_levels(pkg, ctx, orc, ckks_setup):
     """ckks.rs:378-398: L-1 chained multiplications, every intermediate ciphertext bit-identical."""
     from learn_fhe_b200 import ckks
