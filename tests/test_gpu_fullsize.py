@@ -99,6 +99,17 @@ def test_tfhe_16384_programmable_bootstraps(pkg, ctx, orc):
     assert (rev[::-1] == got).all()
     spot = [0, 8191, count - 1]
     assert (got[spot] == K.bootstrap(v, cts[spot], threads=3)).all()
+    # the fused bounded-error modes (3 is the bench headline): every one of the 16384 outputs decrypts to the table, its phase stays
+    # within 2^54 of the bit-identical mode's (decoding margin 2^58), and an output does not depend on its position in the batch
+    ph_exact = K.decrypt(got)[1]
+    for mode in (2, 3):
+        bk.set_mode(mode)
+        fused = tfhe.Bootstrapping.bootstrap(bk, lut, cts)
+        m, ph = K.decrypt(fused)
+        assert (m == table[msgs.astype(np.int64)]).all(), mode
+        assert np.abs((ph - ph_exact).astype(np.int64)).max() < 2 ** 54, mode
+        rev = tfhe.Bootstrapping.bootstrap(bk, lut, np.ascontiguousarray(cts[::-1]))
+        assert (rev[::-1] == fused).all(), mode
     bk.free()
 
 
