@@ -169,6 +169,9 @@ static constexpr int TFHE_FAST_THREADS = 128;
 #ifndef TFHE_PRE
 #define TFHE_PRE 0
 #endif
+#ifndef TFHE_KEY_SMEM_DEFAULT
+#define TFHE_KEY_SMEM_DEFAULT 0
+#endif
 // key polynomial (step, r, o) [N] torus words -> forward spectrum in the coalesced P3 layout; one CTA per polynomial
 template <typename C>
 __global__ void __launch_bounds__(256) tfhe_fast_key_kernel(TfheFastDev P, unsigned long long polys, const uint64_t* __restrict__ src,
@@ -248,6 +251,78 @@ __global__ void __launch_bounds__(TFHE_FAST_THREADS, TFHE_FAST_MINB) tfhe_blind_
         if (threadIdx.x == 0) o[N] = acc_to_t64(acc[N]);
         __syncthreads();
     }
+}
+
+// Variant of the fused kernel (32-bit accumulator words) whose key rows travel global -> shared memory by cp.async one whole CMUX step
+// ahead: every thread copies exactly the 16-byte words its own P3 unit will read (no cross-thread hand-over, so cp.async.wait_group is
+// the only synchronisation), P3 then reads them with plain shared loads and never waits on L2.  Shared memory: X | acc | one step of
+// key rows; the mod-switched exponents are recomputed from the ciphertext (one broadcast load per step, fetched a step ahead).
+DEV void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <typename C>
+__global__ void __launch_bounds__(TFHE_FAST_THREADS, 2) tfhe_blind_rotate_fast_ks_kernel(TfheFastDev P, const uint64_t* __restrict__ lut,
+                                                                                    const uint64_t* __restrict__ ct_in, unsigned long long count,
+                                                                                    uint64_t* __restrict__ out) {
+    typedef uint32_t A;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr uint32_t N = C::N;
+    constexpr uint32_t ROWS = (uint32_t)(C::KEY_STRIDE / C::U3);  // rows of U3 words per step
+    Cx* X = reinterpret_cast<Cx*>(smem_raw);
+    Cx* kbuf = X + (size_t)C::NL * C::M;
+    A* acc = reinterpret_cast<A*>(kbuf + C::KEY_STRIDE);
+    const uint32_t rb = 64 - (C::LG + 2);
+    const uint32_t t = threadIdx.x;
+    auto run = [&](uint32_t units, auto f) {
+        for (uint32_t u = t; u < units; u += TFHE_FAST_THREADS) f(u);
+        __syncthreads();
+    };
+    auto stage = [&](uint32_t step) {  // this thread's words of every row of `step` (units t, t + THREADS, ... of P3)
+        const Cx* src = P.key + (size_t)step * C::KEY_STRIDE;
+        for (uint32_t g = t; g < C::U3; g += TFHE_FAST_THREADS)
+#pragma unroll 8
+            for (uint32_t row = 0; row < ROWS; ++row) cp_async16(kbuf + (size_t)row * C::U3 + g, src + (size_t)row * C::U3 + g);
+        cp_async_commit();
+    };
+    for (unsigned long long ct = blockIdx.x; ct < count; ct += gridDim.x) {
+        const uint64_t* src = ct_in + ct * (P.n_lwe + 1);
+        stage(0);
+        const uint32_t bt = (uint32_t)t64_rounding_shr_dev(src[P.n_lwe], rb) & (2 * N - 1);
+        const uint32_t e0 = (2 * N - bt) & (2 * N - 1);  // rotate(-b~)
+        for (uint32_t c = t; c < N; c += TFHE_FAST_THREADS) {
+            acc[c] = 0;
+            acc[N + c] = t64_to_acc<A>(t64_rot_coef(lut, N, e0, c));
+        }
+        uint64_t a_next = src[0];
+        __syncthreads();
+        for (uint32_t i = 0; i < P.n_lwe; ++i) {
+            const uint32_t e = (uint32_t)t64_rounding_shr_dev(a_next, rb) & (2 * N - 1);
+            if (i + 1 < P.n_lwe) a_next = src[i + 1];
+            if (e != 0) {  // rotate(0) - acc = 0: the external product of zero is exactly zero
+                run(C::U1, [&](uint32_t u) { tfhe_fast_p1<C>(P, acc, X, u, e); });
+                run(C::U2, [&](uint32_t u) { tfhe_fast_mid<C, true>(P, X, u); });
+                cp_async_wait_all();  // own words only: no barrier needed
+                run(C::U3, [&](uint32_t u) { tfhe_fast_p3<C, 0, true>(P, X, kbuf, u, nullptr); });
+                if (i + 1 < P.n_lwe) stage(i + 1);
+                run(C::U4, [&](uint32_t u) { tfhe_fast_mid<C, false>(P, X, u); });
+                run(C::U1, [&](uint32_t u) { tfhe_fast_p5<C>(P, acc, X, u); });
+            } else {
+                cp_async_wait_all();
+                if (i + 1 < P.n_lwe) stage(i + 1);
+            }
+        }
+        cp_async_wait_all();
+        uint64_t* o = out + ct * ((unsigned long long)N + 1);
+        for (uint32_t x = t; x < N; x += TFHE_FAST_THREADS) o[x] = acc_to_t64(x == 0 ? acc[0] : (A)(0 - acc[N - x]));
+        if (t == 0) o[N] = acc_to_t64(acc[N]);
+        __syncthreads();
+    }
+}
+template <typename C>
+static size_t tfhe_fast_ks_smem_bytes() {
+    return ((size_t)C::NL * C::M + C::KEY_STRIDE) * sizeof(Cx) + (size_t)2 * C::N * sizeof(uint32_t);
 }
 
 // Tggsw::external_product(brk[idx[c]], glwe_c) (in1 == nullptr), or Tggsw::cmux(brk[idx[c]], ct0 = in, ct1 = in1) =
@@ -394,7 +469,14 @@ static fhe_status run_blind_rotate(fhe_ctx* ctx, const fhe_tfhe_key* key, const 
                 kern<<<grid, TFHE_FAST_THREADS, smem, ctx->stream>>>(key->F, d_lut, d_in, count, d_out);
                 st = after_launch(ctx, "tfhe_blind_rotate_fast_kernel");
             };
-            if (key->mode == 3)
+            // mode 3 with the key rows staged through shared memory when two such CTAs fit on an SM (FHE_B200_TFHE_KEY_SMEM=0 disables)
+            static const bool ks_on = [] {
+                const char* e = getenv("FHE_B200_TFHE_KEY_SMEM");
+                return e ? atoi(e) != 0 : TFHE_KEY_SMEM_DEFAULT != 0;
+            }();
+            if (key->mode == 3 && ks_on && tfhe_fast_ks_smem_bytes<C>() <= (size_t)112 * 1024)
+                launch(tfhe_blind_rotate_fast_ks_kernel<C>, tfhe_fast_ks_smem_bytes<C>());
+            else if (key->mode == 3)
                 launch(tfhe_blind_rotate_fast_kernel<C, uint32_t>, tfhe_fast_smem_bytes<C, uint32_t>(key->F.n_lwe));
             else
                 launch(tfhe_blind_rotate_fast_kernel<C, uint64_t>, tfhe_fast_smem_bytes<C, uint64_t>(key->F.n_lwe));

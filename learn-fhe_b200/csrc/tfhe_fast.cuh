@@ -327,7 +327,8 @@ HD void tfhe_fast_p3_keys(const Cx* __restrict__ key, uint32_t g, uint32_t r, Cx
 }
 // NPRE > 0: kpre holds the rows of limb 0 at the unit's first NPRE spectral positions, requested by the kernel before P2 so that
 // their L2 latency hides behind that pass (r02 ncu: half of P3's stall samples are long_scoreboard on these loads)
-template <typename C, int NPRE = 0>
+// KS: `key` points at this step's rows already staged in shared memory (same [position][row][output][unit] order): plain loads
+template <typename C, int NPRE = 0, bool KS = false>
 HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restrict__ key, uint32_t g, const Cx* kpre) {
     constexpr int NE = 1 << C::R3;
     constexpr uint32_t G = C::U3;
@@ -338,7 +339,7 @@ HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restr
 #ifndef TFHE_P3K
 #define TFHE_P3K 4  // key rows of this many spectral positions are requested before the forward pass of each limb (mode 3, 16 384 PBS: 0 / 2 / 4 / 8 -> 341 / 339 / 326 / 341 ms)
 #endif
-    constexpr int NPK = TFHE_P3K < NE ? TFHE_P3K : NE;
+    constexpr int NPK = KS ? 0 : (TFHE_P3K < NE ? TFHE_P3K : NE);
 #pragma unroll 1
     for (uint32_t r = 0; r < C::NL; ++r) {
         const Cx* f = X + ((size_t)r << C::LG);
@@ -357,6 +358,9 @@ HD void tfhe_fast_p3(const TfheFastDev& P, Cx* __restrict__ X, const Cx* __restr
             } else if (NPK > 0 && i < NPK) {
                 k0 = kq[2 * i];
                 k1 = kq[2 * i + 1];
+            } else if (KS) {
+                k0 = key[(size_t)((i * C::NL + r) * 2 + 0) * G + g];
+                k1 = key[(size_t)((i * C::NL + r) * 2 + 1) * G + g];
             } else {
                 k0 = ld_key(key + ((size_t)((i * C::NL + r) * 2 + 0) * G + g));
                 k1 = ld_key(key + ((size_t)((i * C::NL + r) * 2 + 1) * G + g));
