@@ -484,6 +484,7 @@ fhe_status fhew_key_build(fhe_ctx* ctx, const fhe_fhew_param* pp, const int64_t*
         W.small_digits = P.small_digits;
         W.lazy = q < (1ull << 56) ? 1u : 0u;
         W.lz = make_lz64(q);
+        W.c64 = (uint64_t)((((u128_t)1) << 64) % q);
         W.tw = (const TwPair<uint64_t>*)t->d_fwd;
         W.itw = (const TwPair<uint64_t>*)t->d_inv;
         W.ninv = make_twpair<uint64_t>(ninv, q);

@@ -166,6 +166,7 @@ struct FhewDevT {
     // the forward direction - at most (1 + 4 log N) q < 128 q -, one Barrett per pass on the sum chain in the inverse)
     uint32_t lazy;
     Lz64 lz;
+    W c64;  // 2^64 mod q (64-bit moduli: folds the high word of the exact 128-bit MAC sums)
 };
 typedef FhewDevT<Mod32> FhewDev;
 template <int R>
@@ -333,11 +334,36 @@ HD void fhew_phase_mac(const FhewDevT<M>& P, typename M::W* smem, const KeyPair<
             }
             dig[si] = P.m.reduce64(sa);
             dig[n + si] = P.m.reduce64(sb);
+        } else if (P.lazy && P.m.s >= 33) {
+            // 2^32 <= q < 2^56 and rows <= 32: the sum of rows products is < 2^117, accumulated exactly in 128 bits (four wide products per
+            // term instead of a full Barrett product) and reduced once: hi 2^64 + lo = hi (2^64 mod q) + lo (mod q).  The canonical
+            // result equals the per-term canonical Zq arithmetic of the reference.  Key rows are fetched two ahead of their use.
+            unsigned __int128 sa = 0, sb = 0;
+            KeyPair<W> k0 = key[i], k1 = rows > 1 ? key[(size_t)n + i] : k0;
+            for (uint32_t k = 0; k < rows; ++k) {
+                const KeyPair<W> kv = k0;
+                k0 = k1;
+                if (k + 2 < rows) k1 = key[(size_t)(k + 2) * n + i];
+                const W dg = P.lz.canon(dig[(size_t)k * n + si]);
+                sa += (unsigned __int128)kv.x * dg;
+                sb += (unsigned __int128)kv.y * dg;
+            }
+            auto fold = [&](unsigned __int128 v) {
+                const W hi = (W)(v >> 64), lo = (W)v;  // hi < 2^53, lo < 2^64: both inside the Barrett input range 2^(2s), s >= 33
+                U128 h, l;
+                h.lo = hi;
+                h.hi = 0;
+                l.lo = lo;
+                l.hi = 0;
+                return P.m.add(P.m.mul(P.m.reduce128(h), P.c64), P.m.reduce128(l));
+            };
+            dig[si] = fold(sa);
+            dig[n + si] = fold(sb);
         } else {  // 64-bit modulus: every product is reduced (rows * q^2 does not fit the 128-bit Barrett's input range)
             W sa = 0, sb = 0;
             for (uint32_t k = 0; k < rows; ++k) {
                 const KeyPair<W> kv = key[(size_t)k * n + i];
-                const W dg = P.lazy ? P.lz.canon(dig[(size_t)k * n + si]) : P.m.canon4(dig[(size_t)k * n + si]);
+                const W dg = P.m.canon4(dig[(size_t)k * n + si]);
                 sa = P.m.add(sa, P.m.mul(kv.x, dg));
                 sb = P.m.add(sb, P.m.mul(kv.y, dg));
             }

@@ -26,6 +26,7 @@ for w in $WHAT; do
         ntt) TRAFFIC= run ntt ntt_fast 12 python tools/prof_cmd.py ntt ;;
         tfhe) TRAFFIC=tfhe_blind_rotate_fast_kernel=16384 KEEP=1 run tfhe tfhe_blind_rotate_fast 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 3 ;;
         tfhe_exact) TRAFFIC=tfhe_blind_rotate_kernel=16384 KEEP=1 run tfhe_exact 'tfhe_blind_rotate_kernel' 1 python tools/tfhe_bench.py tfhe --batch 16384 --modes 0 ;;
+        fhew64) TRAFFIC= KEEP=1 run fhew64 'fhew_blind_rotate_kernel' 1 python tools/fhew_wide_bench.py --batch 296 ;;
         bf) TRAFFIC= KEEP=1 run bf bf_rate 8 python tools/tfhe_bench.py bf ;;
         ckks) TRAFFIC= run ckks 'rns_|ckks_' 8 python tools/tfhe_bench.py ckks --count 128 ;;
         traffic)  # DRAM bytes of whole multi-kernel operations (one metric pass): Ckks::mul on 512 pairs, NTT fwd 4096 x 2^16 u64
