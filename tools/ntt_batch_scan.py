@@ -1,5 +1,7 @@
+#!/usr/bin/env python
+"""NTT throughput at N = 2^10..2^12 for 4096 / 16384 / 65536 polynomials (how much of the configured batch is launch, ramp and tail)."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, _pkg
 pkg = _pkg.load_package()
 import bench

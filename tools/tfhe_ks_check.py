@@ -1,5 +1,7 @@
+#!/usr/bin/env python
+"""Checksum of a 2000-ciphertext TFHE mode-3 batch on synthetic keys: compares kernel variants (FHE_B200_TFHE_KEY_SMEM=0/1) bit for bit."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, _pkg
 pkg = _pkg.load_package()
 from learn_fhe_b200 import tfhe
