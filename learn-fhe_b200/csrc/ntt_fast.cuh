@@ -26,7 +26,7 @@
 #define FAST_HALF32 0
 #endif
 #ifndef FAST_MIN_NTHR
-#define FAST_MIN_NTHR 128  // smallest CTA: tiles covered by fewer threads are batched PB per CTA (128 measured 5-11 % faster than 256 at N = 2^10, 2^11)
+#define FAST_MIN_NTHR 32  // smallest CTA: tiles covered by fewer threads are batched PB per CTA.  128 measured 5-11 % faster than 256 at N = 2^10, 2^11; 32 (one tile per CTA for the 32-thread u32 2^10 tile) another 6-13 % at 4096 x 2^10 u32 (2.01 -> 2.27 TB/s) and +8 % at 65 536 polynomials, neutral elsewhere
 #endif
 #include "modarith.cuh"
 #include "ntt_core.cuh"
